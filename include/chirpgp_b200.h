@@ -1,0 +1,116 @@
+/*
+ * chirpgp_b200.h -- C ABI of the B200-native chirpgp filtering/smoothing hot path.
+ *
+ * Drop-in boundary: each entry point replaces one function of the reference's
+ * chirpgp/filters_smoothers.py (cited per function, paths relative to /root/reference/chirpgp/) for a whole
+ * batch of independent chirps (what the reference obtains with jax.vmap, tetralith/jobs/crlb_ekf.py:68-72).
+ * Plain pointers and sizes only: no torch / JAX types.  Bound by
+ *   - chirpgp_b200/_native.py (ctypes; this image),
+ *   - an XLA-FFI shim (chirpgp_b200/csrc/xla_ffi_shim.cc; needs jaxlib headers).
+ *
+ * Conventions
+ *   - float64 everywhere, row-major, batch-major: ys [B,T], mfs [B,T,d], Pfs [B,T,d,d], nell [B,T].
+ *   - All data pointers are DEVICE pointers unless the function name ends in _host.
+ *   - The caller owns every buffer.  The library allocates nothing persistent; smoothers that need scratch
+ *     take a caller-provided workspace whose size cgp_workspace_bytes() reports.
+ *   - Asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, no mutable global state.
+ *   - Return value: 0 on success, a negative CGP_ERR_* for argument errors, a positive cudaError_t for CUDA
+ *     launch errors.  Never throws, never exits.  Numerical failure (non-PD covariance) is reported in-band
+ *     as NaNs, matching JAX semantics.
+ *   - T >= 1.  A smoother with T == 1 copies the filter result (filters_smoothers.py:140-142, :218).
+ */
+#ifndef CHIRPGP_B200_H
+#define CHIRPGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGP_ABI_VERSION 1
+
+/* model ids (chirpgp_b200/models.py uses the same numbers) */
+enum {
+    CGP_MODEL_LINEAR_DISC = 0, /* (u,dt)->(F u, Sigma): consts [F d*d | Sigma d*d]           (kf/rts, test lambdas) */
+    CGP_MODEL_LCD         = 1, /* chirp/harmonic/La Scala LCD, models.py:295-309,:369-384,:423-432:
+                                  consts [e, F00,F01,F10,F11, q, S00,S01,S11, freq_scale]  (CGP_NC_LCD)          */
+    CGP_MODEL_LINEAR_SDE  = 2, /* u -> A u: consts [A d*d]                                                        */
+    CGP_MODEL_SDE         = 3  /* chirp/harmonic drift, models.py:104-110,:164-168: consts
+                                  [lam, gamma^2, 2 gamma, freq_scale]                       (CGP_NC_SDE)          */
+};
+#define CGP_NC_LCD 10
+#define CGP_NC_SDE 4
+
+/* sigma-point table layout hints (results do not depend on them; they select a kernel specialisation) */
+enum {
+    CGP_SIGMA_GENERIC = 0,
+    CGP_SIGMA_GAUSS_HERMITE = 1 /* table is bit-identical to quadratures.py:157-196 with `gh_order` nodes/dim */
+};
+
+enum {
+    CGP_ERR_BAD_ARG = -1,      /* null pointer, B/T < 1, stride mismatch                       */
+    CGP_ERR_UNSUPPORTED = -2,  /* (model, d, n_sigma) combination has no compiled kernel       */
+    CGP_ERR_WORKSPACE = -3     /* workspace missing or too small                               */
+};
+
+/* One batch of independent filtering problems.  Problem p (0 <= p < B) reads
+ *   ys     + (p / ys_repeat) * T          (ys_repeat >= 1: consecutive problems sharing one measurement row,
+ *                                          used for hyper-parameter candidate grids)
+ *   consts + p * consts_stride            (stride 0 = shared by all problems), likewise m0, P0.            */
+typedef struct CgpProblem {
+    int64_t B;                 /* number of problems (chirps x candidates)                     */
+    int64_t T;                 /* samples per chirp                                            */
+    int32_t model;             /* CGP_MODEL_*                                                  */
+    int32_t d;                 /* state dimension                                              */
+    int32_t num_harmonics;     /* LCD / SDE models: d == 2 * num_harmonics + 2                 */
+    int32_t n_sigma;           /* sigma points (0 for kf/ekf/cd_ekf and their smoothers)       */
+    int32_t sigma_kind;        /* CGP_SIGMA_*                                                  */
+    int32_t gh_order;          /* nodes per dimension when sigma_kind == GAUSS_HERMITE         */
+    int64_t ys_repeat;         /* >= 1                                                         */
+    const double *consts;  int64_t consts_stride;   /* model constants, see model ids          */
+    const double *m0;      int64_t m0_stride;       /* [B|1, d]                                */
+    const double *P0;      int64_t P0_stride;       /* [B|1, d, d] (symmetric)                 */
+    const double *H;           /* [d] measurement row (1-D measurement, filters_smoothers.py:57-58) */
+    const double *Qc;      int64_t Qc_stride;       /* [B|1, d, d] = b b^T, CD variants only   */
+    const double *sig_w;       /* [n_sigma]                                                    */
+    const double *sig_xi;      /* [n_sigma, d]                                                 */
+    double Xi;                 /* measurement variance                                         */
+    double dt;                 /* sampling interval (positive; smoothers negate internally)    */
+} CgpProblem;
+
+int cgp_abi_version(void);
+
+/* ---- filters: ys [.,T] -> mfs [B,T,d], Pfs [B,T,d,d], nell [B,T] (cumulative -log lik., :180-184).
+ * mfs/Pfs may both be NULL (nll-only: nothing but nell is stored);  nell may be NULL.
+ * If nell_last_only != 0, nell is [B] and receives only the final cumulative value (the MLE objective,
+ * demos/ekfs_mle.py:42-45).                                                                          */
+int cgp_kf_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+               int nell_last_only, void *stream);                    /* filters_smoothers.py:145-184 */
+int cgp_ekf_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+                int nell_last_only, void *stream);                   /* :222-264 */
+int cgp_sgp_filter_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+                       int nell_last_only, void *stream);            /* :446-490 (+ :88-121) */
+int cgp_cd_ekf_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+                   int nell_last_only, void *stream);                /* :352-397 (+ quadratures.py:34-54) */
+int cgp_cd_sgp_filter_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+                          int nell_last_only, void *stream);         /* :534-582 (+ :124-137) */
+
+/* ---- smoothers: mfs [B,T,d], Pfs [B,T,d,d] -> mss, Pss (same shapes).  In-place (mss == mfs) is NOT allowed. */
+size_t cgp_workspace_bytes(const char *function_name, const CgpProblem *p);
+int cgp_rts_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
+                void *workspace, size_t workspace_bytes, void *stream);          /* :187-219 */
+int cgp_eks_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
+                void *workspace, size_t workspace_bytes, void *stream);          /* :317-349 */
+int cgp_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
+                         void *workspace, size_t workspace_bytes, void *stream); /* :493-531 */
+int cgp_cd_eks_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
+                   void *workspace, size_t workspace_bytes, void *stream);       /* :400-443 */
+int cgp_cd_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
+                            void *workspace, size_t workspace_bytes, void *stream); /* :585-632 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIRPGP_B200_H */
