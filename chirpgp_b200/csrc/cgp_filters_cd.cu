@@ -1,0 +1,38 @@
+// cd_ekf / cd_sgp_filter launchers (continuous-discrete models, RK4).
+#include "cgp_dispatch.cuh"
+
+namespace cgp {
+
+int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    return dispatch_sde(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        const int block = 128;
+        cd_ekf_thread_kernel<Model><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
+        return check_launch();
+    });
+}
+
+template <class Model, int G, bool SHARE>
+static int launch_cd_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    const int block = 128;
+    sgp_filter_kernel<Model, G, SHARE, true><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
+    return check_launch();
+}
+
+int launch_cd_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    const bool share = use_share(p);
+    const int g = group_size(p, share);
+    return dispatch_sde(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        if constexpr (Model::kLinear) {
+            return launch_cd_sgp_one<Model, 32, false>(p, io, s);
+        } else {
+            if (share) return launch_cd_sgp_one<Model, 32, true>(p, io, s);
+            if (g == 8) return launch_cd_sgp_one<Model, 8, false>(p, io, s);
+            if (g == 16) return launch_cd_sgp_one<Model, 16, false>(p, io, s);
+            return launch_cd_sgp_one<Model, 32, false>(p, io, s);
+        }
+    });
+}
+
+}  // namespace cgp

@@ -1,0 +1,38 @@
+// kf / ekf / sgp_filter launchers (discrete-time models).
+#include "cgp_dispatch.cuh"
+
+namespace cgp {
+
+int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    return dispatch_disc(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        const int block = 128;
+        ekf_thread_kernel<Model><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
+        return check_launch();
+    });
+}
+
+template <class Model, int G, bool SHARE>
+static int launch_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    const int block = 128;
+    sgp_filter_kernel<Model, G, SHARE, false><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
+    return check_launch();
+}
+
+int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    const bool share = use_share(p);
+    const int g = group_size(p, share);
+    return dispatch_disc(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        if constexpr (Model::kLinear) {
+            return launch_sgp_one<Model, 32, false>(p, io, s);
+        } else {
+            if (share) return launch_sgp_one<Model, 32, true>(p, io, s);
+            if (g == 8) return launch_sgp_one<Model, 8, false>(p, io, s);
+            if (g == 16) return launch_sgp_one<Model, 16, false>(p, io, s);
+            return launch_sgp_one<Model, 32, false>(p, io, s);
+        }
+    });
+}
+
+}  // namespace cgp

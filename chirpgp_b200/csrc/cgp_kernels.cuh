@@ -1,0 +1,546 @@
+// cgp_kernels.cuh -- kernel templates of the chirpgp_b200 hot path (sm_100a, FP64 SIMT).
+//
+// Work decomposition (see DESIGN.md "Kernels"):
+//   * sequential filters without sigma points (kf / ekf / cd_ekf): one THREAD owns one chirp and walks the
+//     time loop with mean and covariance in registers;
+//   * sigma-point filters (sgp_filter / cd_sgp_filter) and the sequential CD sigma-point smoother: a GROUP of
+//     G lanes (8/16/32) owns one chirp; every lane keeps a replica of mean/covariance/Cholesky factor in
+//     registers, sigma points are dealt round-robin to lanes and the weighted sums are combined with a
+//     butterfly __shfl_xor all-reduce (every lane gets the bit-identical sum, so replicas never diverge);
+//   * discrete smoothers (rts / eks / sgp_smoother) are split into a TIME-PARALLEL gain kernel (one thread per
+//     (chirp, step): smoother gain G_k, predicted mean/cov -- these depend on the filtering result only) and
+//     a sequential sweep kernel that only evaluates ms = mf + G (ms - mp), Ps = Pf + G (Ps - Pp) G^T.
+//     Same arithmetic per step as the reference's reverse scan (filters_smoothers.py:71-85), re-scheduled.
+#pragma once
+#include "cgp_device.cuh"
+
+namespace cgp {
+
+struct FilterIO {
+    const double *__restrict__ ys;
+    double *__restrict__ mfs;
+    double *__restrict__ Pfs;
+    double *__restrict__ nell;
+    int nell_last_only;
+};
+struct SmootherIO {
+    const double *__restrict__ mfs;
+    const double *__restrict__ Pfs;
+    double *__restrict__ mss;
+    double *__restrict__ Pss;
+    double *__restrict__ ws;     // per (chirp, step): [G d*d | mp d | Pp d*d]
+};
+
+template <int D> CGP_DEV constexpr int ws_record() { return 2 * D * D + D; }
+
+// ================================================================================================ thread-per-chirp filters
+// kf (filters_smoothers.py:145-184) and ekf (:222-264): Model = ModelLinearDisc<D> | ModelLCD<NH>
+template <class Model>
+__global__ void __launch_bounds__(128) ekf_thread_kernel(const CgpProblem p, const FilterIO io) {
+    constexpr int D = Model::D;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double m[D], P[D][D], H[D];
+    load_vec<D>(p.m0 + b * p.m0_stride, m);
+    load_mat<D>(p.P0 + b * p.P0_stride, P);
+    CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
+    const int64_t T = p.T;
+    const bool store = io.mfs != nullptr;
+    double acc = 0.;
+    double ynext = __ldg(y);
+    for (int64_t t = 0; t < T; t++) {
+        const double yt = ynext;
+        if (t + 1 < T) ynext = __ldg(y + t + 1);
+        double mp[D], J[D][D], JP[D][D], Pp[D][D];
+        mdl.mean_jac(m, mp, J);                       // :255-256
+        matmul<D>(J, P, JP);
+        matmul_nt<D>(JP, J, Pp);                      // :257
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
+            if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
+        acc = acc + linear_update<D>(mp, Pp, H, p.Xi, yt, m, P);
+        if (store) {
+            store_vec<D>(io.mfs + (b * T + t) * D, m);
+            store_mat<D>(io.Pfs + (b * T + t) * (D * D), P);
+        }
+        if (io.nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+    }
+    if (io.nell && io.nell_last_only) io.nell[b] = acc;
+}
+
+// ---- continuous-discrete pieces on packed-symmetric covariances --------------------------------
+// rhs of the CD-EKF moment ODE (filters_smoothers.py:384-385): dm = a(m), dP = P J^T + J P + b b^T.
+// With P exactly symmetric (P J^T)_rc == (J P)_cr bit for bit, so one product X = J P suffices.
+template <class Model>
+CGP_DEV void cd_ekf_ode(const Model &mdl, const double (&Qc)[NSym<Model::D>::value], const double (&m)[Model::D],
+                        const double (&P)[NSym<Model::D>::value], double (&dm)[Model::D],
+                        double (&dP)[NSym<Model::D>::value]) {
+    constexpr int D = Model::D;
+    double J[D][D], X[D][D];
+    mdl.drift_jac(m, dm, J);
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) {
+        double s = J[i][0] * P[sidx(0, j)];
+        CGP_UNROLL for (int k = 1; k < D; k++) s = fma(J[i][k], P[sidx(k, j)], s);
+        X[i][j] = s;
+    }
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+        dP[sidx(r, c)] = (X[c][r] + X[r][c]) + Qc[sidx(r, c)];
+}
+
+// One classic RK4 step of size dt on the pair (m, P) (quadratures.py:34-54 / :57-81): exactly one step per
+// measurement interval, 4 rhs evaluations.  `ode(m, P, dm, dP)` is any callable.
+template <int D, class Ode>
+CGP_DEV void rk4_step(Ode &&ode, double (&m)[D], double (&P)[NSym<D>::value], double dt) {
+    constexpr int NS = NSym<D>::value;
+    double km[D], kP[NS], am[D], aP[NS], tm[D], tP[NS];
+    ode(m, P, km, kP);
+    CGP_UNROLL for (int i = 0; i < D; i++) { am[i] = km[i]; tm[i] = m[i] + dt * km[i] * 0.5; }
+    CGP_UNROLL for (int i = 0; i < NS; i++) { aP[i] = kP[i]; tP[i] = P[i] + dt * kP[i] * 0.5; }
+    ode(tm, tP, km, kP);
+    CGP_UNROLL for (int i = 0; i < D; i++) { am[i] = am[i] + 2 * km[i]; tm[i] = m[i] + dt * km[i] * 0.5; }
+    CGP_UNROLL for (int i = 0; i < NS; i++) { aP[i] = aP[i] + 2 * kP[i]; tP[i] = P[i] + dt * kP[i] * 0.5; }
+    ode(tm, tP, km, kP);
+    CGP_UNROLL for (int i = 0; i < D; i++) { am[i] = am[i] + 2 * km[i]; tm[i] = m[i] + dt * km[i]; }
+    CGP_UNROLL for (int i = 0; i < NS; i++) { aP[i] = aP[i] + 2 * kP[i]; tP[i] = P[i] + dt * kP[i]; }
+    ode(tm, tP, km, kP);
+    CGP_UNROLL for (int i = 0; i < D; i++) m[i] = m[i] + dt * (am[i] + km[i]) / 6;
+    CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = P[i] + dt * (aP[i] + kP[i]) / 6;
+}
+
+// cd_ekf (filters_smoothers.py:352-397): Model = ModelLinearSDE<D> | ModelSDE<NH>
+template <class Model>
+__global__ void __launch_bounds__(128) cd_ekf_thread_kernel(const CgpProblem p, const FilterIO io) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride);
+    double m[D], P[NS], Qc[NS], H[D];
+    load_vec<D>(p.m0 + b * p.m0_stride, m);
+    load_sym<D>(p.P0 + b * p.P0_stride, P);
+    load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
+    CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
+    const int64_t T = p.T;
+    const bool store = io.mfs != nullptr;
+    const double dt = p.dt;
+    double acc = 0.;
+    double ynext = __ldg(y);
+    for (int64_t t = 0; t < T; t++) {
+        const double yt = ynext;
+        if (t + 1 < T) ynext = __ldg(y + t + 1);
+        rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+            cd_ekf_ode<Model>(mdl, Qc, mm, PP, dm, dP);
+        }, m, P, dt);
+        double mf[D], Pf[NS];
+        acc = acc + linear_update_sym<D>(m, P, H, p.Xi, yt, mf, Pf);
+        CGP_UNROLL for (int i = 0; i < D; i++) m[i] = mf[i];
+        CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = Pf[i];
+        if (store) {
+            store_vec<D>(io.mfs + (b * T + t) * D, m);
+            store_sym<D>(io.Pfs + (b * T + t) * (D * D), P);
+        }
+        if (io.nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+    }
+    if (io.nell && io.nell_last_only) io.nell[b] = acc;
+}
+
+// ================================================================================================ sigma-point pieces
+// Sigma-point moments of the discretised model (filters_smoothers.py:88-121) computed cooperatively by G lanes:
+//   mp = sum_i w_i f(chi_i),  Pp = sum_i w_i (f f^T + Sigma) - mp mp^T   (uncentred form, :120),
+//   optionally Dx = sum_i w_i chi_i f_i^T - m mp^T (:525).            chi_i = m + L xi_i (quadratures.py:201).
+// SHARE (Gauss-Hermite tables, dimension 0 fastest, quadratures.py:181-189): points i, i + nb, ..., i + (p-1) nb
+// (nb = n / p) differ only in the LAST coordinate of xi, and L is lower triangular, so their chi[0..D-2] -- in
+// particular chi[V] -- are bit-identical: the transcendental part of the model (softplus, sin, cos) is
+// evaluated once per base index instead of once per point.  Results are unchanged.
+template <class Model, int G, bool SHARE, bool CROSS>
+CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n, int p_order,
+                         int lane, const double (&m)[Model::D], const double (&P)[NSym<Model::D>::value],
+                         double (&mp)[Model::D], double (&Pp)[NSym<Model::D>::value], double (&Dx)[Model::D][Model::D]) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    double L[NS];
+    chol_lower_sym<D>(P, L);
+    double am[D], aP[NS];
+    CGP_UNROLL for (int i = 0; i < D; i++) am[i] = 0.;
+    CGP_UNROLL for (int i = 0; i < NS; i++) aP[i] = 0.;
+    if (CROSS) { CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Dx[r][c] = 0.; }
+
+    auto accumulate = [&](int i, const double (&chi)[D], const double (&ev)[D]) {
+        const double w = __ldg(sw + i);
+        CGP_UNROLL for (int r = 0; r < D; r++) am[r] = fma(w, ev[r], am[r]);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++) {
+            double v = ev[r] * ev[c];
+            if (Model::has_sig(r, c)) v += mdl.sig(r, c);
+            aP[sidx(r, c)] = fma(w, v, aP[sidx(r, c)]);
+        }
+        if (CROSS) {
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
+                Dx[r][c] = fma(w, chi[r] * ev[c], Dx[r][c]);
+        }
+    };
+    auto make_chi = [&](int i, double (&chi)[D]) {
+        CGP_UNROLL for (int r = 0; r < D; r++) {
+            double s = L[sidx(r, 0)] * __ldg(sxi + i * D);
+            CGP_UNROLL for (int c = 1; c <= r; c++) s = fma(L[sidx(r, c)], __ldg(sxi + i * D + c), s);
+            chi[r] = m[r] + s;
+        }
+    };
+    if constexpr (SHARE) {
+        const int nb = n / p_order;
+        for (int base = lane; base < nb; base += G) {
+            double chi[D], ev[D];
+            make_chi(base, chi);
+            const typename Model::Trig trig = mdl.prep(chi);
+            mdl.mean_with(trig, chi, ev);
+            accumulate(base, chi, ev);
+            for (int c = 1; c < p_order; c++) {
+                const int i = base + c * nb;
+                make_chi(i, chi);
+                mdl.mean_with(trig, chi, ev);
+                accumulate(i, chi, ev);
+            }
+        }
+    } else {
+        for (int i = lane; i < n; i += G) {
+            double chi[D], ev[D];
+            make_chi(i, chi);
+            mdl.mean(chi, ev);
+            accumulate(i, chi, ev);
+        }
+    }
+    CGP_UNROLL for (int r = 0; r < D; r++) mp[r] = group_allreduce<G>(am[r]);
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+        Pp[sidx(r, c)] = group_allreduce<G>(aP[sidx(r, c)]) - mp[r] * mp[c];
+    if (CROSS) {
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
+            Dx[r][c] = group_allreduce<G>(Dx[r][c]) - m[r] * mp[c];
+    }
+}
+
+// rhs of the CD sigma-point moment ODE (filters_smoothers.py:124-137), G lanes cooperating:
+//   dm = sum_i w_i a(chi_i),  Q = sum_i w_i (chi_i - m) a(chi_i)^T,  dP = Q + Q^T + b b^T.
+template <class Model, int G, bool SHARE>
+CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n, int p_order,
+                        int lane, const double (&Qc)[NSym<Model::D>::value], const double (&m)[Model::D],
+                        const double (&P)[NSym<Model::D>::value], double (&dm)[Model::D],
+                        double (&dP)[NSym<Model::D>::value]) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    double L[NS];
+    chol_lower_sym<D>(P, L);
+    double am[D], aQ[D][D];
+    CGP_UNROLL for (int i = 0; i < D; i++) am[i] = 0.;
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = 0.;
+    auto make_chi = [&](int i, double (&chi)[D]) {
+        CGP_UNROLL for (int r = 0; r < D; r++) {
+            double s = L[sidx(r, 0)] * __ldg(sxi + i * D);
+            CGP_UNROLL for (int c = 1; c <= r; c++) s = fma(L[sidx(r, c)], __ldg(sxi + i * D + c), s);
+            chi[r] = m[r] + s;
+        }
+    };
+    auto accumulate = [&](int i, const double (&chi)[D], const double (&f)[D]) {
+        const double w = __ldg(sw + i);
+        CGP_UNROLL for (int r = 0; r < D; r++) am[r] = fma(w, f[r], am[r]);
+        CGP_UNROLL for (int r = 0; r < D; r++) {
+            const double dr = chi[r] - m[r];
+            CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = fma(w, dr * f[c], aQ[r][c]);
+        }
+    };
+    if constexpr (SHARE && !Model::kLinear) {
+        const int nb = n / p_order;
+        for (int base = lane; base < nb; base += G) {
+            double chi[D], f[D];
+            make_chi(base, chi);
+            const double w = mdl.omega(chi[Model::V]);
+            mdl.drift_w(w, chi, f);
+            accumulate(base, chi, f);
+            for (int c = 1; c < p_order; c++) {
+                const int i = base + c * nb;
+                make_chi(i, chi);
+                mdl.drift_w(w, chi, f);
+                accumulate(i, chi, f);
+            }
+        }
+    } else {
+        for (int i = lane; i < n; i += G) {
+            double chi[D], f[D];
+            make_chi(i, chi);
+            mdl.drift(chi, f);
+            accumulate(i, chi, f);
+        }
+    }
+    CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = group_allreduce<G>(am[r]);
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = group_allreduce<G>(aQ[r][c]);
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+        dP[sidx(r, c)] = (aQ[r][c] + aQ[c][r]) + Qc[sidx(r, c)];
+}
+
+// ================================================================================================ group-per-chirp filters
+// sgp_filter (filters_smoothers.py:446-490) and cd_sgp_filter (:534-582)
+template <class Model, int G, bool SHARE, bool CD>
+__global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, const FilterIO io) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool active = gid < p.B;
+    const int64_t b = active ? gid : p.B - 1;        // idle groups shadow the last chirp (shuffles need all lanes)
+    Model mdl;
+    if constexpr (CD) mdl.load(p.consts + b * p.consts_stride);
+    else mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double m[D], P[NS], H[D], Qc[NS];
+    load_vec<D>(p.m0 + b * p.m0_stride, m);
+    load_sym<D>(p.P0 + b * p.P0_stride, P);
+    if constexpr (CD) load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
+    CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
+    const int64_t T = p.T;
+    const bool store = io.mfs != nullptr && active && lane == 0;
+    const bool store_nell = io.nell != nullptr && active && lane == 0;
+    const int n = p.n_sigma, po = p.gh_order;
+    const double *__restrict__ sw = p.sig_w;
+    const double *__restrict__ sxi = p.sig_xi;
+    const double dt = p.dt;
+    double acc = 0.;
+    double ynext = __ldg(y);
+    for (int64_t t = 0; t < T; t++) {
+        const double yt = ynext;
+        if (t + 1 < T) ynext = __ldg(y + t + 1);
+        double mp[D], Pp[NS];
+        if constexpr (CD) {
+            CGP_UNROLL for (int i = 0; i < D; i++) mp[i] = m[i];
+            CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = P[i];
+            rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+                cd_sgp_ode<Model, G, SHARE>(mdl, sw, sxi, n, po, lane, Qc, mm, PP, dm, dP);
+            }, mp, Pp, dt);
+        } else {
+            double dummy[D][D];
+            sgp_moments<Model, G, SHARE, false>(mdl, sw, sxi, n, po, lane, m, P, mp, Pp, dummy);
+        }
+        acc = acc + linear_update_sym<D>(mp, Pp, H, p.Xi, yt, m, P);
+        if (store) {
+            store_vec<D>(io.mfs + (b * T + t) * D, m);
+            store_sym<D>(io.Pfs + (b * T + t) * (D * D), P);
+        }
+        if (store_nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+    }
+    if (store_nell && io.nell_last_only) io.nell[b] = acc;
+}
+
+// ================================================================================================ discrete smoothers
+// Shared tail of the gain kernels: G = (cho_solve(chol(Pp), DT))^T (filters_smoothers.py:81-82), then the
+// workspace record [G | mp | Pp] of this (chirp, step) is written.
+template <int D>
+CGP_DEV void gain_and_store(const double (&DT)[D][D], const double (&mp)[D], const double (&Pp)[D][D], double *__restrict__ rec) {
+    double L[D][D], X[D][D], Gm[D][D];
+    chol_lower<D>(Pp, L);
+    chol_solve_mat<D>(L, DT, X);
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Gm[r][c] = X[c][r];
+    store_mat<D>(rec, Gm);
+    if constexpr (D % 2 == 0) {
+        store_vec<D>(rec + D * D, mp);
+        store_mat<D>(rec + D * D + D, Pp);
+    } else {
+        CGP_UNROLL for (int i = 0; i < D; i++) rec[D * D + i] = mp[i];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) rec[D * D + D + r * D + c] = Pp[r][c];
+    }
+}
+
+// rts (filters_smoothers.py:187-219) / eks (:317-349) gains: one thread per (chirp, step k), k in [0, T-2].
+template <class Model>
+__global__ void __launch_bounds__(128) eks_gain_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = Model::D;
+    const int64_t Tm1 = p.T - 1;
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= p.B * Tm1) return;
+    const int64_t b = item / Tm1, t = item - b * Tm1;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double mf[D], Pf[D][D];
+    load_vec<D>(io.mfs + (b * p.T + t) * D, mf);
+    load_mat<D>(io.Pfs + (b * p.T + t) * (D * D), Pf);
+    double mp[D], J[D][D], DT[D][D], Pp[D][D];
+    mdl.mean_jac(mf, mp, J);                          // :342-343
+    matmul<D>(J, Pf, DT);                             // DT = J Pf (:345)
+    matmul_nt<D>(DT, J, Pp);                          // :344
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
+        if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
+    gain_and_store<D>(DT, mp, Pp, io.ws + (b * p.T + t) * ws_record<D>());
+}
+
+// sgp_smoother gains (filters_smoothers.py:520-527): one thread per (chirp, step), all sigma points serially.
+template <class Model, bool SHARE>
+__global__ void __launch_bounds__(128) sgp_gain_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    const int64_t Tm1 = p.T - 1;
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= p.B * Tm1) return;
+    const int64_t b = item / Tm1, t = item - b * Tm1;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double mf[D], Pf[NS];
+    load_vec<D>(io.mfs + (b * p.T + t) * D, mf);
+    load_sym<D>(io.Pfs + (b * p.T + t) * (D * D), Pf);
+    double mp[D], Pps[NS], Dx[D][D];
+    sgp_moments<Model, 1, SHARE, true>(mdl, p.sig_w, p.sig_xi, p.n_sigma, p.gh_order, 0, mf, Pf, mp, Pps, Dx);
+    double DT[D][D], Pp[D][D];
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) DT[r][c] = Dx[c][r];
+    sym_to_full<D>(Pps, Pp);
+    gain_and_store<D>(DT, mp, Pp, io.ws + (b * p.T + t) * ws_record<D>());
+}
+
+// Sequential sweep (filters_smoothers.py:83-84, scan :218/:348/:530, stacking :140-142): one thread per chirp.
+//   ms = mf + G (ms - mp);   Ps = Pf + G (Ps - Pp) G^T
+// Records of the next step are fetched into registers while the current step is evaluated.
+template <int D>
+__global__ void __launch_bounds__(64) smoother_sweep_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int R = 2 * D * D + D;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int64_t T = p.T;
+    double ms[D], Ps[D][D];
+    load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
+    load_mat<D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
+    store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
+    store_mat<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+    if (T < 2) return;
+    double Gn[D][D], mpn[D], Ppn[D][D], mfn[D], Pfn[D][D];
+    auto fetch = [&](int64_t t) {
+        const double *rec = io.ws + (b * T + t) * R;
+        load_mat<D>(rec, Gn);
+        if constexpr (D % 2 == 0) { load_vec<D>(rec + D * D, mpn); load_mat<D>(rec + D * D + D, Ppn); }
+        else {
+            CGP_UNROLL for (int i = 0; i < D; i++) mpn[i] = rec[D * D + i];
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ppn[r][c] = rec[D * D + D + r * D + c];
+        }
+        load_vec<D>(io.mfs + (b * T + t) * D, mfn);
+        load_mat<D>(io.Pfs + (b * T + t) * (D * D), Pfn);
+    };
+    fetch(T - 2);
+    for (int64_t t = T - 2; t >= 0; t--) {
+        double Gm[D][D], mp[D], Pp[D][D], mf[D], Pf[D][D];
+        CGP_UNROLL for (int r = 0; r < D; r++) {
+            mp[r] = mpn[r]; mf[r] = mfn[r];
+            CGP_UNROLL for (int c = 0; c < D; c++) { Gm[r][c] = Gn[r][c]; Pp[r][c] = Ppn[r][c]; Pf[r][c] = Pfn[r][c]; }
+        }
+        if (t > 0) fetch(t - 1);
+        double dm[D], dP[D][D], t1[D][D], t2[D][D], gm[D];
+        CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = ms[r] - mp[r];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) dP[r][c] = Ps[r][c] - Pp[r][c];
+        matvec<D>(Gm, dm, gm);
+        CGP_UNROLL for (int r = 0; r < D; r++) ms[r] = mf[r] + gm[r];
+        matmul<D>(Gm, dP, t1);
+        matmul_nt<D>(t1, Gm, t2);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ps[r][c] = Pf[r][c] + t2[r][c];
+        store_vec<D>(io.mss + (b * T + t) * D, ms);
+        store_mat<D>(io.Pss + (b * T + t) * (D * D), Ps);
+    }
+}
+
+// ================================================================================================ CD smoothers
+// cd_eks (filters_smoothers.py:400-443): thread per chirp, RK4 backwards with dt <- -dt (:423).
+//   rhs (:427-432): gamma = b b^T;  M = J_a(m) + (Pf^{-1} gamma^T)^T;  dm = a(m) + gamma Pf^{-1} (m - mf);
+//                   dP = M P + P M^T - gamma.            chol(Pf) and Pf^{-1} gamma are hoisted out of the 4 stages.
+template <class Model>
+__global__ void __launch_bounds__(64) cd_eks_thread_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int64_t T = p.T;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride);
+    double Qc[NS], Qf[D][D];
+    load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
+    sym_to_full<D>(Qc, Qf);
+    double ms[D], Ps[NS];
+    load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
+    load_sym<D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
+    store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
+    store_sym<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+    const double ndt = -p.dt;
+    for (int64_t t = T - 2; t >= 0; t--) {
+        double mf[D], Pf[D][D], Lf[D][D], X[D][D];
+        load_vec<D>(io.mfs + (b * T + t) * D, mf);
+        load_mat<D>(io.Pfs + (b * T + t) * (D * D), Pf);
+        chol_lower<D>(Pf, Lf);
+        chol_solve_mat<D>(Lf, Qf, X);                 // Pf^{-1} gamma^T (gamma symmetric)
+        rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+            double J[D][D], a[D], z[D], Y[D][D];
+            mdl.drift_jac(mm, a, J);
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) J[r][c] = J[r][c] + X[c][r];
+            CGP_UNROLL for (int i = 0; i < D; i++) z[i] = mm[i] - mf[i];
+            chol_solve_vec<D>(Lf, z);
+            CGP_UNROLL for (int r = 0; r < D; r++) {
+                double s = Qf[r][0] * z[0];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Qf[r][k], z[k], s);
+                dm[r] = a[r] + s;
+            }
+            CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) {
+                double s = J[i][0] * PP[sidx(0, j)];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(J[i][k], PP[sidx(k, j)], s);
+                Y[i][j] = s;
+            }
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+                dP[sidx(r, c)] = (Y[r][c] + Y[c][r]) - Qc[sidx(r, c)];
+        }, ms, Ps, ndt);
+        store_vec<D>(io.mss + (b * T + t) * D, ms);
+        store_sym<D>(io.Pss + (b * T + t) * (D * D), Ps);
+    }
+}
+
+// cd_sgp_smoother (filters_smoothers.py:585-632): group of G lanes per chirp.
+//   rhs (:615-621): Gm = Pf^{-1} gamma;  (_m, _P) = cd_sgp_common(m, P);
+//                   dm = _m + Gm^T (m - mf);   dP = _P + Gm^T P + P Gm - 2 gamma.
+template <class Model, int G, bool SHARE>
+__global__ void __launch_bounds__(128) cd_sgp_smoother_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = Model::D, NS = NSym<D>::value;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool active = gid < p.B;
+    const int64_t b = active ? gid : p.B - 1;
+    const bool store = active && lane == 0;
+    const int64_t T = p.T;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride);
+    double Qc[NS], Qf[D][D];
+    load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
+    sym_to_full<D>(Qc, Qf);
+    double ms[D], Ps[NS];
+    load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
+    load_sym<D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
+    if (store) {
+        store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
+        store_sym<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+    }
+    const int n = p.n_sigma, po = p.gh_order;
+    const double ndt = -p.dt;
+    for (int64_t t = T - 2; t >= 0; t--) {
+        double mf[D], Pf[D][D], Lf[D][D], Gm[D][D];
+        load_vec<D>(io.mfs + (b * T + t) * D, mf);
+        load_mat<D>(io.Pfs + (b * T + t) * (D * D), Pf);
+        chol_lower<D>(Pf, Lf);
+        chol_solve_mat<D>(Lf, Qf, Gm);                // Gm = Pf^{-1} gamma
+        rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+            double _m[D], _P[NS], W[D][D];
+            cd_sgp_ode<Model, G, SHARE>(mdl, p.sig_w, p.sig_xi, n, po, lane, Qc, mm, PP, _m, _P);
+            CGP_UNROLL for (int r = 0; r < D; r++) {
+                double s = Gm[0][r] * (mm[0] - mf[0]);
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[k][r], mm[k] - mf[k], s);
+                dm[r] = _m[r] + s;
+            }
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) {      // W = Gm^T P
+                double s = Gm[0][r] * PP[sidx(0, c)];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[k][r], PP[sidx(k, c)], s);
+                W[r][c] = s;
+            }
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+                dP[sidx(r, c)] = ((_P[sidx(r, c)] + W[r][c]) + W[c][r]) - 2 * Qc[sidx(r, c)];
+        }, ms, Ps, ndt);
+        if (store) {
+            store_vec<D>(io.mss + (b * T + t) * D, ms);
+            store_sym<D>(io.Pss + (b * T + t) * (D * D), Ps);
+        }
+    }
+}
+
+}  // namespace cgp

@@ -1,0 +1,38 @@
+// cd_eks / cd_sgp_smoother launchers (sequential RK4 backwards in time).
+#include "cgp_dispatch.cuh"
+
+namespace cgp {
+
+int launch_cd_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    return dispatch_sde(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        const int block = 64;
+        cd_eks_thread_kernel<Model><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
+        return check_launch();
+    });
+}
+
+template <class Model, int G, bool SHARE>
+static int launch_one(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    const int block = 128;
+    cd_sgp_smoother_kernel<Model, G, SHARE><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
+    return check_launch();
+}
+
+int launch_cd_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    const bool share = use_share(p);
+    const int g = group_size(p, share);
+    return dispatch_sde(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        if constexpr (Model::kLinear) {
+            return launch_one<Model, 32, false>(p, io, s);
+        } else {
+            if (share) return launch_one<Model, 32, true>(p, io, s);
+            if (g == 8) return launch_one<Model, 8, false>(p, io, s);
+            if (g == 16) return launch_one<Model, 16, false>(p, io, s);
+            return launch_one<Model, 32, false>(p, io, s);
+        }
+    });
+}
+
+}  // namespace cgp

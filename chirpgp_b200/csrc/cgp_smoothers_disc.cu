@@ -1,0 +1,47 @@
+// rts / eks / sgp_smoother launchers: time-parallel gain kernel + sequential sweep.
+#include "cgp_dispatch.cuh"
+
+namespace cgp {
+
+template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    const int block = 64;
+    smoother_sweep_kernel<D><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
+    return check_launch();
+}
+
+int launch_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    return dispatch_disc(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        const int block = 128;
+        const int64_t items = p.B * (p.T - 1);
+        if (items > 0) {
+            eks_gain_kernel<Model><<<(unsigned)ceil_div(items, block), block, 0, s>>>(p, io);
+            int rc = check_launch();
+            if (rc) return rc;
+        }
+        return launch_sweep<Model::D>(p, io, s);
+    });
+}
+
+int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    const bool share = use_share(p);
+    return dispatch_disc(p, [&](auto tag) {
+        using Model = typename decltype(tag)::type;
+        const int block = 128;
+        const int64_t items = p.B * (p.T - 1);
+        if (items > 0) {
+            const unsigned grid = (unsigned)ceil_div(items, block);
+            if constexpr (Model::kLinear) {
+                sgp_gain_kernel<Model, false><<<grid, block, 0, s>>>(p, io);
+            } else {
+                if (share) sgp_gain_kernel<Model, true><<<grid, block, 0, s>>>(p, io);
+                else sgp_gain_kernel<Model, false><<<grid, block, 0, s>>>(p, io);
+            }
+            int rc = check_launch();
+            if (rc) return rc;
+        }
+        return launch_sweep<Model::D>(p, io, s);
+    });
+}
+
+}  // namespace cgp

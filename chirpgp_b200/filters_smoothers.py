@@ -1,0 +1,348 @@
+"""Gaussian filters and smoothers -- host-side mirror of the reference interface
+``chirpgp.filters_smoothers`` (/root/reference/chirpgp/filters_smoothers.py), running on hand-written sm_100a
+CUDA kernels through the C ABI of include/chirpgp_b200.h.
+
+Same names, positional signatures and return tuples as the reference:
+
+    kf :145-148, rts :187-188, ekf :222-225, eks :317-318, cd_ekf :352-355, cd_eks :400-402,
+    sgp_filter :446-450, sgp_smoother :493-496, cd_sgp_filter :534-538, cd_sgp_smoother :585-588
+
+Differences that follow from running compiled kernels instead of traced Python closures:
+
+* model arguments (``cond_m_cov``, ``a``, ``b``) must be the tagged callables that ``chirpgp_b200.models``
+  builds (``LCDModel``, ``SDEDrift``, ``Dispersion``, ``LinearDisc``, ``LinearSDE``); a plain Python callable
+  is accepted only if probing shows it is linear, anything else raises ``NotImplementedError`` -- there is no
+  CPU fallback;
+* batching is native instead of ``jax.vmap``: ``ys`` may be ``(T,)`` or ``(B, T)``; model parameters, ``m0`` and
+  ``P0`` may carry a matching leading batch axis (or none = shared).  Outputs get the same leading axis;
+* arrays may be NumPy arrays or torch tensors (CPU or CUDA); results come back as the kind of ``ys`` /
+  ``mfs`` (NumPy in -> NumPy out, CUDA tensor in -> CUDA tensors out, no host round trip).
+"""
+import ctypes as C
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .models import (LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, MODEL_LINEAR_DISC, MODEL_LCD,
+                     MODEL_LINEAR_SDE, MODEL_SDE)
+
+__all__ = ['kf', 'rts', 'ekf', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
+           'cd_sgp_smoother']
+
+_F64 = torch.float64
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError('chirpgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _dev(x, dev) -> torch.Tensor:
+    """-> contiguous float64 tensor on the GPU (no copy if it already is one)."""
+    if isinstance(x, torch.Tensor):
+        t = x.detach()
+    else:
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    return t.to(device=dev, dtype=_F64, non_blocking=True).contiguous()
+
+
+def _kind(x):
+    if isinstance(x, torch.Tensor):
+        return ('torch', x.device)
+    return ('numpy', None)
+
+
+def _back(t: torch.Tensor, kind):
+    if kind[0] == 'numpy':
+        return t.cpu().numpy()
+    return t.to(kind[1])
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+_sigma_cache = {}
+
+
+def _sigma_tables(sgps, dev):
+    w = np.ascontiguousarray(np.asarray(sgps.w.detach().cpu() if isinstance(sgps.w, torch.Tensor) else sgps.w,
+                                        dtype=np.float64))
+    xi = np.ascontiguousarray(np.asarray(sgps.xi.detach().cpu() if isinstance(sgps.xi, torch.Tensor) else sgps.xi,
+                                         dtype=np.float64))
+    key = (w.tobytes(), xi.tobytes(), str(dev))
+    hit = _sigma_cache.get(key)
+    if hit is None:
+        from .quadratures import SigmaPoints
+        order = SigmaPoints(int(xi.shape[1]), int(w.shape[0]), w, None, xi).gauss_hermite_order()
+        hit = (torch.as_tensor(w).to(dev), torch.as_tensor(xi).to(dev), order)
+        _sigma_cache[key] = hit
+    return hit
+
+
+def _probe_linear(fn, d, with_dt, dt):
+    """Accept a plain Python callable only if it is linear: f(u) = F u (and a constant covariance)."""
+    def call(u):
+        out = fn(u, dt) if with_dt else fn(u)
+        if with_dt:
+            mean, cov = out
+            return np.asarray(mean, dtype=np.float64), np.asarray(cov, dtype=np.float64)
+        return np.asarray(out, dtype=np.float64), None
+    try:
+        c0, S0 = call(np.zeros(d))
+        F = np.stack([call(np.eye(d)[i])[0] - c0 for i in range(d)], axis=1)
+        x = np.linspace(-1.3, 0.7, d) + 0.1
+        fx, Sx = call(x)
+        ok = np.all(c0 == 0.) and np.allclose(fx, F @ x, rtol=1e-12, atol=1e-14)
+        if with_dt:
+            ok = ok and np.array_equal(S0, Sx)
+    except Exception as exc:  # noqa: BLE001
+        raise NotImplementedError('chirpgp_b200: cannot lower an arbitrary Python callable to a CUDA kernel (%s); '
+                                  'use the tagged models from chirpgp_b200.models' % exc)
+    if not ok:
+        raise NotImplementedError('chirpgp_b200: only linear Python callables can be lowered automatically; use the '
+                                  'tagged models from chirpgp_b200.models (no CPU fallback)')
+    return (LinearDisc(F, S0) if with_dt else LinearSDE(F))
+
+
+def _disc_model(cond_m_cov, d, dt):
+    if isinstance(cond_m_cov, (LCDModel, LinearDisc)):
+        return cond_m_cov
+    if callable(cond_m_cov):
+        return _probe_linear(cond_m_cov, d, True, dt)
+    raise TypeError('cond_m_cov must be a chirpgp_b200.models tagged callable')
+
+
+def _sde_model(a, d):
+    if isinstance(a, (SDEDrift, LinearSDE)):
+        return a
+    if callable(a):
+        return _probe_linear(a, d, False, None)
+    raise TypeError('drift must be a chirpgp_b200.models tagged callable')
+
+
+def _dispersion_matrix(b, m0):
+    """cd_ekf / cd_eks take a dispersion *callable* (filters_smoothers.py:362, :409); the kernels need it state
+    independent (true for every model of the reference)."""
+    if isinstance(b, Dispersion):
+        return b.matrix()
+    if callable(b):
+        probe = np.zeros(int(m0.shape[-1])) if not isinstance(m0, torch.Tensor) else np.zeros(int(m0.shape[-1]))
+        b0 = np.asarray(b(probe), dtype=np.float64)
+        b1 = np.asarray(b(probe + 1.), dtype=np.float64)
+        if not np.array_equal(b0, b1):
+            raise NotImplementedError('chirpgp_b200: state-dependent dispersion is not supported by the kernels')
+        return torch.as_tensor(b0)
+    return b if isinstance(b, torch.Tensor) else torch.as_tensor(np.asarray(b, dtype=np.float64))
+
+
+def _model_fields(model):
+    nh = getattr(model, 'num_harmonics', 0)
+    return model.model_id, int(model.d), int(nh)
+
+
+class _Batch:
+    """Resolves the batch size from the leading axes of the per-problem inputs."""
+
+    def __init__(self):
+        self.B = None
+
+    def see(self, t: torch.Tensor, core_dims: int, what: str):
+        lead = t.shape[:t.dim() - core_dims]
+        if len(lead) == 0:
+            return t.reshape((1,) + tuple(t.shape)), 0
+        n = int(np.prod(lead))
+        t = t.reshape((n,) + tuple(t.shape[len(lead):]))
+        if n == 1:
+            return t, 0
+        if self.B is None:
+            self.B = n
+        elif self.B != n:
+            raise ValueError('inconsistent batch sizes: %s has %d, expected %d' % (what, n, self.B))
+        return t, int(np.prod(t.shape[1:]))
+
+
+def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, Xi, dt, ys_repeat=1):
+    p = N.CgpProblem()
+    p.B, p.T = B, T
+    p.model, p.d, p.num_harmonics = model, d, nh
+    p.ys_repeat = ys_repeat
+    p.consts, p.consts_stride = _ptr(consts), cs
+    p.m0, p.m0_stride = _ptr(m0), m0s
+    p.P0, p.P0_stride = _ptr(P0), P0s
+    p.H = _ptr(H)
+    p.Qc, p.Qc_stride = _ptr(Qc), Qs
+    if sig is not None:
+        w, xi, order = sig
+        p.n_sigma = int(w.shape[0])
+        p.sig_w, p.sig_xi = _ptr(w), _ptr(xi)
+        p.sigma_kind = N.CGP_SIGMA_GAUSS_HERMITE if order else N.CGP_SIGMA_GENERIC
+        p.gh_order = order
+    p.Xi, p.dt = float(Xi), float(dt)
+    return p
+
+
+def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, store=True, last_only=False):
+    dev = _device()
+    L = N.lib()
+    kind = _kind(ys)
+    model_id, d, nh = _model_fields(model)
+    ys_t = _dev(ys, dev)
+    if ys_t.dim() == 0:
+        raise ValueError('ys must have at least one axis (T,)')
+    out_lead = tuple(ys_t.shape[:-1])
+    T = int(ys_t.shape[-1])
+    bt = _Batch()
+    ys2, _ = bt.see(ys_t, 1, 'ys')
+    consts_t, cs = bt.see(_dev(consts, dev), 1, 'model parameters')
+    m0_t, m0s = bt.see(_dev(m0, dev), 1, 'm0')
+    P0_t, P0s = bt.see(_dev(P0, dev), 2, 'P0')
+    Qc_t, Qs = (None, 0)
+    if Qc is not None:
+        Qc_t, Qs = bt.see(_dev(Qc, dev), 2, 'dispersion')
+    B = bt.B or 1
+    if ys2.shape[0] == 1 and B > 1:          # one signal, many parameter sets
+        ys_repeat = B
+        out_lead = (B,)
+    else:
+        ys_repeat = 1
+        if B > 1 and len(out_lead) == 0:
+            out_lead = (B,)
+    H_t = _dev(H, dev).reshape(-1)
+    if m0_t.shape[-1] != d or P0_t.shape[-1] != d or H_t.shape[0] != d:
+        raise ValueError('state dimension mismatch: model d=%d, m0 %s, P0 %s, H %s'
+                         % (d, tuple(m0_t.shape), tuple(P0_t.shape), tuple(H_t.shape)))
+    sig = _sigma_tables(sgps, dev) if sgps is not None else None
+    if sig is not None and int(sig[1].shape[1]) != d:
+        raise ValueError('sigma points have dimension %d, model has %d' % (int(sig[1].shape[1]), d))
+    p = _problem(B, T, model_id, d, nh, consts_t, cs, m0_t, m0s, P0_t, P0s, H_t, Qc_t, Qs, sig, Xi, dt, ys_repeat)
+    mfs = torch.empty((B, T, d), dtype=_F64, device=dev) if store else None
+    Pfs = torch.empty((B, T, d, d), dtype=_F64, device=dev) if store else None
+    nell = torch.empty((B,) if last_only else (B, T), dtype=_F64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = getattr(L, 'cgp_%s_f64' % name)(C.byref(p), _ptr(ys2), _ptr(mfs), _ptr(Pfs), _ptr(nell), int(last_only), stream)
+    N.check(rc, name)
+    if store:
+        mfs = mfs.reshape(out_lead + (T, d))
+        Pfs = Pfs.reshape(out_lead + (T, d, d))
+    nell = nell.reshape(out_lead if last_only else out_lead + (T,))
+    if not store:
+        return _back(nell, kind)
+    return _back(mfs, kind), _back(Pfs, kind), _back(nell, kind)
+
+
+def _run_smoother(name, model, consts, mfs, Pfs, dt, sgps=None, Qc=None):
+    dev = _device()
+    L = N.lib()
+    kind = _kind(mfs)
+    model_id, d, nh = _model_fields(model)
+    mfs_t, Pfs_t = _dev(mfs, dev), _dev(Pfs, dev)
+    if mfs_t.dim() < 2 or Pfs_t.dim() != mfs_t.dim() + 1:
+        raise ValueError('mfs must be (..., T, d) and Pfs (..., T, d, d)')
+    out_lead = tuple(mfs_t.shape[:-2])
+    T = int(mfs_t.shape[-2])
+    if int(mfs_t.shape[-1]) != d:
+        raise ValueError('state dimension mismatch: model d=%d, mfs %s' % (d, tuple(mfs_t.shape)))
+    bt = _Batch()
+    m2, _ = bt.see(mfs_t, 2, 'mfs')
+    P2, _ = bt.see(Pfs_t, 3, 'Pfs')
+    consts_t, cs = bt.see(_dev(consts, dev), 1, 'model parameters')
+    Qc_t, Qs = (None, 0)
+    if Qc is not None:
+        Qc_t, Qs = bt.see(_dev(Qc, dev), 2, 'dispersion')
+    B = int(m2.shape[0])
+    if bt.B is not None and bt.B != B:
+        raise ValueError('batched model parameters need equally batched mfs / Pfs')
+    sig = _sigma_tables(sgps, dev) if sgps is not None else None
+    p = _problem(B, T, model_id, d, nh, consts_t, cs, None, 0, None, 0, None, Qc_t, Qs, sig, 0., dt)
+    mss = torch.empty_like(m2)
+    Pss = torch.empty_like(P2)
+    nbytes = L.cgp_workspace_bytes(name.encode(), C.byref(p))
+    ws = torch.empty((max(nbytes, 8) // 8,), dtype=_F64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = getattr(L, 'cgp_%s_f64' % name)(C.byref(p), _ptr(m2), _ptr(P2), _ptr(mss), _ptr(Pss), _ptr(ws),
+                                         C.c_size_t(nbytes), stream)
+    N.check(rc, name)
+    return _back(mss.reshape(out_lead + (T, d)), kind), _back(Pss.reshape(out_lead + (T, d, d)), kind)
+
+
+def _state_dim(m0):
+    return int(m0.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------ public API
+def kf(F, Sigma, H, Xi, m0, P0, ys) -> Tuple:
+    """Kalman filter for 1-d measurements (filters_smoothers.py:145-184).
+    Returns (mfs (T, d), Pfs (T, d, d), n_ell (T,)); n_ell is the cumulative negative log-likelihood."""
+    model = LinearDisc(F, Sigma)
+    return _run_filter('kf', model, model.consts(), H, Xi, m0, P0, 0., ys)
+
+
+def rts(F, Sigma, mfs, Pfs) -> Tuple:
+    """RTS smoother (filters_smoothers.py:187-219)."""
+    model = LinearDisc(F, Sigma)
+    return _run_smoother('rts', model, model.consts(), mfs, Pfs, 0.)
+
+
+def ekf(cond_m_cov, H, Xi, m0, P0, dt, ys) -> Tuple:
+    """Extended Kalman filter (filters_smoothers.py:222-264)."""
+    dt = float(dt)
+    model = _disc_model(cond_m_cov, _state_dim(m0), dt)
+    return _run_filter('ekf', model, model.consts(dt), H, Xi, m0, P0, dt, ys)
+
+
+def eks(cond_m_cov, mfs, Pfs, dt) -> Tuple:
+    """Extended Kalman smoother (filters_smoothers.py:317-349)."""
+    dt = float(dt)
+    model = _disc_model(cond_m_cov, int(mfs.shape[-1]), dt)
+    return _run_smoother('eks', model, model.consts(dt), mfs, Pfs, dt)
+
+
+def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys) -> Tuple:
+    """Sigma-point (Gauss--Hermite / cubature) filter (filters_smoothers.py:446-490)."""
+    dt = float(dt)
+    model = _disc_model(cond_m_cov, _state_dim(m0), dt)
+    return _run_filter('sgp_filter', model, model.consts(dt), H, Xi, m0, P0, dt, ys, sgps=sgps)
+
+
+def sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt) -> Tuple:
+    """Sigma-point smoother (filters_smoothers.py:493-531)."""
+    dt = float(dt)
+    model = _disc_model(cond_m_cov, int(mfs.shape[-1]), dt)
+    return _run_smoother('sgp_smoother', model, model.consts(dt), mfs, Pfs, dt, sgps=sgps)
+
+
+def _qc(bm):
+    bm = bm if isinstance(bm, torch.Tensor) else torch.as_tensor(np.asarray(bm, dtype=np.float64))
+    bm = bm.to(_F64)
+    return bm @ bm.transpose(-1, -2)
+
+
+def cd_ekf(a, b, H, Xi, m0, P0, dt, ys) -> Tuple:
+    """Continuous-discrete EKF, one RK4 step per sample (filters_smoothers.py:352-397).
+    ``b`` is the dispersion *callable* as in the reference."""
+    model = _sde_model(a, _state_dim(m0))
+    return _run_filter('cd_ekf', model, model.consts(), H, Xi, m0, P0, float(dt), ys, Qc=_qc(_dispersion_matrix(b, m0)))
+
+
+def cd_eks(a, b, mfs, Pfs, dt) -> Tuple:
+    """Continuous-discrete EKS (filters_smoothers.py:400-443)."""
+    model = _sde_model(a, int(mfs.shape[-1]))
+    return _run_smoother('cd_eks', model, model.consts(), mfs, Pfs, float(dt), Qc=_qc(_dispersion_matrix(b, mfs[..., 0, :])))
+
+
+def cd_sgp_filter(a, b, sgps, H, Xi, m0, P0, dt, ys) -> Tuple:
+    """Continuous-discrete sigma-point filter (filters_smoothers.py:534-582).  ``b`` is the dispersion *matrix*
+    (d, dw) as in the reference (callers pass ``dispersion(eye(d))``)."""
+    model = _sde_model(a, _state_dim(m0))
+    return _run_filter('cd_sgp_filter', model, model.consts(), H, Xi, m0, P0, float(dt), ys, sgps=sgps, Qc=_qc(b))
+
+
+def cd_sgp_smoother(a, b, sgps, mfs, Pfs, dt) -> Tuple:
+    """Continuous-discrete sigma-point smoother (filters_smoothers.py:585-632)."""
+    model = _sde_model(a, int(mfs.shape[-1]))
+    return _run_smoother('cd_sgp_smoother', model, model.consts(), mfs, Pfs, float(dt), sgps=sgps, Qc=_qc(b))

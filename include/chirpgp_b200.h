@@ -110,6 +110,10 @@ int cgp_cd_eks_f64(const CgpProblem *p, const double *mfs, const double *Pfs, do
 int cgp_cd_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
                             void *workspace, size_t workspace_bytes, void *stream); /* :585-632 */
 
+/* ---- measurement utility: DFMA-only kernel (8 independent chains / thread) for the FP64 roofline denominator.
+ * `out` holds blocks * 256 doubles.  Returns the flops issued (caller times the stream), < 0 on error. */
+double cgp_bench_dfma(double *out, int blocks, int iters, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

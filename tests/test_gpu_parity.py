@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Tolerances (float64), stated once:
+  * golden fixtures (T <= 400):     means / covariances  |a - b| <= 1e-11 + 1e-9 |b|;
+  * full-length runs (T = 3141):    |a - b| <= ATOL_LONG + 1e-9 |b| with ATOL_LONG = 1e-9 (states and covariances
+    are O(1); components that oscillate through zero cannot meet a purely relative bound);
+  * cumulative nll:                 rtol 1e-11 (fixtures), 1e-10 (T = 3141).
+They are set by the summation-order noise floor of the reference algorithm itself (the
+uncentred sigma-point covariance cancels 4-5 digits; re-ordering the 81 Gauss-Hermite points alone moves the
+means by 4.5e-11 over T = 3141)."""
+import numpy as np
+import numpy.testing as npt
+import pytest
+import torch
+
+import chirpgp_b200 as cg
+from chirpgp_b200 import toymodels
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RT, AT = 1e-9, 1e-11
+ATOL_LONG = 1e-9
+NLL_RT = 1e-11
+NLL_RT_LONG = 1e-10     # cumulative sum over 3141 steps (harmonic d=8 reaches 2e-11)
+
+
+def _close(a, b, rtol=RT, atol=AT):
+    npt.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+def _check_filter(got, want, atol=AT):
+    _close(got[0], want[0], atol=atol)
+    _close(got[1], want[1], atol=atol)
+    _close(got[2], want[2], rtol=NLL_RT if atol == AT else NLL_RT_LONG, atol=1e-9)
+
+
+def _check_smoother(got, want, atol=AT):
+    _close(got[0], want[0], atol=atol)
+    _close(got[1], want[1], atol=atol)
+
+
+class _SG:
+    def __init__(self, w, xi):
+        self.w, self.xi, self.n_points, self.d = w, xi, w.shape[0], xi.shape[1]
+
+
+PARAMS = np.array([0.1, 0.1, 0.1, 1., 1., 7.])
+
+
+def _chirp_setup(params=PARAMS, h=1, freq_scale=1.):
+    if h == 1 and freq_scale == 1.:
+        drift, disp, mc, m0, P0, H = cg.build_chirp_model(params)
+    else:
+        drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(params, num_harmonics=h, freq_scale=freq_scale)
+    lam, b, delta, ell, sigma, m0v = params
+    spec = orc.ChirpSpec(lam, b, ell, sigma, num_harmonics=h, freq_scale=freq_scale)
+    return drift, disp, mc, m0.numpy(), P0.numpy(), H.numpy(), spec
+
+
+@pytest.mark.parametrize('idx', [0, 1])
+def test_linear_golden_all_ten(golden, idx):
+    """The reference's own test case (test/test_filters_smoothers.py:19-85) through the CUDA path, compared
+    with the outputs of the reference sources (golden) AND with the reference's own equivalence assertions."""
+    z = golden('linear_a%d' % idx)
+    sg = cg.SigmaPoints(3, z['sg_w'].shape[0], z['sg_w'], None, z['sg_xi'])
+    dt, Xi = float(z['dt']), float(z['Xi'])
+    F, Sigma, A, B, H, m0, P0, ys = (z[k] for k in ('F', 'Sigma', 'A', 'B', 'H', 'm0', 'P0', 'ys'))
+    m_and_cov = lambda u, _: (F @ u, Sigma)     # plain lambdas as in the reference test: probed as linear
+    drift = lambda u: A @ u
+    dispersion = lambda _: B
+    r = {}
+    r['kf'] = cg.kf(F, Sigma, H, Xi, m0, P0, ys)
+    r['ekf'] = cg.ekf(m_and_cov, H, Xi, m0, P0, dt, ys)
+    r['cd_ekf'] = cg.cd_ekf(drift, dispersion, H, Xi, m0, P0, dt, ys)
+    r['sgp_filter'] = cg.sgp_filter(m_and_cov, sg, H, Xi, m0, P0, dt, ys)
+    r['cd_sgp_filter'] = cg.cd_sgp_filter(drift, B, sg, H, Xi, m0, P0, dt, ys)
+    r['rts'] = cg.rts(F, Sigma, r['kf'][0], r['kf'][1])
+    r['eks'] = cg.eks(m_and_cov, r['ekf'][0], r['ekf'][1], dt)
+    r['cd_eks'] = cg.cd_eks(drift, dispersion, r['cd_ekf'][0], r['cd_ekf'][1], dt)
+    r['sgp_smoother'] = cg.sgp_smoother(m_and_cov, sg, r['sgp_filter'][0], r['sgp_filter'][1], dt)
+    r['cd_sgp_smoother'] = cg.cd_sgp_smoother(drift, B, sg, r['cd_sgp_filter'][0], r['cd_sgp_filter'][1], dt)
+    for k, v in r.items():
+        for j, arr in enumerate(v):
+            _close(arr, z['%s_%d' % (k, j)])
+    # the reference's assertions (:70-73, :82-85)
+    for i in range(3):
+        npt.assert_allclose(r['kf'][i], r['ekf'][i])
+        npt.assert_allclose(r['kf'][i], r['sgp_filter'][i])
+        npt.assert_allclose(r['kf'][i], r['cd_ekf'][i], rtol=1e-5)
+        npt.assert_allclose(r['kf'][i], r['cd_sgp_filter'][i], rtol=1e-5)
+    for i in range(2):
+        npt.assert_allclose(r['rts'][i], r['eks'][i])
+        npt.assert_allclose(r['rts'][i], r['sgp_smoother'][i])
+        npt.assert_allclose(r['rts'][i], r['cd_eks'][i], atol=1e-1)
+        npt.assert_allclose(r['cd_eks'][i], r['cd_sgp_smoother'][i])
+
+
+def _run_all_nonlinear(z, builder, tags):
+    drift, disp, mc, m0, P0, H = builder(z['params'])
+    dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
+    d = m0.shape[-1]
+    out = {}
+    out['ekf'] = cg.ekf(mc, H, Xi, m0, P0, dt, ys)
+    out['eks'] = cg.eks(mc, z['ekf_0'], z['ekf_1'], dt)
+    out['cd_ekf'] = cg.cd_ekf(drift, disp, H, Xi, m0, P0, dt, ys)
+    out['cd_eks'] = cg.cd_eks(drift, disp, z['cd_ekf_0'], z['cd_ekf_1'], dt)
+    for tag in tags:
+        sg = cg.SigmaPoints(d, z['sg_w_' + tag].shape[0], z['sg_w_' + tag], None, z['sg_xi_' + tag])
+        bm = disp(torch.eye(d))
+        out['sgp_filter_' + tag] = cg.sgp_filter(mc, sg, H, Xi, m0, P0, dt, ys)
+        out['sgp_smoother_' + tag] = cg.sgp_smoother(mc, sg, z['sgp_filter_%s_0' % tag], z['sgp_filter_%s_1' % tag], dt)
+        out['cd_sgp_filter_' + tag] = cg.cd_sgp_filter(drift, bm, sg, H, Xi, m0, P0, dt, ys)
+        out['cd_sgp_smoother_' + tag] = cg.cd_sgp_smoother(drift, bm, sg, z['cd_sgp_filter_%s_0' % tag],
+                                                          z['cd_sgp_filter_%s_1' % tag], dt)
+    for k, v in out.items():
+        for j, arr in enumerate(v):
+            a = arr.cpu().numpy() if isinstance(arr, torch.Tensor) else arr
+            if j == 2:
+                _close(a, z['%s_%d' % (k, j)], rtol=NLL_RT, atol=1e-9)
+            else:
+                _close(a, z['%s_%d' % (k, j)])
+
+
+@pytest.mark.parametrize('name,tags', [('chirp', ['gh3', 'cub']), ('chirp_lam0', ['gh3']), ('short', ['gh3'])])
+def test_chirp_golden(golden, name, tags):
+    _run_all_nonlinear(golden(name), cg.build_chirp_model, tags)
+
+
+def test_lascala_golden(golden):
+    _run_all_nonlinear(golden('lascala'), cg.build_lascala_model, ['gh3'])
+
+
+def test_harmonic_golden(golden):
+    _run_all_nonlinear(golden('harmonic'), lambda p: cg.build_harmonic_chirp_model(p, num_harmonics=3), ['cub'])
+
+
+def test_harmonic2_golden(golden):
+    z = golden('harmonic2')
+    drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(z['params'], num_harmonics=2, freq_scale=1.7)
+    dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
+    sg = cg.SigmaPoints.cubature(6)
+    _check_filter(cg.ekf(mc, H, Xi, m0, P0, dt, ys), [z['ekf_%d' % j] for j in range(3)])
+    _check_filter(cg.sgp_filter(mc, sg, H, Xi, m0, P0, dt, ys), [z['sgp_filter_cub_%d' % j] for j in range(3)])
+    _check_filter(cg.cd_sgp_filter(drift, disp(None), sg, H, Xi, m0, P0, dt, ys),
+                  [z['cd_sgp_filter_cub_%d' % j] for j in range(3)])
+
+
+# ---------------------------------------------------------------------------------------- batched vs oracle
+@pytest.fixture(scope='module')
+def batch():
+    B, T, dt = 24, 3141, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, T, dt, Xi=0.1, seed=2)
+    return B, T, dt, ys
+
+
+def test_batched_ekf_eks_vs_oracle(batch):
+    B, T, dt, ys = batch
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    f = cg.ekf(mc, H, 0.1, m0, P0, dt, ys)
+    fo = orc.ekf(spec, H, 0.1, m0, P0, dt, ys)
+    _check_filter(f, fo, ATOL_LONG)
+    s = cg.eks(mc, f[0], f[1], dt)
+    so = orc.eks(spec, fo[0], fo[1], dt)
+    _check_smoother(s, so, ATOL_LONG)
+
+
+def test_batched_ghf_ghs_vs_oracle(batch):
+    B, T, dt, ys = batch
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
+    fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
+    _check_filter(f, fo, ATOL_LONG)
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_smoother(s, so, ATOL_LONG)
+
+
+def test_batched_cd_vs_oracle(batch):
+    B, T, dt, ys = batch
+    ys = ys[:8]
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    Bm = disp(None).numpy()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    f = cg.cd_ekf(drift, disp, H, 0.1, m0, P0, dt, ys)
+    fo = orc.cd_ekf(spec, Bm, H, 0.1, m0, P0, dt, ys)
+    _check_filter(f, fo, ATOL_LONG)
+    s = cg.cd_eks(drift, disp, f[0], f[1], dt)
+    so = orc.cd_eks(spec, Bm, fo[0], fo[1], dt)
+    _check_smoother(s, so, ATOL_LONG)
+    f = cg.cd_sgp_filter(drift, Bm, sg, H, 0.1, m0, P0, dt, ys)
+    fo = orc.cd_sgp_filter(spec, Bm, sg, H, 0.1, m0, P0, dt, ys)
+    _check_filter(f, fo, ATOL_LONG)
+    s = cg.cd_sgp_smoother(drift, Bm, sg, f[0], f[1], dt)
+    so = orc.cd_sgp_smoother(spec, Bm, sg, fo[0], fo[1], dt)
+    _check_smoother(s, so, ATOL_LONG)
+
+
+def test_batched_harmonic_ckf_cks_vs_oracle():
+    B, T, dt = 8, 3141, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, T, dt, Xi=0.1, num_harmonics=3, seed=4)
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup(h=3)
+    m0 = np.array([0., 1., 0., 1., 0., 1., 7., 0.])
+    sg = cg.SigmaPoints.cubature(8)
+    f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
+    fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
+    _check_filter(f, fo, ATOL_LONG)
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_smoother(s, so, ATOL_LONG)
+
+
+def test_per_chirp_parameters_and_shared_signal(batch):
+    """Batched hyper-parameters: (a) one parameter set per chirp, (b) one signal against a candidate grid."""
+    B, T, dt, ys = batch
+    rng = np.random.default_rng(7)
+    params = PARAMS * np.exp(0.2 * rng.standard_normal((B, 6)))
+    drift, disp, mc, m0, P0, H = cg.build_chirp_model(params)
+    spec = orc.ChirpSpec(params[:, 0], params[:, 1], params[:, 3], params[:, 4])
+    f = cg.ekf(mc, H, 0.1, m0, P0, dt, ys[:, :500])
+    fo = orc.ekf(spec, H.numpy(), 0.1, m0.numpy(), P0.numpy(), dt, ys[:, :500])
+    _check_filter(f, fo, ATOL_LONG)
+    f1 = cg.ekf(mc, H, 0.1, m0, P0, dt, ys[3, :500])          # shared signal
+    fo1 = orc.ekf(spec, H.numpy(), 0.1, m0.numpy(), P0.numpy(), dt, ys[3, :500])
+    _check_filter(f1, fo1, ATOL_LONG)
+
+
+def test_edge_cases_T1_T2_and_cuda_tensors():
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    for T in (1, 2):
+        ys = np.ones(T)
+        f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, 1e-3, ys)
+        fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, 1e-3, ys)
+        _check_filter(f, fo, ATOL_LONG)
+        s = cg.sgp_smoother(mc, sg, f[0], f[1], 1e-3)
+        so = orc.sgp_smoother(spec, sg, fo[0], fo[1], 1e-3)
+        _check_smoother(s, so, ATOL_LONG)
+        if T == 1:
+            _close(s[0], f[0], rtol=0, atol=0)
+    # CUDA tensors in -> CUDA tensors out
+    ys = torch.ones(5, dtype=torch.float64, device='cuda')
+    f = cg.ekf(mc, H, 0.1, m0, P0, 1e-3, ys)
+    assert all(isinstance(x, torch.Tensor) and x.is_cuda for x in f)
+
+
+def test_covariances_identical_across_batch():
+    """test/test_crlb.py:64-66: with vmap(kf) the covariances are bit-identical across the batch."""
+    rng = np.random.default_rng(0)
+    F = np.array([[0.9, 0.1], [0., 0.8]]); Sigma = np.diag([0.1, 0.2])
+    ys = rng.standard_normal((1000, 10))
+    _, Pfs, _ = cg.kf(F, Sigma, np.array([1., 0.]), 0.5, np.zeros(2), np.eye(2), ys)
+    assert np.array_equal(Pfs[0], Pfs[1]) and np.array_equal(Pfs[0], Pfs[-1])
+
+
+def test_non_pd_gives_nan_not_a_trap():
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    badP0 = -np.eye(4)
+    f = cg.sgp_filter(mc, sg, H, 0.1, m0, badP0, 1e-3, np.ones(4))
+    assert np.all(np.isnan(f[0]))
+
+
+def test_unknown_callable_raises():
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    with pytest.raises(NotImplementedError):
+        cg.ekf(lambda u, dt: (np.sin(u), np.eye(4)), H, 0.1, m0, P0, 1e-3, np.ones(4))
