@@ -156,6 +156,48 @@ template <int D> CGP_DEV void chol_solve_mat(const double (&L)[D][D], const doub
         CGP_UNROLL for (int i = 0; i < D; i++) X[i][c] = col[i];
     }
 }
+// rsqrt-scaled Cholesky variants (columns scaled by rsqrt(pivot): <= 2 ulp from the divide-by-sqrt form)
+template <int D> CGP_DEV void chol_lower_sym_rsqrt(const double (&P)[NSym<D>::value], double (&L)[NSym<D>::value]) {
+    CGP_UNROLL for (int j = 0; j < D; j++) {
+        double s = P[sidx(j, j)];
+        CGP_UNROLL for (int k = 0; k < j; k++) s = fma(-L[sidx(j, k)], L[sidx(j, k)], s);
+        const double r = rsqrt(s);
+        L[sidx(j, j)] = s * r;
+        CGP_UNROLL for (int i = j + 1; i < D; i++) {
+            double t = P[sidx(i, j)];
+            CGP_UNROLL for (int k = 0; k < j; k++) t = fma(-L[sidx(i, k)], L[sidx(j, k)], t);
+            L[sidx(i, j)] = t * r;
+        }
+    }
+}
+// full-storage variant that also returns 1 / L_jj (for the triangular solves)
+template <int D> CGP_DEV void chol_lower_rsqrt(const double (&P)[D][D], double (&L)[D][D], double (&rinv)[D]) {
+    CGP_UNROLL for (int j = 0; j < D; j++) {
+        double s = P[j][j];
+        CGP_UNROLL for (int k = 0; k < j; k++) s = fma(-L[j][k], L[j][k], s);
+        const double r = rsqrt(s);
+        rinv[j] = r;
+        L[j][j] = s * r;
+        CGP_UNROLL for (int i = j + 1; i < D; i++) {
+            double t = P[i][j];
+            CGP_UNROLL for (int k = 0; k < j; k++) t = fma(-L[i][k], L[j][k], t);
+            L[i][j] = t * r;
+        }
+    }
+}
+template <int D> CGP_DEV void chol_solve_vec_rinv(const double (&L)[D][D], const double (&rinv)[D], double (&x)[D]) {
+    CGP_UNROLL for (int i = 0; i < D; i++) {
+        double s = x[i];
+        CGP_UNROLL for (int k = 0; k < i; k++) s = fma(-L[i][k], x[k], s);
+        x[i] = s * rinv[i];
+    }
+    CGP_UNROLL for (int i = D - 1; i >= 0; i--) {
+        double s = x[i];
+        CGP_UNROLL for (int k = i + 1; k < D; k++) s = fma(-L[k][i], x[k], s);
+        x[i] = s * rinv[i];
+    }
+}
+
 template <int D> CGP_DEV void sym_to_full(const double (&S)[NSym<D>::value], double (&F)[D][D]) {
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) F[r][c] = S[sidx(r, c)];
 }
@@ -241,6 +283,7 @@ template <int D_> struct ModelLinearDisc {
     CGP_DEV Trig prep(const double (&)[D]) const { return Trig{}; }
     CGP_DEV void mean_with(const Trig &, const double (&u)[D], double (&m)[D]) const { matvec<D>(F, u, m); }
     CGP_DEV void mean(const double (&u)[D], double (&m)[D]) const { matvec<D>(F, u, m); }
+    CGP_DEV void mean_tail(const double (&u)[D], double (&m)[D]) const { matvec<D>(F, u, m); }
     CGP_DEV void mean_jac(const double (&u)[D], double (&m)[D], double (&J)[D][D]) const {
         matvec<D>(F, u, m);
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int k = 0; k < D; k++) J[r][k] = F[r][k];
@@ -288,6 +331,11 @@ template <int NH_> struct ModelLCD {
         m[V + 1] = fma(f11, u[V + 1], f10 * u[V]);
     }
     CGP_DEV void mean(const double (&u)[D], double (&m)[D]) const { mean_with(prep(u), u, m); }
+    // only the Matern rows (the chirp rows do not depend on u[V + 1])
+    CGP_DEV void mean_tail(const double (&u)[D], double (&m)[D]) const {
+        m[V] = fma(f01, u[V + 1], f00 * u[V]);
+        m[V + 1] = fma(f11, u[V + 1], f10 * u[V]);
+    }
     // closed form of jax.jacfwd(lambda u: cond_m_cov(u, dt)[0]) (filters_smoothers.py:255, :342)
     CGP_DEV void mean_jac(const double (&u)[D], double (&m)[D], double (&J)[D][D]) const {
         double gv, sg;

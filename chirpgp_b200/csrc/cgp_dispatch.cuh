@@ -1,6 +1,6 @@
 // cgp_dispatch.cuh -- runtime (model, d, group size) -> compiled kernel instance.
 #pragma once
-#include "cgp_kernels.cuh"
+#include "cgp_fast.cuh"
 
 namespace cgp {
 
@@ -52,8 +52,9 @@ template <class F> int dispatch_sde(const CgpProblem &p, F &&f) {
 
 // Lanes per chirp for the sigma-point kernels: enough lanes for one "work item" each (a point, or with the
 // Gauss-Hermite sharing a base index), capped at a warp.
+// The sharing specialisation is compiled for Gauss-Hermite order 3 (the reference's default, quadratures.py:157).
 inline bool use_share(const CgpProblem &p) {
-    if (p.sigma_kind != CGP_SIGMA_GAUSS_HERMITE || p.gh_order < 2) return false;
+    if (p.sigma_kind != CGP_SIGMA_GAUSS_HERMITE || p.gh_order != 3) return false;
     if (p.model == CGP_MODEL_LINEAR_DISC || p.model == CGP_MODEL_LINEAR_SDE) return false;
     int64_t n = 1;
     for (int i = 0; i < p.d; i++) n *= p.gh_order;
@@ -65,6 +66,8 @@ inline int group_size(const CgpProblem &p, bool share) {
     if (work <= 16) return 16;
     return 32;
 }
+
+inline bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -12,10 +12,10 @@ int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     });
 }
 
-template <class Model, int G, bool SHARE>
+template <class Model, int G, int P>
 static int launch_cd_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     const int block = 128;
-    sgp_filter_kernel<Model, G, SHARE, true><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
+    sgp_filter_kernel<Model, G, P, true><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
     return check_launch();
 }
 
@@ -25,12 +25,12 @@ int launch_cd_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s
     return dispatch_sde(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         if constexpr (Model::kLinear) {
-            return launch_cd_sgp_one<Model, 32, false>(p, io, s);
+            return launch_cd_sgp_one<Model, 32, 0>(p, io, s);
         } else {
-            if (share) return launch_cd_sgp_one<Model, 32, true>(p, io, s);
-            if (g == 8) return launch_cd_sgp_one<Model, 8, false>(p, io, s);
-            if (g == 16) return launch_cd_sgp_one<Model, 16, false>(p, io, s);
-            return launch_cd_sgp_one<Model, 32, false>(p, io, s);
+            if (share) return launch_cd_sgp_one<Model, 32, 3>(p, io, s);
+            if (g == 8) return launch_cd_sgp_one<Model, 8, 0>(p, io, s);
+            if (g == 16) return launch_cd_sgp_one<Model, 16, 0>(p, io, s);
+            return launch_cd_sgp_one<Model, 32, 0>(p, io, s);
         }
     });
 }

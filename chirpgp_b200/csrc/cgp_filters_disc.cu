@@ -12,10 +12,10 @@ int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     });
 }
 
-template <class Model, int G, bool SHARE>
+template <class Model, int G, int P>
 static int launch_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     const int block = 128;
-    sgp_filter_kernel<Model, G, SHARE, false><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
+    sgp_filter_kernel<Model, G, P, false><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
     return check_launch();
 }
 
@@ -25,12 +25,19 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     return dispatch_disc(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         if constexpr (Model::kLinear) {
-            return launch_sgp_one<Model, 32, false>(p, io, s);
+            return launch_sgp_one<Model, 32, 0>(p, io, s);
         } else {
-            if (share) return launch_sgp_one<Model, 32, true>(p, io, s);
-            if (g == 8) return launch_sgp_one<Model, 8, false>(p, io, s);
-            if (g == 16) return launch_sgp_one<Model, 16, false>(p, io, s);
-            return launch_sgp_one<Model, 32, false>(p, io, s);
+            if constexpr (Model::NH == 1) {
+                // headline path: chirp model, Gauss-Hermite order 3 -> 27 base indices, one per lane
+                if (share) {
+                    ghf_filter_kernel<1, 3><<<(unsigned)ceil_div(p.B, 4), 128, 0, s>>>(p, io);
+                    return check_launch();
+                }
+            }
+            if (share) return launch_sgp_one<Model, 32, 3>(p, io, s);
+            if (g == 8) return launch_sgp_one<Model, 8, 0>(p, io, s);
+            if (g == 16) return launch_sgp_one<Model, 16, 0>(p, io, s);
+            return launch_sgp_one<Model, 32, 0>(p, io, s);
         }
     });
 }

@@ -155,13 +155,13 @@ __global__ void __launch_bounds__(128) cd_ekf_thread_kernel(const CgpProblem p, 
 // (nb = n / p) differ only in the LAST coordinate of xi, and L is lower triangular, so their chi[0..D-2] -- in
 // particular chi[V] -- are bit-identical: the transcendental part of the model (softplus, sin, cos) is
 // evaluated once per base index instead of once per point.  Results are unchanged.
-template <class Model, int G, bool SHARE, bool CROSS>
-CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n, int p_order,
-                         int lane, const double (&m)[Model::D], const double (&P)[NSym<Model::D>::value],
+template <class Model, int G, int P, bool CROSS>
+CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n,
+                         int lane, const double (&m)[Model::D], const double (&Pc)[NSym<Model::D>::value],
                          double (&mp)[Model::D], double (&Pp)[NSym<Model::D>::value], double (&Dx)[Model::D][Model::D]) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     double L[NS];
-    chol_lower_sym<D>(P, L);
+    chol_lower_sym_rsqrt<D>(Pc, L);
     double am[D], aP[NS];
     CGP_UNROLL for (int i = 0; i < D; i++) am[i] = 0.;
     CGP_UNROLL for (int i = 0; i < NS; i++) aP[i] = 0.;
@@ -180,32 +180,33 @@ CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const 
                 Dx[r][c] = fma(w, chi[r] * ev[c], Dx[r][c]);
         }
     };
-    auto make_chi = [&](int i, double (&chi)[D]) {
-        CGP_UNROLL for (int r = 0; r < D; r++) {
-            double s = L[sidx(r, 0)] * __ldg(sxi + i * D);
-            CGP_UNROLL for (int c = 1; c <= r; c++) s = fma(L[sidx(r, c)], __ldg(sxi + i * D + c), s);
-            chi[r] = m[r] + s;
-        }
+    auto chi_row = [&](int i, int r) {
+        double s = L[sidx(r, 0)] * __ldg(sxi + i * D);
+        CGP_UNROLL for (int c = 1; c <= r; c++) s = fma(L[sidx(r, c)], __ldg(sxi + i * D + c), s);
+        return m[r] + s;
     };
-    if constexpr (SHARE) {
-        const int nb = n / p_order;
+    if constexpr (P > 0) {
+        // Gauss-Hermite table with P nodes per dimension: points base + c nb (c < P) share chi[0..D-2] and with it
+        // the transcendental part and the chirp rows of the model; only the last coordinate is re-evaluated.
+        // (Bit-identical to evaluating every point from scratch: the skipped operations have identical inputs.)
+        const int nb = n / P;
         for (int base = lane; base < nb; base += G) {
             double chi[D], ev[D];
-            make_chi(base, chi);
+            CGP_UNROLL for (int r = 0; r < D; r++) chi[r] = chi_row(base, r);
             const typename Model::Trig trig = mdl.prep(chi);
             mdl.mean_with(trig, chi, ev);
             accumulate(base, chi, ev);
-            for (int c = 1; c < p_order; c++) {
+            CGP_UNROLL for (int c = 1; c < P; c++) {
                 const int i = base + c * nb;
-                make_chi(i, chi);
-                mdl.mean_with(trig, chi, ev);
+                chi[D - 1] = chi_row(i, D - 1);
+                mdl.mean_tail(chi, ev);
                 accumulate(i, chi, ev);
             }
         }
     } else {
         for (int i = lane; i < n; i += G) {
             double chi[D], ev[D];
-            make_chi(i, chi);
+            CGP_UNROLL for (int r = 0; r < D; r++) chi[r] = chi_row(i, r);
             mdl.mean(chi, ev);
             accumulate(i, chi, ev);
         }
@@ -221,14 +222,14 @@ CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const 
 
 // rhs of the CD sigma-point moment ODE (filters_smoothers.py:124-137), G lanes cooperating:
 //   dm = sum_i w_i a(chi_i),  Q = sum_i w_i (chi_i - m) a(chi_i)^T,  dP = Q + Q^T + b b^T.
-template <class Model, int G, bool SHARE>
-CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n, int p_order,
+template <class Model, int G, int P>
+CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n,
                         int lane, const double (&Qc)[NSym<Model::D>::value], const double (&m)[Model::D],
-                        const double (&P)[NSym<Model::D>::value], double (&dm)[Model::D],
+                        const double (&Pc)[NSym<Model::D>::value], double (&dm)[Model::D],
                         double (&dP)[NSym<Model::D>::value]) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     double L[NS];
-    chol_lower_sym<D>(P, L);
+    chol_lower_sym_rsqrt<D>(Pc, L);
     double am[D], aQ[D][D];
     CGP_UNROLL for (int i = 0; i < D; i++) am[i] = 0.;
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = 0.;
@@ -247,15 +248,15 @@ CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const d
             CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = fma(w, dr * f[c], aQ[r][c]);
         }
     };
-    if constexpr (SHARE && !Model::kLinear) {
-        const int nb = n / p_order;
+    if constexpr (P > 0 && !Model::kLinear) {
+        const int nb = n / P;
         for (int base = lane; base < nb; base += G) {
             double chi[D], f[D];
             make_chi(base, chi);
             const double w = mdl.omega(chi[Model::V]);
             mdl.drift_w(w, chi, f);
             accumulate(base, chi, f);
-            for (int c = 1; c < p_order; c++) {
+            CGP_UNROLL for (int c = 1; c < P; c++) {
                 const int i = base + c * nb;
                 make_chi(i, chi);
                 mdl.drift_w(w, chi, f);
@@ -278,7 +279,7 @@ CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const d
 
 // ================================================================================================ group-per-chirp filters
 // sgp_filter (filters_smoothers.py:446-490) and cd_sgp_filter (:534-582)
-template <class Model, int G, bool SHARE, bool CD>
+template <class Model, int G, int P, bool CD>
 __global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, const FilterIO io) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -288,16 +289,16 @@ __global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, con
     Model mdl;
     if constexpr (CD) mdl.load(p.consts + b * p.consts_stride);
     else mdl.load(p.consts + b * p.consts_stride, p.dt);
-    double m[D], P[NS], H[D], Qc[NS];
+    double m[D], Pc[NS], H[D], Qc[NS];
     load_vec<D>(p.m0 + b * p.m0_stride, m);
-    load_sym<D>(p.P0 + b * p.P0_stride, P);
+    load_sym<D>(p.P0 + b * p.P0_stride, Pc);
     if constexpr (CD) load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
     CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
     const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
     const int64_t T = p.T;
     const bool store = io.mfs != nullptr && active && lane == 0;
     const bool store_nell = io.nell != nullptr && active && lane == 0;
-    const int n = p.n_sigma, po = p.gh_order;
+    const int n = p.n_sigma;
     const double *__restrict__ sw = p.sig_w;
     const double *__restrict__ sxi = p.sig_xi;
     const double dt = p.dt;
@@ -309,18 +310,18 @@ __global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, con
         double mp[D], Pp[NS];
         if constexpr (CD) {
             CGP_UNROLL for (int i = 0; i < D; i++) mp[i] = m[i];
-            CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = P[i];
+            CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = Pc[i];
             rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
-                cd_sgp_ode<Model, G, SHARE>(mdl, sw, sxi, n, po, lane, Qc, mm, PP, dm, dP);
+                cd_sgp_ode<Model, G, P>(mdl, sw, sxi, n, lane, Qc, mm, PP, dm, dP);
             }, mp, Pp, dt);
         } else {
             double dummy[D][D];
-            sgp_moments<Model, G, SHARE, false>(mdl, sw, sxi, n, po, lane, m, P, mp, Pp, dummy);
+            sgp_moments<Model, G, P, false>(mdl, sw, sxi, n, lane, m, Pc, mp, Pp, dummy);
         }
-        acc = acc + linear_update_sym<D>(mp, Pp, H, p.Xi, yt, m, P);
+        acc = acc + linear_update_sym<D>(mp, Pp, H, p.Xi, yt, m, Pc);
         if (store) {
             store_vec<D>(io.mfs + (b * T + t) * D, m);
-            store_sym<D>(io.Pfs + (b * T + t) * (D * D), P);
+            store_sym<D>(io.Pfs + (b * T + t) * (D * D), Pc);
         }
         if (store_nell && !io.nell_last_only) io.nell[b * T + t] = acc;
     }
@@ -332,10 +333,14 @@ __global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, con
 // workspace record [G | mp | Pp] of this (chirp, step) is written.
 template <int D>
 CGP_DEV void gain_and_store(const double (&DT)[D][D], const double (&mp)[D], const double (&Pp)[D][D], double *__restrict__ rec) {
-    double L[D][D], X[D][D], Gm[D][D];
-    chol_lower<D>(Pp, L);
-    chol_solve_mat<D>(L, DT, X);
-    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Gm[r][c] = X[c][r];
+    double L[D][D], rinv[D], Gm[D][D];
+    chol_lower_rsqrt<D>(Pp, L, rinv);
+    CGP_UNROLL for (int c = 0; c < D; c++) {          // column c of X = Pp^{-1} DT is row c of G^T ... G = X^T
+        double col[D];
+        CGP_UNROLL for (int i = 0; i < D; i++) col[i] = DT[i][c];
+        chol_solve_vec_rinv<D>(L, rinv, col);
+        CGP_UNROLL for (int i = 0; i < D; i++) Gm[c][i] = col[i];
+    }
     store_mat<D>(rec, Gm);
     if constexpr (D % 2 == 0) {
         store_vec<D>(rec + D * D, mp);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const CgpProblem p, const
 }
 
 // sgp_smoother gains (filters_smoothers.py:520-527): one thread per (chirp, step), all sigma points serially.
-template <class Model, bool SHARE>
+template <class Model, int P>
 __global__ void __launch_bounds__(128) sgp_gain_kernel(const CgpProblem p, const SmootherIO io) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     const int64_t Tm1 = p.T - 1;
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(128) sgp_gain_kernel(const CgpProblem p, const
     load_vec<D>(io.mfs + (b * p.T + t) * D, mf);
     load_sym<D>(io.Pfs + (b * p.T + t) * (D * D), Pf);
     double mp[D], Pps[NS], Dx[D][D];
-    sgp_moments<Model, 1, SHARE, true>(mdl, p.sig_w, p.sig_xi, p.n_sigma, p.gh_order, 0, mf, Pf, mp, Pps, Dx);
+    sgp_moments<Model, 1, P, true>(mdl, p.sig_w, p.sig_xi, p.n_sigma, 0, mf, Pf, mp, Pps, Dx);
     double DT[D][D], Pp[D][D];
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) DT[r][c] = Dx[c][r];
     sym_to_full<D>(Pps, Pp);
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(64) cd_eks_thread_kernel(const CgpProblem p, c
 // cd_sgp_smoother (filters_smoothers.py:585-632): group of G lanes per chirp.
 //   rhs (:615-621): Gm = Pf^{-1} gamma;  (_m, _P) = cd_sgp_common(m, P);
 //                   dm = _m + Gm^T (m - mf);   dP = _P + Gm^T P + P Gm - 2 gamma.
-template <class Model, int G, bool SHARE>
+template <class Model, int G, int P>
 __global__ void __launch_bounds__(128) cd_sgp_smoother_kernel(const CgpProblem p, const SmootherIO io) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(128) cd_sgp_smoother_kernel(const CgpProblem p
         store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
         store_sym<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
     }
-    const int n = p.n_sigma, po = p.gh_order;
+    const int n = p.n_sigma;
     const double ndt = -p.dt;
     for (int64_t t = T - 2; t >= 0; t--) {
         double mf[D], Pf[D][D], Lf[D][D], Gm[D][D];
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(128) cd_sgp_smoother_kernel(const CgpProblem p
         chol_solve_mat<D>(Lf, Qf, Gm);                // Gm = Pf^{-1} gamma
         rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
             double _m[D], _P[NS], W[D][D];
-            cd_sgp_ode<Model, G, SHARE>(mdl, p.sig_w, p.sig_xi, n, po, lane, Qc, mm, PP, _m, _P);
+            cd_sgp_ode<Model, G, P>(mdl, p.sig_w, p.sig_xi, n, lane, Qc, mm, PP, _m, _P);
             CGP_UNROLL for (int r = 0; r < D; r++) {
                 double s = Gm[0][r] * (mm[0] - mf[0]);
                 CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[k][r], mm[k] - mf[k], s);

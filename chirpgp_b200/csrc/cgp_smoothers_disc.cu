@@ -3,7 +3,16 @@
 
 namespace cgp {
 
+// Sweep: warp-per-chirp kernel (shared-memory tiles, one matrix entry per lane) whenever the 16-byte async
+// copies are legal (even d, 16-byte aligned buffers); otherwise the thread-per-chirp fallback.
 template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    if constexpr (D % 2 == 0) {
+        if (aligned16(io.ws) && aligned16(io.mfs) && aligned16(io.Pfs) && aligned16(io.mss) && aligned16(io.Pss)) {
+            using Cfg = SweepCfg<D>;
+            smoother_sweep_warp_kernel<D><<<(unsigned)ceil_div(p.B, Cfg::WARPS), 32 * Cfg::WARPS, Cfg::smem_bytes(), s>>>(p, io);
+            return check_launch();
+        }
+    }
     const int block = 64;
     smoother_sweep_kernel<D><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
     return check_launch();
@@ -32,10 +41,10 @@ int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t 
         if (items > 0) {
             const unsigned grid = (unsigned)ceil_div(items, block);
             if constexpr (Model::kLinear) {
-                sgp_gain_kernel<Model, false><<<grid, block, 0, s>>>(p, io);
+                sgp_gain_kernel<Model, 0><<<grid, block, 0, s>>>(p, io);
             } else {
-                if (share) sgp_gain_kernel<Model, true><<<grid, block, 0, s>>>(p, io);
-                else sgp_gain_kernel<Model, false><<<grid, block, 0, s>>>(p, io);
+                if (share) sgp_gain_kernel<Model, 3><<<grid, block, 0, s>>>(p, io);
+                else sgp_gain_kernel<Model, 0><<<grid, block, 0, s>>>(p, io);
             }
             int rc = check_launch();
             if (rc) return rc;

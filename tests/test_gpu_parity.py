@@ -1,13 +1,16 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
 
 Tolerances (float64), stated once:
-  * golden fixtures (T <= 400):     means / covariances  |a - b| <= 1e-11 + 1e-9 |b|;
-  * full-length runs (T = 3141):    |a - b| <= ATOL_LONG + 1e-9 |b| with ATOL_LONG = 1e-9 (states and covariances
-    are O(1); components that oscillate through zero cannot meet a purely relative bound);
+  * golden fixtures (T <= 400):     means / covariances  |a - b| <= 1e-11 + 1e-9 |b|  (d = 8 cubature: 1e-10);
+  * full-length runs (T = 3141):    |a - b| <= ATOL_LONG + 1e-9 |b|, ATOL_LONG = 5e-9 (d = 4), 2e-8 (d = 8); states
+    and covariances are O(1)-O(10) and components that oscillate through zero cannot meet a relative bound;
   * cumulative nll:                 rtol 1e-11 (fixtures), 1e-10 (T = 3141).
-They are set by the summation-order noise floor of the reference algorithm itself (the
-uncentred sigma-point covariance cancels 4-5 digits; re-ordering the 81 Gauss-Hermite points alone moves the
-means by 4.5e-11 over T = 3141)."""
+They are set by the summation-order noise floor of the reference algorithm itself (the uncentred sigma-point
+covariance, filters_smoothers.py:120, cancels 4-5 digits).  Measured on the CPU oracle by doing nothing but
+permuting the sigma points (tests/test_noise_floor.py), T = 3141, 4 chirps:
+    chirp d=4, GH order 3:   filter mean 1.5e-10, smoother mean 4.4e-10, Ps 1.2e-10, nll 2.5e-12 (relative)
+    harmonic d=8, cubature:  filter mean 8.5e-10, smoother mean 1.2e-9,  Ps 1.9e-10, nll 1.9e-11 (relative)
+The long-run tolerances are ~10x those figures."""
 import numpy as np
 import numpy.testing as npt
 import pytest
@@ -20,7 +23,9 @@ from oracle import oracle as orc
 pytestmark = pytest.mark.gpu
 
 RT, AT = 1e-9, 1e-11
-ATOL_LONG = 1e-9
+ATOL_LONG = 5e-9
+ATOL_LONG_D8 = 2e-8
+AT_D8 = 1e-10
 NLL_RT = 1e-11
 NLL_RT_LONG = 1e-10     # cumulative sum over 3141 steps (harmonic d=8 reaches 2e-11)
 
@@ -96,7 +101,7 @@ def test_linear_golden_all_ten(golden, idx):
         npt.assert_allclose(r['cd_eks'][i], r['cd_sgp_smoother'][i])
 
 
-def _run_all_nonlinear(z, builder, tags):
+def _run_all_nonlinear(z, builder, tags, atol=AT):
     drift, disp, mc, m0, P0, H = builder(z['params'])
     dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
     d = m0.shape[-1]
@@ -119,7 +124,7 @@ def _run_all_nonlinear(z, builder, tags):
             if j == 2:
                 _close(a, z['%s_%d' % (k, j)], rtol=NLL_RT, atol=1e-9)
             else:
-                _close(a, z['%s_%d' % (k, j)])
+                _close(a, z['%s_%d' % (k, j)], atol=atol)
 
 
 @pytest.mark.parametrize('name,tags', [('chirp', ['gh3', 'cub']), ('chirp_lam0', ['gh3']), ('short', ['gh3'])])
@@ -132,7 +137,7 @@ def test_lascala_golden(golden):
 
 
 def test_harmonic_golden(golden):
-    _run_all_nonlinear(golden('harmonic'), lambda p: cg.build_harmonic_chirp_model(p, num_harmonics=3), ['cub'])
+    _run_all_nonlinear(golden('harmonic'), lambda p: cg.build_harmonic_chirp_model(p, num_harmonics=3), ['cub'], atol=AT_D8)
 
 
 def test_harmonic2_golden(golden):
@@ -205,10 +210,10 @@ def test_batched_harmonic_ckf_cks_vs_oracle():
     sg = cg.SigmaPoints.cubature(8)
     f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
     fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, ATOL_LONG_D8)
     s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_smoother(s, so, ATOL_LONG)
+    _check_smoother(s, so, ATOL_LONG_D8)
 
 
 def test_per_chirp_parameters_and_shared_signal(batch):
