@@ -9,10 +9,12 @@
 
 namespace cgp {
 
-// measurement update on packed-symmetric covariance with one reciprocal; H generic or the unit vector e_1
+// measurement update on packed-symmetric covariance with one reciprocal; H generic or the unit vector e_1.
+// Returns the innovation variance S and residual r = y - H mp; the nll increment is formed from them later
+// (nll_increment), off the critical path of the state recursion.
 template <int D, bool H_E1>
-CGP_DEV double linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym<D>::value], const double (&H)[D], double Xi,
-                                  double y, double (&mf)[D], double (&Pf)[NSym<D>::value]) {
+CGP_DEV void linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym<D>::value], const double (&H)[D], double Xi,
+                                double y, double (&mf)[D], double (&Pf)[NSym<D>::value], double &S_out, double &r_out) {
     double PH[D], S, pred;
     if constexpr (H_E1) {
         CGP_UNROLL for (int i = 0; i < D; i++) PH[i] = Pp[sidx(i, 1)];
@@ -37,6 +39,11 @@ CGP_DEV double linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym
     CGP_UNROLL for (int i = 0; i < D; i++) mf[i] = fma(K[i], r, mp[i]);
     CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j <= i; j++)
         Pf[sidx(i, j)] = fma(-(K[i] * K[j]), S, Pp[sidx(i, j)]);
+    S_out = S;
+    r_out = r;
+}
+// -norm.logpdf(y, pred, sqrt(S)) in jax.scipy.stats.norm.logpdf's operation order (filters_smoothers.py:44-45)
+CGP_DEV double nll_increment(double S, double r) {
     const double sc = sqrt(S), sc2 = sc * sc;
     return (log(kTwoPi * sc2) + r * r / sc2) * 0.5;
 }
@@ -45,20 +52,24 @@ CGP_DEV double linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym
 // sgp_filter (filters_smoothers.py:446-490) for ModelLCD<NH> with a Gauss-Hermite table of P nodes per dimension
 // whose P^(D-1) base indices fit one warp.  Lane `l` owns base index l: its P points (l + c * nb) share
 // chi[0..D-2] and the transcendental part of the model; all table entries the lane needs sit in registers.
+//
+// Output staging: every lane holds a replica of (m, P, S, r).  Lane 0 drops (m, P) of each step into a 32-step
+// shared-memory ring and lane (t mod 32) keeps (S, r) of step t; every 32 steps the warp evaluates the 32 nll
+// increments in SIMD (one log / sqrt / div per lane instead of one per step on the critical path), accumulates
+// them in the reference's sequential order, and writes mfs / Pfs / nell with coalesced 16-byte stores.
 template <int NH, int P>
-__global__ void __launch_bounds__(128) ghf_filter_kernel(const CgpProblem p, const FilterIO io) {
+__global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, const FilterIO io) {
     using Model = ModelLCD<NH>;
-    constexpr int D = Model::D, V = Model::V, NS = NSym<D>::value, NA = D + NS;
+    constexpr int D = Model::D, V = Model::V, NS = NSym<D>::value, NA = D + NS, DD = D * D, REC = D + DD;
     constexpr int PITCH = 33;
     constexpr int KP = (NA <= 16) ? 16 : 32;          // lanes per "half" in the shared-memory reduction
     constexpr int HS = 32 / KP;                       // halves: each sums 32 / HS partials
-    constexpr int WARPS = 4;
-    __shared__ double red[WARPS][NA][PITCH];
-    __shared__ __align__(16) double res[WARPS][(NA + 1) & ~1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t gid = (int64_t)blockIdx.x * WARPS + warp;
-    const bool active = gid < p.B;
-    const int64_t b = active ? gid : p.B - 1;
+    __shared__ double red[NA][PITCH];
+    __shared__ __align__(16) double res[(NA + 1) & ~1];
+    __shared__ __align__(16) double ring[32][REC];
+    __shared__ double nl[32];
+    const int lane = threadIdx.x;
+    const int64_t b = blockIdx.x;
     Model mdl;
     mdl.load(p.consts + b * p.consts_stride, p.dt);
     double m[D], Pc[NS], H[D];
@@ -78,13 +89,15 @@ __global__ void __launch_bounds__(128) ghf_filter_kernel(const CgpProblem p, con
     }
     const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
     const int64_t T = p.T;
-    const bool store = io.mfs != nullptr && active && lane == 0;
-    const bool store_nell = io.nell != nullptr && active && lane == 0;
-    double acc_nll = 0.;
-    double ynext = __ldg(y);
+    const bool store_state = io.mfs != nullptr;
+    const bool store_nell = io.nell != nullptr;
+    double carry = 0.;                 // cumulative nll up to the last flushed step
+    double Sk = 1., rk = 0.;           // (S, r) of the step this lane is responsible for
+    double yv = (lane < T) ? __ldg(y + lane) : 0.;      // 32 measurements per load, broadcast by shuffle
     for (int64_t t = 0; t < T; t++) {
-        const double yt = ynext;
-        if (t + 1 < T) ynext = __ldg(y + t + 1);
+        const int slot = (int)(t & 31);
+        const double yt = __shfl_sync(0xffffffffu, yv, slot);
+        if (slot == 31 && t + 1 < T) yv = (t + 1 + lane < T) ? __ldg(y + t + 1 + lane) : 0.;
         // ---- sigma points of this lane
         double L[NS];
         chol_lower_sym_rsqrt<D>(Pc, L);
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(128) ghf_filter_kernel(const CgpProblem p, con
             }
         }
         // ---- combine the 32 lanes' partial sums through shared memory (fixed tree order)
-        CGP_UNROLL for (int k = 0; k < NA; k++) red[warp][k][lane] = a[k];
+        CGP_UNROLL for (int k = 0; k < NA; k++) red[k][lane] = a[k];
         __syncwarp();
         double tot[NA];
         {
@@ -122,21 +135,21 @@ __global__ void __launch_bounds__(128) ghf_filter_kernel(const CgpProblem p, con
                 const int kk = k0 + k;
                 double v[CNT];
                 const bool ok = kk < NA;
-                CGP_UNROLL for (int j = 0; j < CNT; j++) v[j] = ok ? red[warp][ok ? kk : 0][h * CNT + j] : 0.;
+                CGP_UNROLL for (int j = 0; j < CNT; j++) v[j] = red[ok ? kk : 0][h * CNT + j];
                 CGP_UNROLL for (int w2 = 1; w2 < CNT; w2 <<= 1)
                     CGP_UNROLL for (int j = 0; j + w2 < CNT; j += 2 * w2) v[j] += v[j + w2];
                 double s = v[0];
                 if (HS == 2) s += __shfl_xor_sync(0xffffffffu, s, 16);
-                if (ok && h == 0) res[warp][kk] = s;
+                if (ok && h == 0) res[kk] = s;
             }
         }
         __syncwarp();
         CGP_UNROLL for (int k = 0; k < NA; k += 2) {
             if (k + 1 < NA) {
-                const double2 v = *reinterpret_cast<const double2 *>(&res[warp][k]);
+                const double2 v = *reinterpret_cast<const double2 *>(&res[k]);
                 tot[k] = v.x; tot[k + 1] = v.y;
             } else {
-                tot[k] = res[warp][k];
+                tot[k] = res[k];
             }
         }
         double mp[D], Pp[NS];
@@ -144,17 +157,39 @@ __global__ void __launch_bounds__(128) ghf_filter_kernel(const CgpProblem p, con
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++)
             Pp[sidx(r, q)] = fma(-mp[r], mp[q], tot[D + sidx(r, q)]);
         // ---- measurement update (filters_smoothers.py:55-68)
-        double inc;
-        if (h_e1) inc = linear_update_fast<D, true>(mp, Pp, H, p.Xi, yt, m, Pc);
-        else inc = linear_update_fast<D, false>(mp, Pp, H, p.Xi, yt, m, Pc);
-        acc_nll = acc_nll + inc;
-        if (store) {
-            store_vec<D>(io.mfs + (b * T + t) * D, m);
-            store_sym<D>(io.Pfs + (b * T + t) * (D * D), Pc);
+        double S, resid;
+        if (h_e1) linear_update_fast<D, true>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
+        else linear_update_fast<D, false>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
+        if (lane == slot) { Sk = S; rk = resid; }
+        if (store_state && lane == 0) {
+            store_vec<D>(&ring[slot][0], m);
+            store_sym<D>(&ring[slot][D], Pc);
         }
-        if (store_nell && !io.nell_last_only) io.nell[b * T + t] = acc_nll;
+        // ---- every 32 steps (and at the end): nll increments in SIMD, sequential accumulation, coalesced stores
+        if (slot == 31 || t == T - 1) {
+            const int n = slot + 1;
+            const int64_t t0 = t - slot;
+            nl[lane] = lane < n ? nll_increment(Sk, rk) : 0.;
+            __syncwarp();
+            if (lane == 0) {
+                double c = carry;
+                for (int j = 0; j < n; j++) { c = c + nl[j]; nl[j] = c; }     // reference order: n_ell = n_ell + inc
+            }
+            __syncwarp();
+            carry = nl[n - 1];
+            if (store_nell && !io.nell_last_only && lane < n) io.nell[b * T + t0 + lane] = nl[lane];
+            if (store_state) {
+                double2 *dm = reinterpret_cast<double2 *>(io.mfs + (b * T + t0) * D);
+                for (int i = lane; i < n * (D / 2); i += 32)
+                    dm[i] = *reinterpret_cast<const double2 *>(&ring[i / (D / 2)][2 * (i % (D / 2))]);
+                double2 *dP = reinterpret_cast<double2 *>(io.Pfs + (b * T + t0) * DD);
+                for (int i = lane; i < n * (DD / 2); i += 32)
+                    dP[i] = *reinterpret_cast<const double2 *>(&ring[i / (DD / 2)][D + 2 * (i % (DD / 2))]);
+            }
+            __syncwarp();
+        }
     }
-    if (store_nell && io.nell_last_only) io.nell[b] = acc_nll;
+    if (store_nell && io.nell_last_only && lane == 0) io.nell[b] = carry;
 }
 
 // ------------------------------------------------------------------------------------------------ smoother sweep, warp per chirp
@@ -170,7 +205,7 @@ template <int D> struct SweepCfg {
     static constexpr int TILE_DOUBLES = TS * (R + D + D * D); // ws + mf + Pf
     static constexpr int WARPS = 1;
     static constexpr size_t smem_bytes() {
-        return sizeof(double) * WARPS * (2 * TILE_DOUBLES + TS * OUT + 2 * D * D + 2 * D);
+        return sizeof(double) * (2 * TILE_DOUBLES + TS * OUT + 2 * D * D + 2 * D);
     }
 };
 
@@ -182,20 +217,15 @@ CGP_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> CGP_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 template <int D>
-__global__ void __launch_bounds__(32 * SweepCfg<D>::WARPS) smoother_sweep_warp_kernel(const CgpProblem p, const SmootherIO io) {
+__global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProblem p, const SmootherIO io) {
     using Cfg = SweepCfg<D>;
     constexpr int R = Cfg::R, TS = Cfg::TS, DD = D * D, OUT = Cfg::OUT, TILE = Cfg::TILE_DOUBLES;
+    constexpr int EPL = (DD + 31) / 32;                    // matrix entries per lane
+    // shared-memory map (doubles): two input tiles, the output tile, X = Ps - Pp, T1 = G X, dm = ms - mp
+    constexpr int O_OUT = 2 * TILE, O_X = O_OUT + TS * OUT, O_T1 = O_X + DD, O_DM = O_T1 + DD;
     extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * Cfg::WARPS + warp;
-    if (b >= p.B) return;                                  // whole warp exits together
-    double *base = smem + (size_t)warp * (2 * TILE + TS * OUT + 2 * DD + 2 * D);
-    double *tile[2] = {base, base + TILE};
-    double *outb = base + 2 * TILE;                        // [TS][OUT]
-    double *Xs = outb + TS * OUT;                          // Ps - Pp      (DD)
-    double *T1 = Xs + DD;                                  // G (Ps - Pp)  (DD)
-    double *ms_s = T1 + DD;                                // ms           (D)
-    double *dm_s = ms_s + D;                               // ms - mp      (D)
+    const int lane = threadIdx.x;
+    const int64_t b = blockIdx.x;
     const int64_t T = p.T;
     const double *__restrict__ ws = io.ws + b * T * R;
     const double *__restrict__ mfs = io.mfs + b * T * D;
@@ -203,91 +233,85 @@ __global__ void __launch_bounds__(32 * SweepCfg<D>::WARPS) smoother_sweep_warp_k
     double *__restrict__ mss = io.mss + b * T * D;
     double *__restrict__ Pss = io.Pss + b * T * DD;
 
+    // entry e of the covariance handled by this lane (clamped duplicates keep every lane busy: no divergence)
+    int er[EPL], ec[EPL];
+    bool own[EPL];
+    CGP_UNROLL for (int q = 0; q < EPL; q++) {
+        const int e = lane + 32 * q;
+        own[q] = e < DD;
+        const int ee = own[q] ? e : e % DD;
+        er[q] = ee / D; ec[q] = ee % D;
+    }
+    const int mr = lane % D;                               // mean component handled by this lane
     // last step: copy the filter result (filters_smoothers.py:140-142)
-    for (int i = lane; i < D; i += 32) { const double v = mfs[(T - 1) * D + i]; mss[(T - 1) * D + i] = v; ms_s[i] = v; }
-    for (int i = lane; i < DD; i += 32) { const double v = Pfs[(T - 1) * DD + i]; Pss[(T - 1) * DD + i] = v; T1[i] = v; }
-    __syncwarp();
+    double Pcur[EPL], mcur;
+    CGP_UNROLL for (int q = 0; q < EPL; q++) {
+        Pcur[q] = Pfs[(T - 1) * DD + er[q] * D + ec[q]];
+        if (own[q]) Pss[(T - 1) * DD + er[q] * D + ec[q]] = Pcur[q];
+    }
+    mcur = mfs[(T - 1) * D + mr];
+    if (lane < D) mss[(T - 1) * D + mr] = mcur;
     if (T < 2) return;
-    // tiles cover steps [lo, hi) going backwards from T-1 (exclusive)
+
     auto issue_tile = [&](int buf, int64_t lo, int n) {
-        double *dst = tile[buf];
+        double *dst = smem + buf * TILE;
         const double *s0 = ws + lo * R;
         for (int i = lane; i < n * R / 2; i += 32) cp_async16(dst + 2 * i, s0 + 2 * i);
         const double *s1 = mfs + lo * D;
-        double *d1 = dst + TS * R;
-        for (int i = lane; i < n * D / 2; i += 32) cp_async16(d1 + 2 * i, s1 + 2 * i);
+        for (int i = lane; i < n * D / 2; i += 32) cp_async16(dst + TS * R + 2 * i, s1 + 2 * i);
         const double *s2 = Pfs + lo * DD;
-        double *d2 = d1 + TS * D;
-        for (int i = lane; i < n * DD / 2; i += 32) cp_async16(d2 + 2 * i, s2 + 2 * i);
+        for (int i = lane; i < n * DD / 2; i += 32) cp_async16(dst + TS * (R + D) + 2 * i, s2 + 2 * i);
         cp_async_commit();
     };
-    static_assert((R % 2 == 0) || (SweepCfg<D>::TS % 2 == 0), "16-byte copies need even element counts");
-    int64_t hi = T - 1;
+    int64_t hi = T - 1;                                    // steps [lo, hi) of the current tile, walking backwards
     int buf = 0;
     {
         const int n = (int)(hi < TS ? hi : TS);
         issue_tile(0, hi - n, n);
     }
-    // current Ps lives in T1-slot "Pcur" registers: entry e of lane (e = lane, lane + 32, ...)
-    constexpr int EPL = (DD + 31) / 32;                    // entries per lane
-    double Pcur[EPL], mcur = 0.;
-    CGP_UNROLL for (int q = 0; q < EPL; q++) { const int e = lane + 32 * q; Pcur[q] = e < DD ? T1[e] : 0.; }
-    if (lane < D) mcur = ms_s[lane];
     while (hi > 0) {
         const int n = (int)(hi < TS ? hi : TS);
         const int64_t lo = hi - n;
-        const int64_t nhi = lo;
-        if (nhi > 0) {
-            const int nn = (int)(nhi < TS ? nhi : TS);
-            issue_tile(buf ^ 1, nhi - nn, nn);
+        if (lo > 0) {
+            const int nn = (int)(lo < TS ? lo : TS);
+            issue_tile(buf ^ 1, lo - nn, nn);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncwarp();
-        const double *tw = tile[buf];
-        const double *tm = tw + TS * R;
-        const double *tP = tm + TS * D;
+        const int o_ws = buf * TILE, o_mf = o_ws + TS * R, o_Pf = o_ws + TS * (R + D);
         for (int j = n - 1; j >= 0; j--) {
-            const double *rec = tw + j * R;                // [G | mp | Pp]
-            const double *Gm = rec, *mp = rec + DD, *Pp = rec + DD + D;
+            const int oG = o_ws + j * R, omp = oG + DD, oPp = omp + D;
             // X = Ps - Pp ; dm = ms - mp
-            CGP_UNROLL for (int q = 0; q < EPL; q++) { const int e = lane + 32 * q; if (e < DD) Xs[e] = Pcur[q] - Pp[e]; }
-            if (lane < D) dm_s[lane] = mcur - mp[lane];
+            CGP_UNROLL for (int q = 0; q < EPL; q++) smem[O_X + er[q] * D + ec[q]] = Pcur[q] - smem[oPp + er[q] * D + ec[q]];
+            smem[O_DM + mr] = mcur - smem[omp + mr];
             __syncwarp();
             // T1 = G X ; ms = mf + G dm
             CGP_UNROLL for (int q = 0; q < EPL; q++) {
-                const int e = lane + 32 * q;
-                if (e < DD) {
-                    const int r = e / D, c = e % D;
-                    double s = Gm[r * D] * Xs[c];
-                    CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[r * D + k], Xs[k * D + c], s);
-                    T1[e] = s;
-                }
+                double s = smem[oG + er[q] * D] * smem[O_X + ec[q]];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(smem[oG + er[q] * D + k], smem[O_X + k * D + ec[q]], s);
+                smem[O_T1 + er[q] * D + ec[q]] = s;
             }
-            if (lane < D) {
-                double s = Gm[lane * D] * dm_s[0];
-                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[lane * D + k], dm_s[k], s);
-                mcur = tm[j * D + lane] + s;
-                outb[j * OUT + lane] = mcur;
+            {
+                double s = smem[oG + mr * D] * smem[O_DM];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(smem[oG + mr * D + k], smem[O_DM + k], s);
+                mcur = smem[o_mf + j * D + mr] + s;
+                smem[O_OUT + j * OUT + mr] = mcur;
             }
             __syncwarp();
             // Ps = Pf + T1 G^T
             CGP_UNROLL for (int q = 0; q < EPL; q++) {
-                const int e = lane + 32 * q;
-                if (e < DD) {
-                    const int r = e / D, c = e % D;
-                    double s = T1[r * D] * Gm[c * D];
-                    CGP_UNROLL for (int k = 1; k < D; k++) s = fma(T1[r * D + k], Gm[c * D + k], s);
-                    Pcur[q] = tP[j * DD + e] + s;
-                    outb[j * OUT + D + e] = Pcur[q];
-                }
+                double s = smem[O_T1 + er[q] * D] * smem[oG + ec[q] * D];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(smem[O_T1 + er[q] * D + k], smem[oG + ec[q] * D + k], s);
+                Pcur[q] = smem[o_Pf + j * DD + er[q] * D + ec[q]] + s;
+                smem[O_OUT + j * OUT + D + er[q] * D + ec[q]] = Pcur[q];
             }
             __syncwarp();
         }
         // coalesced write-back of the n finished steps
-        for (int i = lane; i < n * D; i += 32) mss[lo * D + i] = outb[(i / D) * OUT + (i % D)];
-        for (int i = lane; i < n * DD; i += 32) Pss[lo * DD + i] = outb[(i / DD) * OUT + D + (i % DD)];
+        for (int i = lane; i < n * D; i += 32) mss[lo * D + i] = smem[O_OUT + (i / D) * OUT + (i % D)];
+        for (int i = lane; i < n * DD; i += 32) Pss[lo * DD + i] = smem[O_OUT + (i / DD) * OUT + D + (i % DD)];
         __syncwarp();
         hi = lo;
         buf ^= 1;

@@ -9,7 +9,7 @@ template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &
     if constexpr (D % 2 == 0) {
         if (aligned16(io.ws) && aligned16(io.mfs) && aligned16(io.Pfs) && aligned16(io.mss) && aligned16(io.Pss)) {
             using Cfg = SweepCfg<D>;
-            smoother_sweep_warp_kernel<D><<<(unsigned)ceil_div(p.B, Cfg::WARPS), 32 * Cfg::WARPS, Cfg::smem_bytes(), s>>>(p, io);
+            smoother_sweep_warp_kernel<D><<<(unsigned)p.B, 32, Cfg::smem_bytes(), s>>>(p, io);
             return check_launch();
         }
     }
