@@ -24,6 +24,7 @@ class CgpProblem(C.Structure):
         ('model', C.c_int32), ('d', C.c_int32), ('num_harmonics', C.c_int32), ('n_sigma', C.c_int32),
         ('sigma_kind', C.c_int32), ('gh_order', C.c_int32),
         ('ys_repeat', C.c_int64),
+        ('h_unit_index', C.c_int32), ('reserved0', C.c_int32),
         ('consts', C.c_void_p), ('consts_stride', C.c_int64),
         ('m0', C.c_void_p), ('m0_stride', C.c_int64),
         ('P0', C.c_void_p), ('P0_stride', C.c_int64),
@@ -37,7 +38,7 @@ class CgpProblem(C.Structure):
 FILTER_FUNCS = ('kf', 'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
 SMOOTHER_FUNCS = ('rts', 'eks', 'sgp_smoother', 'cd_eks', 'cd_sgp_smoother')
 EXPORTED = (['cgp_abi_version', 'cgp_workspace_bytes'] + ['cgp_%s_f64' % f for f in FILTER_FUNCS + SMOOTHER_FUNCS]
-            + ['cgp_bench_dfma'])
+            + ['cgp_bench_dfma', 'cgp_test_math'])
 
 _lib = None
 
@@ -76,6 +77,8 @@ def lib():
                            C.c_size_t, C.c_void_p]
         L.cgp_bench_dfma.restype = C.c_double
         L.cgp_bench_dfma.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.cgp_test_math.restype = C.c_int
+        L.cgp_test_math.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

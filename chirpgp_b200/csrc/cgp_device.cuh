@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/chirpgp_b200.h"
+#include "cgp_math.cuh"
 
 namespace cgp {
 
@@ -161,7 +162,7 @@ template <int D> CGP_DEV void chol_lower_sym_rsqrt(const double (&P)[NSym<D>::va
     CGP_UNROLL for (int j = 0; j < D; j++) {
         double s = P[sidx(j, j)];
         CGP_UNROLL for (int k = 0; k < j; k++) s = fma(-L[sidx(j, k)], L[sidx(j, k)], s);
-        const double r = rsqrt(s);
+        const double r = fast_rsqrt(s);
         L[sidx(j, j)] = s * r;
         CGP_UNROLL for (int i = j + 1; i < D; i++) {
             double t = P[sidx(i, j)];
@@ -175,7 +176,7 @@ template <int D> CGP_DEV void chol_lower_rsqrt(const double (&P)[D][D], double (
     CGP_UNROLL for (int j = 0; j < D; j++) {
         double s = P[j][j];
         CGP_UNROLL for (int k = 0; k < j; k++) s = fma(-L[j][k], L[j][k], s);
-        const double r = rsqrt(s);
+        const double r = fast_rsqrt(s);
         rinv[j] = r;
         L[j][j] = s * r;
         CGP_UNROLL for (int i = j + 1; i < D; i++) {
@@ -259,9 +260,7 @@ CGP_DEV double linear_update_sym(const double (&mp)[D], const double (&Pp)[NSym<
 // ------------------------------------------------------------------------------------------------ models
 // Softplus and its derivative sharing one exp: g = log(e^x + 1) (naive, as models.py:50), g' = e^x / (e^x + 1).
 CGP_DEV void softplus_and_sigmoid(double x, double &gv, double &sg) {
-    double ex = exp(x), d = ex + 1.;
-    gv = log(d);
-    sg = ex / d;
+    fast_softplus_sigmoid(x, gv, sg);
 }
 
 // Discrete linear model (u, dt) -> (F u, Sigma).  consts = [F | Sigma].
@@ -311,12 +310,12 @@ template <int NH_> struct ModelLCD {
         return s01;
     }
     // trig depends on u[V] only (angles dt * k * w, w = 2 pi g(u_V) freq_scale; models.py:296-298, :370-372)
-    CGP_DEV Trig prep_v(double uv) const {
+    template <bool WARP_UNIFORM = false> CGP_DEV Trig prep_v(double uv) const {
         Trig t;
-        double w = (kTwoPi * log(exp(uv) + 1.)) * fs;
+        double w = (kTwoPi * (WARP_UNIFORM ? fast_softplus_warp(uv) : fast_softplus(uv))) * fs;
         CGP_UNROLL for (int k = 0; k < NH; k++) {
             double sn, cs;
-            sincos((dt * (double)(k + 1)) * w, &sn, &cs);
+            fast_sincos((dt * (double)(k + 1)) * w, &sn, &cs);
             t.c[k] = cs * e; t.s[k] = sn * e;
         }
         return t;
@@ -344,7 +343,7 @@ template <int NH_> struct ModelLCD {
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) J[r][c] = 0.;
         CGP_UNROLL for (int k = 0; k < NH; k++) {
             double sn, cs, dtk = dt * (double)(k + 1);
-            sincos(dtk * w, &sn, &cs);
+            fast_sincos(dtk * w, &sn, &cs);
             double ce = cs * e, se = sn * e, dth = dtk * dw;
             double u0 = u[2 * k], u1 = u[2 * k + 1];
             m[2 * k] = fma(-se, u1, ce * u0);
@@ -395,7 +394,7 @@ template <int NH_> struct ModelSDE {
         a[V] = u[V + 1];
         a[V + 1] = fma(-tg, u[V + 1], -g2 * u[V]);
     }
-    CGP_DEV double omega(double uv) const { return (kTwoPi * log(exp(uv) + 1.)) * fs; }
+    CGP_DEV double omega(double uv) const { return (kTwoPi * fast_softplus(uv)) * fs; }
     CGP_DEV void drift(const double (&u)[D], double (&a)[D]) const { drift_w(omega(u[V]), u, a); }
     // closed form of jax.jacfwd(a) (filters_smoothers.py:382, :425)
     CGP_DEV void drift_jac(const double (&u)[D], double (&a)[D], double (&J)[D][D]) const {

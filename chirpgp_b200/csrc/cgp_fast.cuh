@@ -32,7 +32,7 @@ CGP_DEV void linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym<D
         pred = H[0] * mp[0];
         CGP_UNROLL for (int i = 1; i < D; i++) pred = fma(H[i], mp[i], pred);
     }
-    const double rS = 1. / S;
+    const double rS = fast_rcp(S);
     double K[D];
     CGP_UNROLL for (int i = 0; i < D; i++) K[i] = PH[i] * rS;
     const double r = y - pred;
@@ -57,7 +57,7 @@ CGP_DEV double nll_increment(double S, double r) {
 // shared-memory ring and lane (t mod 32) keeps (S, r) of step t; every 32 steps the warp evaluates the 32 nll
 // increments in SIMD (one log / sqrt / div per lane instead of one per step on the critical path), accumulates
 // them in the reference's sequential order, and writes mfs / Pfs / nell with coalesced 16-byte stores.
-template <int NH, int P>
+template <int NH, int P, bool H_E1, int DBG = 0>   // DBG != 0: timing experiments only (profiles/microbench/ghf_ablate.cu)
 __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, const FilterIO io) {
     using Model = ModelLCD<NH>;
     constexpr int D = Model::D, V = Model::V, NS = NSym<D>::value, NA = D + NS, DD = D * D, REC = D + DD;
@@ -75,8 +75,7 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
     double m[D], Pc[NS], H[D];
     load_vec<D>(p.m0 + b * p.m0_stride, m);
     load_sym<D>(p.P0 + b * p.P0_stride, Pc);
-    bool h_e1 = true;
-    CGP_UNROLL for (int i = 0; i < D; i++) { H[i] = p.H[i]; h_e1 = h_e1 && (H[i] == (i == 1 ? 1. : 0.)); }
+    CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
     // per-lane table entries
     int nb = 1;
     CGP_UNROLL for (int i = 0; i < D - 1; i++) nb *= P;
@@ -100,7 +99,8 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
         if (slot == 31 && t + 1 < T) yv = (t + 1 + lane < T) ? __ldg(y + t + 1 + lane) : 0.;
         // ---- sigma points of this lane
         double L[NS];
-        chol_lower_sym_rsqrt<D>(Pc, L);
+        if constexpr (DBG == 3) { CGP_UNROLL for (int i = 0; i < NS; i++) L[i] = Pc[i]; }
+        else chol_lower_sym_rsqrt<D>(Pc, L);
         double chi[D];
         CGP_UNROLL for (int r = 0; r < D - 1; r++) {
             double s = L[sidx(r, 0)] * xb[0];
@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
         }
         double slast = L[sidx(D - 1, 0)] * xb[0];
         CGP_UNROLL for (int c = 1; c < D - 1; c++) slast = fma(L[sidx(D - 1, c)], xb[c], slast);
-        const typename Model::Trig trig = mdl.prep_v(chi[V]);
+        typename Model::Trig trig;
+        if constexpr (DBG == 2) { CGP_UNROLL for (int k = 0; k < NH; k++) { trig.c[k] = 0.99 + 1e-3 * chi[V]; trig.s[k] = 0.05; } }
+        else trig = mdl.template prep_v<true>(chi[V]);
         double a[NA];
         CGP_UNROLL for (int i = 0; i < NA; i++) a[i] = 0.;
         CGP_UNROLL for (int c = 0; c < P; c++) {
@@ -125,9 +127,11 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
             }
         }
         // ---- combine the 32 lanes' partial sums through shared memory (fixed tree order)
+        double tot[NA];
+        if constexpr (DBG == 1) { CGP_UNROLL for (int k = 0; k < NA; k++) tot[k] = a[k] * 27.; }
+        else {
         CGP_UNROLL for (int k = 0; k < NA; k++) red[k][lane] = a[k];
         __syncwarp();
-        double tot[NA];
         {
             const int k = lane % KP, h = lane / KP;
             constexpr int CNT = 32 / HS;
@@ -152,14 +156,14 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
                 tot[k] = res[k];
             }
         }
+        }
         double mp[D], Pp[NS];
         CGP_UNROLL for (int r = 0; r < D; r++) mp[r] = tot[r];
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++)
             Pp[sidx(r, q)] = fma(-mp[r], mp[q], tot[D + sidx(r, q)]);
         // ---- measurement update (filters_smoothers.py:55-68)
         double S, resid;
-        if (h_e1) linear_update_fast<D, true>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
-        else linear_update_fast<D, false>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
+        linear_update_fast<D, H_E1>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
         if (lane == slot) { Sk = S; rk = resid; }
         if (store_state && lane == 0) {
             store_vec<D>(&ring[slot][0], m);

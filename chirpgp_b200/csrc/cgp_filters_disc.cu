@@ -30,7 +30,8 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
             if constexpr (Model::NH == 1) {
                 // headline path: chirp model, Gauss-Hermite order 3 -> 27 base indices, one per lane
                 if (share) {
-                    ghf_filter_kernel<1, 3><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    if (p.h_unit_index == 1) ghf_filter_kernel<1, 3, true><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    else ghf_filter_kernel<1, 3, false><<<(unsigned)p.B, 32, 0, s>>>(p, io);
                     return check_launch();
                 }
             }

@@ -25,3 +25,31 @@ double cgp_bench_dfma(double *out, int blocks, int iters, void *stream) {
     return (double)blocks * 256. * (double)iters * 16.;
 }
 }
+
+// ---- test hook for cgp_math.cuh: evaluates one of the fast elementary functions element-wise (device pointers)
+#include "cgp_math.cuh"
+namespace {
+__global__ void math_probe_kernel(int kind, int64_t n, const double *__restrict__ x, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r = 0., s, c;
+    switch (kind) {
+        case 0: r = cgp::fast_exp(v); break;
+        case 1: r = cgp::fast_softplus(v); break;
+        case 2: cgp::fast_sincos(v, &s, &c); r = s; break;
+        case 3: cgp::fast_sincos(v, &s, &c); r = c; break;
+        case 4: r = cgp::fast_rsqrt(v); break;
+        case 5: r = cgp::fast_rcp(v); break;
+        case 6: cgp::fast_softplus_sigmoid(v, s, c); r = c; break;
+        case 7: cgp::fast_softplus_sigmoid(v, s, c); r = s; break;
+        default: r = v;
+    }
+    out[i] = r;
+}
+}  // namespace
+extern "C" int cgp_test_math(int kind, int64_t n, const double *x, double *out, void *stream) {
+    if (n < 1 || !x || !out) return -1;
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, n, x, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}

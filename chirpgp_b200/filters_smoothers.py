@@ -166,7 +166,7 @@ class _Batch:
         return t, int(np.prod(t.shape[1:]))
 
 
-def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, Xi, dt, ys_repeat=1):
+def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, Xi, dt, ys_repeat=1, h_unit=-1):
     p = N.CgpProblem()
     p.B, p.T = B, T
     p.model, p.d, p.num_harmonics = model, d, nh
@@ -175,6 +175,7 @@ def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, X
     p.m0, p.m0_stride = _ptr(m0), m0s
     p.P0, p.P0_stride = _ptr(P0), P0s
     p.H = _ptr(H)
+    p.h_unit_index = h_unit
     p.Qc, p.Qc_stride = _ptr(Qc), Qs
     if sig is not None:
         w, xi, order = sig
@@ -212,6 +213,9 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
         ys_repeat = 1
         if B > 1 and len(out_lead) == 0:
             out_lead = (B,)
+    H_host = (H.detach().cpu().numpy() if isinstance(H, torch.Tensor) else np.asarray(H, dtype=np.float64)).reshape(-1)
+    ones = np.flatnonzero(H_host)
+    h_unit = int(ones[0]) if ones.size == 1 and H_host[ones[0]] == 1. else -1
     H_t = _dev(H, dev).reshape(-1)
     if m0_t.shape[-1] != d or P0_t.shape[-1] != d or H_t.shape[0] != d:
         raise ValueError('state dimension mismatch: model d=%d, m0 %s, P0 %s, H %s'
@@ -219,7 +223,7 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
     sig = _sigma_tables(sgps, dev) if sgps is not None else None
     if sig is not None and int(sig[1].shape[1]) != d:
         raise ValueError('sigma points have dimension %d, model has %d' % (int(sig[1].shape[1]), d))
-    p = _problem(B, T, model_id, d, nh, consts_t, cs, m0_t, m0s, P0_t, P0s, H_t, Qc_t, Qs, sig, Xi, dt, ys_repeat)
+    p = _problem(B, T, model_id, d, nh, consts_t, cs, m0_t, m0s, P0_t, P0s, H_t, Qc_t, Qs, sig, Xi, dt, ys_repeat, h_unit)
     mfs = torch.empty((B, T, d), dtype=_F64, device=dev) if store else None
     Pfs = torch.empty((B, T, d, d), dtype=_F64, device=dev) if store else None
     nell = torch.empty((B,) if last_only else (B, T), dtype=_F64, device=dev)

@@ -69,6 +69,8 @@ typedef struct CgpProblem {
     int32_t sigma_kind;        /* CGP_SIGMA_*                                                  */
     int32_t gh_order;          /* nodes per dimension when sigma_kind == GAUSS_HERMITE         */
     int64_t ys_repeat;         /* >= 1                                                         */
+    int32_t h_unit_index;      /* hint: j if H is exactly the unit vector e_j, else -1 (results identical)  */
+    int32_t reserved0;
     const double *consts;  int64_t consts_stride;   /* model constants, see model ids          */
     const double *m0;      int64_t m0_stride;       /* [B|1, d]                                */
     const double *P0;      int64_t P0_stride;       /* [B|1, d, d] (symmetric)                 */
@@ -113,6 +115,11 @@ int cgp_cd_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double
 /* ---- measurement utility: DFMA-only kernel (8 independent chains / thread) for the FP64 roofline denominator.
  * `out` holds blocks * 256 doubles.  Returns the flops issued (caller times the stream), < 0 on error. */
 double cgp_bench_dfma(double *out, int blocks, int iters, void *stream);
+
+/* ---- test hook: element-wise evaluation of the library's internal FP64 elementary functions (csrc/cgp_math.cuh)
+ * kind: 0 exp, 1 softplus log(exp(x)+1), 2 sin, 3 cos, 4 rsqrt, 5 1/x, 6 sigmoid, 7 softplus (paired variant).
+ * x, out: device pointers [n]. */
+int cgp_test_math(int kind, int64_t n, const double *x, double *out, void *stream);
 
 #ifdef __cplusplus
 }
