@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
         wl[c] = has_pts ? p.sig_w[lane + c * nb] : 0.;
         xlast[c] = p.sig_xi[(c * nb) * D + (D - 1)];
     }
+    double Wl = 0.;
+    CGP_UNROLL for (int c = 0; c < P; c++) Wl += wl[c];
     const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
     const int64_t T = p.T;
     const bool store_state = io.mfs != nullptr;
@@ -112,19 +114,33 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
         typename Model::Trig trig;
         if constexpr (DBG == 2) { CGP_UNROLL for (int k = 0; k < NH; k++) { trig.c[k] = 0.99 + 1e-3 * chi[V]; trig.s[k] = 0.05; } }
         else trig = mdl.template prep_v<true>(chi[V]);
+        // weighted sums over this lane's P points: only chi[D-1] and the Matern rows ev[V], ev[V+1] differ between
+        // them, so the sums factor through W = sum w_c (precomputed), S_t = sum w_c ev[V+t]_c and three quadratic terms
         double a[NA];
-        CGP_UNROLL for (int i = 0; i < NA; i++) a[i] = 0.;
-        CGP_UNROLL for (int c = 0; c < P; c++) {
-            chi[D - 1] = m[D - 1] + fma(L[sidx(D - 1, D - 1)], xlast[c], slast);
-            double ev[D];
-            mdl.mean_with(trig, chi, ev);
-            const double w = wl[c];
-            CGP_UNROLL for (int r = 0; r < D; r++) a[r] = fma(w, ev[r], a[r]);
-            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++) {
+        {
+            double ev[D], S0 = 0., S1 = 0., q00 = 0., q10 = 0., q11 = 0.;
+            CGP_UNROLL for (int c = 0; c < P; c++) {
+                chi[D - 1] = m[D - 1] + fma(L[sidx(D - 1, D - 1)], xlast[c], slast);
+                if (c == 0) mdl.mean_with(trig, chi, ev); else mdl.mean_tail(chi, ev);
+                const double w = wl[c];
+                S0 = fma(w, ev[V], S0);
+                S1 = fma(w, ev[V + 1], S1);
+                q00 = fma(w, ev[V] * ev[V] + mdl.sig(V, V), q00);
+                q10 = fma(w, ev[V + 1] * ev[V] + mdl.sig(V + 1, V), q10);
+                q11 = fma(w, ev[V + 1] * ev[V + 1] + mdl.sig(V + 1, V + 1), q11);
+            }
+            CGP_UNROLL for (int r = 0; r < V; r++) a[r] = Wl * ev[r];
+            a[V] = S0; a[V + 1] = S1;
+            CGP_UNROLL for (int r = 0; r < V; r++) CGP_UNROLL for (int q = 0; q <= r; q++) {
                 double v = ev[r] * ev[q];
                 if (Model::has_sig(r, q)) v += mdl.sig(r, q);
-                a[D + sidx(r, q)] = fma(w, v, a[D + sidx(r, q)]);
+                a[D + sidx(r, q)] = Wl * v;
             }
+            CGP_UNROLL for (int q = 0; q < V; q++) {
+                a[D + sidx(V, q)] = ev[q] * S0;
+                a[D + sidx(V + 1, q)] = ev[q] * S1;
+            }
+            a[D + sidx(V, V)] = q00; a[D + sidx(V + 1, V)] = q10; a[D + sidx(V + 1, V + 1)] = q11;
         }
         // ---- combine the 32 lanes' partial sums through shared memory (fixed tree order)
         double tot[NA];

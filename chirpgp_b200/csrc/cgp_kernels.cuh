@@ -187,20 +187,55 @@ CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const 
     };
     if constexpr (P > 0) {
         // Gauss-Hermite table with P nodes per dimension: points base + c nb (c < P) share chi[0..D-2] and with it
-        // the transcendental part and the chirp rows of the model; only the last coordinate is re-evaluated.
-        // (Bit-identical to evaluating every point from scratch: the skipped operations have identical inputs.)
+        // the transcendental part and the chirp rows ev[0..V-1] of the model; only chi[D-1] and the Matern rows
+        // ev[V], ev[V+1] differ.  The weighted sums over the P points are therefore formed from
+        //   W = sum_c w_c,  S_t = sum_c w_c ev[V+t]_c,  X = sum_c w_c chi[D-1]_c
+        // and the P x (3 or 2) genuinely quadratic terms: the same sums as the reference's einsum, associated
+        // differently (differences at rounding level, far below the algorithm's own summation-order noise).
+        constexpr int V = D - 2;
         const int nb = n / P;
         for (int base = lane; base < nb; base += G) {
             double chi[D], ev[D];
             CGP_UNROLL for (int r = 0; r < D; r++) chi[r] = chi_row(base, r);
             const typename Model::Trig trig = mdl.prep(chi);
             mdl.mean_with(trig, chi, ev);
-            accumulate(base, chi, ev);
-            CGP_UNROLL for (int c = 1; c < P; c++) {
+            double W = 0., S0 = 0., S1 = 0., X = 0., q00 = 0., q10 = 0., q11 = 0., x0 = 0., x1 = 0.;
+            CGP_UNROLL for (int c = 0; c < P; c++) {
                 const int i = base + c * nb;
-                chi[D - 1] = chi_row(i, D - 1);
-                mdl.mean_tail(chi, ev);
-                accumulate(i, chi, ev);
+                if (c > 0) { chi[D - 1] = chi_row(i, D - 1); mdl.mean_tail(chi, ev); }
+                const double w = __ldg(sw + i);
+                W += w;
+                S0 = fma(w, ev[V], S0);
+                S1 = fma(w, ev[V + 1], S1);
+                q00 = fma(w, ev[V] * ev[V] + mdl.sig(V, V), q00);
+                q10 = fma(w, ev[V + 1] * ev[V] + mdl.sig(V + 1, V), q10);
+                q11 = fma(w, ev[V + 1] * ev[V + 1] + mdl.sig(V + 1, V + 1), q11);
+                if (CROSS) {
+                    X = fma(w, chi[D - 1], X);
+                    x0 = fma(w, chi[D - 1] * ev[V], x0);
+                    x1 = fma(w, chi[D - 1] * ev[V + 1], x1);
+                }
+            }
+            CGP_UNROLL for (int r = 0; r < V; r++) am[r] = fma(W, ev[r], am[r]);
+            am[V] += S0; am[V + 1] += S1;
+            CGP_UNROLL for (int r = 0; r < V; r++) CGP_UNROLL for (int c = 0; c <= r; c++) {
+                double v = ev[r] * ev[c];
+                if (Model::has_sig(r, c)) v += mdl.sig(r, c);
+                aP[sidx(r, c)] = fma(W, v, aP[sidx(r, c)]);
+            }
+            CGP_UNROLL for (int c = 0; c < V; c++) {
+                aP[sidx(V, c)] = fma(ev[c], S0, aP[sidx(V, c)]);
+                aP[sidx(V + 1, c)] = fma(ev[c], S1, aP[sidx(V + 1, c)]);
+            }
+            aP[sidx(V, V)] += q00; aP[sidx(V + 1, V)] += q10; aP[sidx(V + 1, V + 1)] += q11;
+            if (CROSS) {
+                CGP_UNROLL for (int r = 0; r < D - 1; r++) {
+                    CGP_UNROLL for (int c = 0; c < V; c++) Dx[r][c] = fma(W, chi[r] * ev[c], Dx[r][c]);
+                    Dx[r][V] = fma(chi[r], S0, Dx[r][V]);
+                    Dx[r][V + 1] = fma(chi[r], S1, Dx[r][V + 1]);
+                }
+                CGP_UNROLL for (int c = 0; c < V; c++) Dx[D - 1][c] = fma(ev[c], X, Dx[D - 1][c]);
+                Dx[D - 1][V] += x0; Dx[D - 1][V + 1] += x1;
             }
         }
     } else {
