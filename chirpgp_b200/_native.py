@@ -38,7 +38,8 @@ class CgpProblem(C.Structure):
 FILTER_FUNCS = ('kf', 'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
 SMOOTHER_FUNCS = ('rts', 'eks', 'sgp_smoother', 'cd_eks', 'cd_sgp_smoother')
 EXPORTED = (['cgp_abi_version', 'cgp_workspace_bytes'] + ['cgp_%s_f64' % f for f in FILTER_FUNCS + SMOOTHER_FUNCS]
-            + ['cgp_bench_dfma', 'cgp_test_math'])
+            + ['cgp_ekf_nll_default_ckpt', 'cgp_ekf_nll_workspace_bytes', 'cgp_ekf_nll_fwd_f64', 'cgp_ekf_nll_bwd_f64',
+               'cgp_bench_dfma', 'cgp_test_math'])
 
 _lib = None
 
@@ -75,6 +76,16 @@ def lib():
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_size_t, C.c_void_p]
+        L.cgp_ekf_nll_default_ckpt.restype = C.c_int64
+        L.cgp_ekf_nll_default_ckpt.argtypes = [C.c_int64]
+        L.cgp_ekf_nll_workspace_bytes.restype = C.c_size_t
+        L.cgp_ekf_nll_workspace_bytes.argtypes = [C.POINTER(CgpProblem), C.c_int64]
+        L.cgp_ekf_nll_fwd_f64.restype = C.c_int
+        L.cgp_ekf_nll_fwd_f64.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64,
+                                          C.c_void_p]
+        L.cgp_ekf_nll_bwd_f64.restype = C.c_int
+        L.cgp_ekf_nll_bwd_f64.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cgp_bench_dfma.restype = C.c_double
         L.cgp_bench_dfma.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.cgp_test_math.restype = C.c_int

@@ -1,0 +1,158 @@
+"""Maximum-likelihood path: the EKF negative log-likelihood as a differentiable objective.
+
+What the reference does: ``obj_func(theta) = ekf(m_and_cov, H, Xi, m0, P0, dt, ys)[-1][-1]`` differentiated with
+``jax.grad`` through ``lax.scan`` and minimised with L-BFGS-B (/root/reference/demos/ekfs_mle.py:42-49,
+tetralith/jobs/ekfs_mle.py:41-48).  Here the objective is one CUDA kernel without per-step outputs and the gradient is a
+hand-written reverse-mode adjoint kernel (csrc/cgp_nll.cu) wrapped in ``torch.autograd.Function`` -- the torch analogue
+of the ``jax.custom_vjp`` wrapper (chirpgp_b200/jax_ffi.py holds the JAX binding of the same C ABI).  The kernels
+differentiate w.r.t. the derived model constants, ``m0`` and ``P0``; the small map ``theta -> g(theta) -> constants``
+(models.py:50, :56-73, :295-309, :453-456) stays in host autograd, which also reproduces the exact ``lam == 0`` branch.
+
+Batching: ``ys`` (T,) or (B, T); parameters shared or per chirp.  ``candidates=True`` evaluates every chirp against
+every parameter set (hyper-parameter grid): ys (B, T) x params (G, ...) -> nll (B, G).
+"""
+import ctypes as C
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .filters_smoothers import _device, _problem, _ptr
+from .models import LCDModel, NC_LCD
+
+__all__ = ['ekf_nll', 'fit_mle']
+
+_F64 = torch.float64
+
+
+class _EkfNll(torch.autograd.Function):
+    """consts [B, NC_LCD], m0 [B, d], P0 [B, d, d], Xi (0-d tensor) -> nll [B]  (all CUDA float64, contiguous)."""
+
+    @staticmethod
+    def forward(ctx, consts, m0, P0, Xi, ys, H, dt, nh, ys_repeat, h_unit, ckpt_every):
+        L = N.lib()
+        dev = consts.device
+        B, d = m0.shape
+        T = ys.shape[-1]
+        p = _problem(B, T, N.CGP_MODEL_LCD, d, nh, consts, NC_LCD, m0, d, P0, d * d, H, None, 0, None, float(Xi), dt,
+                     ys_repeat, h_unit)
+        need_grad = any(ctx.needs_input_grad[:4])
+        every = int(ckpt_every or L.cgp_ekf_nll_default_ckpt(T))
+        ws, nbytes = None, 0
+        if need_grad:
+            nbytes = L.cgp_ekf_nll_workspace_bytes(C.byref(p), every)
+            ws = torch.empty((nbytes // 8,), dtype=_F64, device=dev)
+        nll = torch.empty((B,), dtype=_F64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = L.cgp_ekf_nll_fwd_f64(C.byref(p), _ptr(ys), _ptr(nll), _ptr(ws), C.c_size_t(nbytes), every, stream)
+        N.check(rc, 'ekf_nll')
+        ctx.save_for_backward(consts, m0, P0, Xi, ys, H)
+        ctx.ws, ctx.meta = ws, (dt, nh, ys_repeat, h_unit, every, nbytes)
+        return nll
+
+    @staticmethod
+    def backward(ctx, nll_bar):
+        consts, m0, P0, Xi, ys, H = ctx.saved_tensors
+        dt, nh, ys_repeat, h_unit, every, nbytes = ctx.meta
+        L = N.lib()
+        dev = consts.device
+        B, d = m0.shape
+        T = ys.shape[-1]
+        p = _problem(B, T, N.CGP_MODEL_LCD, d, nh, consts, NC_LCD, m0, d, P0, d * d, H, None, 0, None, float(Xi), dt,
+                     ys_repeat, h_unit)
+        cb = torch.empty((B, NC_LCD), dtype=_F64, device=dev)
+        mb = torch.empty((B, d), dtype=_F64, device=dev)
+        Pb = torch.empty((B, d, d), dtype=_F64, device=dev)
+        xb = torch.empty((B,), dtype=_F64, device=dev)
+        nb = nll_bar.contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = L.cgp_ekf_nll_bwd_f64(C.byref(p), _ptr(ys), _ptr(nb), _ptr(ctx.ws), C.c_size_t(nbytes), every, _ptr(cb),
+                                   _ptr(mb), _ptr(Pb), _ptr(xb), stream)
+        N.check(rc, 'ekf_nll backward')
+        return cb, mb, Pb, xb.sum(), None, None, None, None, None, None, None
+
+
+def _as_dev(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=_F64)
+    return torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev)
+
+
+def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = False,
+            ckpt_every: Optional[int] = None) -> torch.Tensor:
+    """Final cumulative negative log-likelihood of the EKF == ``ekf(cond_m_cov, H, Xi, m0, P0, dt, ys)[-1][-1]``
+    (filters_smoothers.py:222-264), differentiable w.r.t. the model hyper-parameters, ``m0``, ``P0`` and ``Xi``.
+
+    Returns a CUDA tensor of shape () for one problem, (B,) for a batch, (B, G) with ``candidates=True``."""
+    if not isinstance(cond_m_cov, LCDModel):
+        raise NotImplementedError('ekf_nll: the adjoint kernel is compiled for the chirp-family LCD models only')
+    dev = _device()
+    dt = float(dt)
+    d, nh = cond_m_cov.d, cond_m_cov.num_harmonics
+    ys_t = _as_dev(ys, dev)
+    lead = ys_t.shape[:-1]
+    ys2 = ys_t.reshape(-1, ys_t.shape[-1]).contiguous()
+    Bc = ys2.shape[0]
+    consts = _as_dev(cond_m_cov.consts(dt), dev)
+    m0_t, P0_t = _as_dev(m0, dev), _as_dev(P0, dev)
+    Xi_t = Xi.to(device=dev, dtype=_F64) if isinstance(Xi, torch.Tensor) else torch.tensor(float(Xi), dtype=_F64, device=dev)
+    pb = [int(np.prod(t.shape[:t.dim() - k])) for t, k in ((consts, 1), (m0_t, 1), (P0_t, 2))]
+    G = max(pb)
+    if any(n not in (1, G) for n in pb):
+        raise ValueError('inconsistent parameter batch sizes %s' % pb)
+    if candidates:
+        B, ys_repeat, out_shape = Bc * G, G, tuple(lead) + (G,)
+        expand = lambda t, core: t.reshape((1, -1) + core).expand((Bc, G) + core).reshape((B,) + core)
+    else:
+        if G > 1 and Bc == 1:
+            B, ys_repeat, out_shape = G, G, (G,)
+        elif G in (1, Bc):
+            B, ys_repeat, out_shape = Bc, 1, tuple(lead)
+        else:
+            raise ValueError('batched parameters (%d) do not match the %d chirps (use candidates=True for a grid)' % (G, Bc))
+        expand = lambda t, core: t.reshape((-1,) + core).expand((B,) + core)
+    consts_b = expand(consts, (NC_LCD,)).contiguous()
+    m0_b = expand(m0_t, (d,)).contiguous()
+    P0_b = expand(P0_t, (d, d)).contiguous()
+    H_host = (H.detach().cpu().numpy() if isinstance(H, torch.Tensor) else np.asarray(H, dtype=np.float64)).reshape(-1)
+    ones = np.flatnonzero(H_host)
+    h_unit = int(ones[0]) if ones.size == 1 and H_host[ones[0]] == 1. else -1
+    H_t = torch.as_tensor(H_host, device=dev)
+    nll = _EkfNll.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every)
+    return nll.reshape(out_shape)
+
+
+def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optional[Callable] = None, maxiter: int = 200,
+            reduce_group=None):
+    """L-BFGS-B maximum-likelihood fit driving the nll / adjoint kernels -- the role of
+    ``jaxopt.ScipyMinimize(method='L-BFGS-B', fun=obj_func).run(init_theta)`` (demos/ekfs_mle.py:48-49).
+
+    build_model(params) -> (drift, dispersion, m_and_cov, m0, P0, H') as chirpgp_b200.models.build_*; ``transform`` maps
+    the unconstrained theta to params (default: the reference's softplus ``g``).  The objective is the SUM of the nll over
+    all chirps in ``ys``; with ``reduce_group`` (a torch.distributed process group) chirps are sharded over ranks and the
+    scalar objective and its 6-vector gradient are all-reduced -- the only collective on this path.
+
+    Returns (theta_opt (numpy), scipy OptimizeResult); ``result.success`` follows the reference's convention
+    (tetralith/jobs/ekfs_mle.py:49, :75-78: a failed fit is reported, not raised)."""
+    import scipy.optimize
+    from .models import g as _g
+    transform = transform or _g
+    dev = _device()
+    ys_t = _as_dev(ys, dev)
+
+    def fun(theta_np):
+        theta = torch.tensor(theta_np, dtype=_F64, device=dev, requires_grad=True)
+        _, _, m_and_cov, m0, P0, _ = build_model(transform(theta))
+        val = ekf_nll(m_and_cov, H, Xi, m0, P0, dt, ys_t).sum()
+        grad, = torch.autograd.grad(val, theta)
+        packed = torch.cat([val.detach().reshape(1), grad])
+        if reduce_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=reduce_group)
+        packed = packed.cpu().numpy()
+        return float(packed[0]), packed[1:].copy()
+
+    res = scipy.optimize.minimize(fun, np.asarray(init_theta, dtype=np.float64), jac=True, method='L-BFGS-B',
+                                  options={'maxiter': maxiter})
+    return res.x, res

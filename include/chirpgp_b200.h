@@ -112,6 +112,22 @@ int cgp_cd_eks_f64(const CgpProblem *p, const double *mfs, const double *Pfs, do
 int cgp_cd_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
                             void *workspace, size_t workspace_bytes, void *stream); /* :585-632 */
 
+/* ---- MLE path: EKF negative log-likelihood without per-step outputs, and its reverse-mode adjoint
+ * (jax.grad of `ekf(...)[-1][-1]`, demos/ekfs_mle.py:42-49, tetralith/jobs/ekfs_mle.py:41-48).  LCD models only.
+ *   fwd: nll [B] = final cumulative negative log-likelihood.  With a workspace, (m, P) checkpoints are stored every
+ *        `ckpt_every` steps for the adjoint; workspace == NULL gives a pure objective evaluation.
+ *   bwd: given nll_bar [B] (NULL = ones) and the workspace filled by fwd (same problem, same ckpt_every), returns the
+ *        cotangents of the kernel inputs: consts_bar [B, CGP_NC_LCD], m0_bar [B, d], P0_bar [B, d, d] (general matrix,
+ *        JAX's unsymmetrised convention), Xi_bar [B] (may be NULL).  Shared inputs (stride 0) get per-problem
+ *        cotangents that the caller sums.  */
+int64_t cgp_ekf_nll_default_ckpt(int64_t T);                       /* ~ sqrt(T) */
+size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every);
+int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void *workspace, size_t workspace_bytes,
+                        int64_t ckpt_every, void *stream);
+int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace,
+                        size_t workspace_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,
+                        double *Xi_bar, void *stream);
+
 /* ---- measurement utility: DFMA-only kernel (8 independent chains / thread) for the FP64 roofline denominator.
  * `out` holds blocks * 256 doubles.  Returns the flops issued (caller times the stream), < 0 on error. */
 double cgp_bench_dfma(double *out, int blocks, int iters, void *stream);
