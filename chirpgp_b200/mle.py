@@ -130,8 +130,8 @@ def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optiona
 
     build_model(params) -> (drift, dispersion, m_and_cov, m0, P0, H') as chirpgp_b200.models.build_*; ``transform`` maps
     the unconstrained theta to params (default: the reference's softplus ``g``).  The objective is the SUM of the nll over
-    all chirps in ``ys``; with ``reduce_group`` (a torch.distributed process group) chirps are sharded over ranks and the
-    scalar objective and its 6-vector gradient are all-reduced -- the only collective on this path.
+    all chirps in ``ys`` (this rank's shard when torch.distributed is initialised: the scalar objective and its 6-vector
+    gradient are then summed over ranks with one all-reduce -- the only collective on this path).
 
     Returns (theta_opt (numpy), scipy OptimizeResult); ``result.success`` follows the reference's convention
     (tetralith/jobs/ekfs_mle.py:49, :75-78: a failed fit is reported, not raised)."""
@@ -146,12 +146,9 @@ def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optiona
         _, _, m_and_cov, m0, P0, _ = build_model(transform(theta))
         val = ekf_nll(m_and_cov, H, Xi, m0, P0, dt, ys_t).sum()
         grad, = torch.autograd.grad(val, theta)
-        packed = torch.cat([val.detach().reshape(1), grad])
-        if reduce_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=reduce_group)
-        packed = packed.cpu().numpy()
-        return float(packed[0]), packed[1:].copy()
+        from .distributed import allreduce_objective
+        v, gr = allreduce_objective(val.detach(), grad, group=reduce_group)
+        return float(v.cpu()), gr.cpu().numpy().copy()
 
     res = scipy.optimize.minimize(fun, np.asarray(init_theta, dtype=np.float64), jac=True, method='L-BFGS-B',
                                   options={'maxiter': maxiter})
