@@ -36,6 +36,9 @@ N_SIGMA = 81
 METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
 UNIT = 'steps/s'
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one ghf_filter_kernel launch (ncu --set full, profiles/r1_ncu_summary.txt)
+NCU_TRAFFIC_BYTES = 494_872_504      # 25.5 MB read + 469.3 MB written; algorithmic: 552.8 MB (nell + ys counted, L2 absorbs part)
+
 # algorithmic bytes / flops per chirp time-step (DESIGN.md "Roofline accounting")
 BYTES_FILTER = 8 + 8 * (D + D * D + 1)          # ys in, mf + Pf + nell out                      = 176
 BYTES_SMOOTHER = 2 * 8 * (D + D * D)            # mf, Pf in; ms, Ps out                          = 320
@@ -227,9 +230,45 @@ def run_ours(args):
     ms_step = statistics.mean(t_step)
     ms_filter = statistics.mean(t_filter)
 
-    # ---- end-to-end: pinned host ys -> device -> filter -> smoother -> pinned host (mss, Pss)
-    e2e_ms = []
-    for i in range(max(1, min(args.steps, 5)) + 1):
+    # ---- end-to-end through the public API: every step copies its inputs from pinned host memory, filters, smooths and
+    # copies the smoothed means / covariances back to pinned host memory.  Steps are issued on two alternating CUDA
+    # streams (what a user who processes batch after batch does), so the device->host copy of step i overlaps the
+    # filter of step i+1; all copies of all steps are inside the timed region.
+    n_e2e = max(4, min(args.steps, 10))
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    outs = [(mss_host, Pss_host),
+            (torch.empty((B_PER_GPU, T, D), dtype=torch.float64).pin_memory(),
+             torch.empty((B_PER_GPU, T, D, D), dtype=torch.float64).pin_memory())]
+
+    def e2e_step(i):
+        st = streams[i % 2]
+        with torch.cuda.stream(st):
+            ys_d = ys_host.to(dev, non_blocking=True)
+            f = cg.sgp_filter(m_and_cov, sgps, H, XI, m0, P0, DT, ys_d)
+            s = cg.sgp_smoother(m_and_cov, sgps, f[0], f[1], DT)
+            outs[i % 2][0].copy_(s[0], non_blocking=True)
+            outs[i % 2][1].copy_(s[1], non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    flush.fill_(1.)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e0 = ev(); e0.record()
+    for st in streams:
+        st.wait_event(e0)
+    for i in range(n_e2e):
+        e2e_step(i)
+    e1 = ev()
+    for st in streams:
+        torch.cuda.current_stream(dev).wait_stream(st)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_e2e = e0.elapsed_time(e1) / n_e2e
+    ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_e2e
+    # single-step latency (one stream, no overlap) for reference; first pass warms the default stream's allocator pool
+    for _ in range(2):
         flush.fill_(1.)
         torch.cuda.synchronize(dev)
         e0, e1 = ev(), ev()
@@ -241,10 +280,8 @@ def run_ours(args):
         Pss_host.copy_(s[1], non_blocking=True)
         e1.record()
         torch.cuda.synchronize(dev)
-        if i > 0:
-            e2e_ms.append(e0.elapsed_time(e1))
+        ms_e2e_single = e0.elapsed_time(e1)
         del f, s, ys_d
-    ms_e2e = statistics.mean(e2e_ms)
 
     # ---- FP64 peak (DFMA-only kernel) on this GPU
     L = _native.lib()
@@ -304,15 +341,17 @@ def run_ours(args):
                        'l2': 'flushed between timed steps (256 MiB write)'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': B_PER_GPU * T * 8,
-                    'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D),
-                    'what': 'pinned host ys -> cg.sgp_filter -> cg.sgp_smoother -> pinned host (mss, Pss)'},
+                    'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D), 'steps': n_e2e,
+                    'ms_per_step_wall_clock': ms_e2e_wall, 'ms_single_step_latency': ms_e2e_single,
+                    'what': 'pinned host ys -> cg.sgp_filter -> cg.sgp_smoother -> pinned host (mss, Pss); steps issued on '
+                            'two alternating streams so the D2H copy of one step overlaps the filter of the next'},
             'gpu_launches': args.steps * 3,
-            'kernels_per_step': ['sgp_filter_kernel', 'sgp_gain_kernel', 'smoother_sweep_kernel'],
-            'roofline': {'bound': 'hbm', 'kernel': 'sgp_filter_kernel<ModelLCD<1>,32,share>', 'achieved': ach_gbs,
-                         'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': None,
+            'kernels_per_step': ['ghf_filter_kernel<1,3>', 'sgp_gain_kernel<ModelLCD<1>,3>', 'smoother_sweep_warp_kernel<4>'],
+            'roofline': {'bound': 'hbm', 'kernel': 'ghf_filter_kernel<1,3> (sgp_filter, warp per chirp)', 'achieved': ach_gbs,
+                         'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': NCU_TRAFFIC_BYTES,
                          'peak_source': hbm_src, 'kernel_ms': ms_filter,
                          'algorithmic_bytes_per_step': BYTES_FILTER},
-            'roofline_fp64': {'bound': 'fp64', 'kernel': 'sgp_filter_kernel', 'achieved': ach_tf, 'peak': fp64_peak,
+            'roofline_fp64': {'bound': 'fp64', 'kernel': 'ghf_filter_kernel<1,3>', 'achieved': ach_tf, 'peak': fp64_peak,
                               'unit': 'TFLOP/s', 'frac': ach_tf / fp64_peak if fp64_peak else None,
                               'flops_per_step': flops_per_step('sgp_filter'),
                               'peak_source': 'DFMA-only kernel measured in this run',

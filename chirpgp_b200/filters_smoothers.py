@@ -67,6 +67,45 @@ def _ptr(t):
 
 
 _sigma_cache = {}
+_h_cache = {}
+
+
+def _h_unit_index(H) -> int:
+    """j if H is exactly the unit vector e_j, else -1 (a kernel specialisation hint).  Device tensors are inspected
+    once per (storage, version) so that steady-state calls do not synchronise the stream."""
+    if isinstance(H, torch.Tensor) and H.is_cuda:
+        key = (H.data_ptr(), H._version, tuple(H.shape))
+        hit = _h_cache.get(key)
+        if hit is not None:
+            return hit
+        host = H.detach().cpu().numpy().reshape(-1)
+    else:
+        key = None
+        host = (H.detach().numpy() if isinstance(H, torch.Tensor) else np.asarray(H, dtype=np.float64)).reshape(-1)
+    ones = np.flatnonzero(host)
+    out = int(ones[0]) if ones.size == 1 and host[ones[0]] == 1. else -1
+    if key is not None:
+        if len(_h_cache) > 64:
+            _h_cache.clear()
+        _h_cache[key] = out
+    return out
+
+
+def _consts_on_device(model, dt, dev, *args):
+    """model.consts(dt) uploaded once per (model instance, dt, parameter versions): the constants are a handful of
+    doubles computed on the host; re-uploading them from pageable memory on every call would serialise the stream."""
+    params = [getattr(model, a, None) for a in ('lam', 'b', 'ell', 'sigma', 'F', 'Sigma', 'A')]
+    params = [t for t in params if isinstance(t, torch.Tensor)]
+    if any(t.requires_grad for t in params) or not hasattr(model, '__dict__'):
+        return _dev(model.consts(*args), dev)
+    key = (dt, str(dev), tuple((t.data_ptr(), t._version) for t in params))
+    cache = model.__dict__.setdefault('_dev_consts', {})
+    hit = cache.get(key)
+    if hit is None:
+        cache.clear()
+        hit = _dev(model.consts(*args), dev)
+        cache[key] = hit
+    return hit
 
 
 def _sigma_tables(sgps, dev):
@@ -213,9 +252,7 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
         ys_repeat = 1
         if B > 1 and len(out_lead) == 0:
             out_lead = (B,)
-    H_host = (H.detach().cpu().numpy() if isinstance(H, torch.Tensor) else np.asarray(H, dtype=np.float64)).reshape(-1)
-    ones = np.flatnonzero(H_host)
-    h_unit = int(ones[0]) if ones.size == 1 and H_host[ones[0]] == 1. else -1
+    h_unit = _h_unit_index(H)
     H_t = _dev(H, dev).reshape(-1)
     if m0_t.shape[-1] != d or P0_t.shape[-1] != d or H_t.shape[0] != d:
         raise ValueError('state dimension mismatch: model d=%d, m0 %s, P0 %s, H %s'
@@ -283,41 +320,41 @@ def kf(F, Sigma, H, Xi, m0, P0, ys) -> Tuple:
     """Kalman filter for 1-d measurements (filters_smoothers.py:145-184).
     Returns (mfs (T, d), Pfs (T, d, d), n_ell (T,)); n_ell is the cumulative negative log-likelihood."""
     model = LinearDisc(F, Sigma)
-    return _run_filter('kf', model, model.consts(), H, Xi, m0, P0, 0., ys)
+    return _run_filter('kf', model, _consts_on_device(model, None, _device()), H, Xi, m0, P0, 0., ys)
 
 
 def rts(F, Sigma, mfs, Pfs) -> Tuple:
     """RTS smoother (filters_smoothers.py:187-219)."""
     model = LinearDisc(F, Sigma)
-    return _run_smoother('rts', model, model.consts(), mfs, Pfs, 0.)
+    return _run_smoother('rts', model, _consts_on_device(model, None, _device()), mfs, Pfs, 0.)
 
 
 def ekf(cond_m_cov, H, Xi, m0, P0, dt, ys) -> Tuple:
     """Extended Kalman filter (filters_smoothers.py:222-264)."""
     dt = float(dt)
     model = _disc_model(cond_m_cov, _state_dim(m0), dt)
-    return _run_filter('ekf', model, model.consts(dt), H, Xi, m0, P0, dt, ys)
+    return _run_filter('ekf', model, _consts_on_device(model, dt, _device(), dt), H, Xi, m0, P0, dt, ys)
 
 
 def eks(cond_m_cov, mfs, Pfs, dt) -> Tuple:
     """Extended Kalman smoother (filters_smoothers.py:317-349)."""
     dt = float(dt)
     model = _disc_model(cond_m_cov, int(mfs.shape[-1]), dt)
-    return _run_smoother('eks', model, model.consts(dt), mfs, Pfs, dt)
+    return _run_smoother('eks', model, _consts_on_device(model, dt, _device(), dt), mfs, Pfs, dt)
 
 
 def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys) -> Tuple:
     """Sigma-point (Gauss--Hermite / cubature) filter (filters_smoothers.py:446-490)."""
     dt = float(dt)
     model = _disc_model(cond_m_cov, _state_dim(m0), dt)
-    return _run_filter('sgp_filter', model, model.consts(dt), H, Xi, m0, P0, dt, ys, sgps=sgps)
+    return _run_filter('sgp_filter', model, _consts_on_device(model, dt, _device(), dt), H, Xi, m0, P0, dt, ys, sgps=sgps)
 
 
 def sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt) -> Tuple:
     """Sigma-point smoother (filters_smoothers.py:493-531)."""
     dt = float(dt)
     model = _disc_model(cond_m_cov, int(mfs.shape[-1]), dt)
-    return _run_smoother('sgp_smoother', model, model.consts(dt), mfs, Pfs, dt, sgps=sgps)
+    return _run_smoother('sgp_smoother', model, _consts_on_device(model, dt, _device(), dt), mfs, Pfs, dt, sgps=sgps)
 
 
 def _qc(bm):

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .filters_smoothers import _device, _problem, _ptr
+from .filters_smoothers import _device, _problem, _ptr, _h_unit_index
 from .models import LCDModel, NC_LCD
 
 __all__ = ['ekf_nll', 'fit_mle']
@@ -115,10 +115,8 @@ def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = Fals
     consts_b = expand(consts, (NC_LCD,)).contiguous()
     m0_b = expand(m0_t, (d,)).contiguous()
     P0_b = expand(P0_t, (d, d)).contiguous()
-    H_host = (H.detach().cpu().numpy() if isinstance(H, torch.Tensor) else np.asarray(H, dtype=np.float64)).reshape(-1)
-    ones = np.flatnonzero(H_host)
-    h_unit = int(ones[0]) if ones.size == 1 and H_host[ones[0]] == 1. else -1
-    H_t = torch.as_tensor(H_host, device=dev)
+    h_unit = _h_unit_index(H)
+    H_t = _as_dev(H, dev).reshape(-1).contiguous()
     nll = _EkfNll.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every)
     return nll.reshape(out_shape)
 
