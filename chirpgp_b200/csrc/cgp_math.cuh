@@ -60,6 +60,29 @@ CGP_MDEV double fast_exp(double x) {
     return (x != x) ? x : res;                                            // fmin/fmax drop NaN: put it back
 }
 
+// ---- log(v) for normal positive v (fdlibm's e_log.c kernel with the division replaced by fast_rcp); +inf -> +inf,
+// NaN -> NaN.  Used for log(exp(x) + 1), where v >= 1.
+CGP_MDEV double fast_log_pos(double v) {
+    int hx = __double2hiint(v);
+    const int lx = __double2loint(v);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    const double mth = __hiloint2double(hx | (i ^ 0x3ff00000), lx);      // m in [sqrt(2)/2, sqrt(2))
+    k += i >> 20;
+    const double dk = (double)k;
+    const double f = mth - 1.;
+    const double s = f * fast_rcp(2. + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
+                              6.666666666666735130e-01);
+    const double R = t1 + t2;
+    const double hfsq = 0.5 * f * f;
+    const double res = fma(dk, 6.93147180369123816490e-01, -((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+    return (v < 1.7976931348623157e308) ? res : v;                       // inf / NaN pass through
+}
+
 // series branch of fast_softplus (valid for 3 <= x <= 700)
 CGP_MDEV double softplus_series(double x) {
     const double u = fast_exp(-x);
@@ -79,22 +102,23 @@ CGP_MDEV double softplus_series(double x) {
 // ---- softplus g(x) = log(exp(x) + 1) (models.py:50).  For x >= 3:  g = x + log1p(u), u = exp(-x) <= 0.05, with
 // the alternating series of log1p (12 terms, < 1e-17 truncation).  Else (and for x > 700, where the reference's
 // naive form overflows to +inf, and NaN) the reference's literal formula.
+CGP_MDEV double softplus_general(double x) { return fast_log_pos(fast_exp(x) + 1.); }   // the reference's formula
 CGP_MDEV double fast_softplus(double x) {
-    if (!(x >= 3. && x <= 700.)) return log(exp(x) + 1.);
+    if (!(x >= 3. && x <= 700.)) return softplus_general(x);
     return softplus_series(x);
 }
 // Warp-uniform variant: every lane of the (fully active) warp takes the same side, so the loop body of the
 // sequential filters keeps one straight-line fast path (no divergence bookkeeping).
 CGP_MDEV double fast_softplus_warp(double x) {
     if (__all_sync(0xffffffffu, x >= 3. && x <= 700.)) return softplus_series(x);
-    return log(exp(x) + 1.);
+    return softplus_general(x);
 }
 // softplus and its derivative sigmoid(x) = e^x / (e^x + 1) = 1 / (1 + e^-x)
 CGP_MDEV void fast_softplus_sigmoid(double x, double &g, double &sg) {
     if (!(x >= 3. && x <= 700.)) {
-        const double ex = exp(x), d = ex + 1.;
-        g = log(d);
-        sg = ex / d;
+        const double ex = fast_exp(x), d = ex + 1.;
+        g = fast_log_pos(d);
+        sg = (ex < 1.7976931348623157e308) ? ex * fast_rcp(d) : 1.;     // e^x / (e^x + 1); inf / inf would be NaN
         return;
     }
     const double u = fast_exp(-x);
