@@ -48,93 +48,108 @@ CGP_DEV double nll_increment(double S, double r) {
     return (log(kTwoPi * sc2) + r * r / sc2) * 0.5;
 }
 
-// ------------------------------------------------------------------------------------------------ GH filter, warp per chirp
-// sgp_filter (filters_smoothers.py:446-490) for ModelLCD<NH> with a Gauss-Hermite table of P nodes per dimension
-// whose P^(D-1) base indices fit one warp.  Lane `l` owns base index l: its P points (l + c * nb) share
-// chi[0..D-2] and the transcendental part of the model; all table entries the lane needs sit in registers.
-//
-// Output staging: every lane holds a replica of (m, P, S, r).  Lane 0 drops (m, P) of each step into a 32-step
-// shared-memory ring and lane (t mod 32) keeps (S, r) of step t; every 32 steps the warp evaluates the 32 nll
-// increments in SIMD (one log / sqrt / div per lane instead of one per step on the critical path), accumulates
-// them in the reference's sequential order, and writes mfs / Pfs / nell with coalesced 16-byte stores.
-template <int NH, int P, bool H_E1, int DBG = 0>   // DBG != 0: timing experiments only (profiles/microbench/ghf_ablate.cu)
-__global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, const FilterIO io) {
-    using Model = ModelLCD<NH>;
-    constexpr int D = Model::D, V = Model::V, NS = NSym<D>::value, NA = D + NS, DD = D * D, REC = D + DD;
-    constexpr int PITCH = 33;
-    constexpr int KP = (NA <= 16) ? 16 : 32;          // lanes per "half" in the shared-memory reduction
+// ------------------------------------------------------------------------------------------------ warp-per-chirp sigma-point filters
+// All 32 lanes' partial sums a[0..NA) are combined through shared memory in a fixed tree order; every lane gets
+// the same totals.  red: [NA][33] doubles, res: [NA rounded up to even] doubles (16-byte aligned).
+template <int NA>
+CGP_DEV void warp_sum_smem(const double (&a)[NA], double (*red)[33], double *res, int lane, double (&tot)[NA]) {
+    constexpr int KP = (NA <= 16) ? 16 : 32;          // lanes per "half"
     constexpr int HS = 32 / KP;                       // halves: each sums 32 / HS partials
-    __shared__ double red[NA][PITCH];
-    __shared__ __align__(16) double res[(NA + 1) & ~1];
-    __shared__ __align__(16) double ring[32][REC];
-    __shared__ double nl[32];
-    const int lane = threadIdx.x;
-    const int64_t b = blockIdx.x;
-    Model mdl;
-    mdl.load(p.consts + b * p.consts_stride, p.dt);
-    double m[D], Pc[NS], H[D];
-    load_vec<D>(p.m0 + b * p.m0_stride, m);
-    load_sym<D>(p.P0 + b * p.P0_stride, Pc);
-    CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
-    // per-lane table entries
-    int nb = 1;
-    CGP_UNROLL for (int i = 0; i < D - 1; i++) nb *= P;
-    const bool has_pts = lane < nb;
-    double xb[D - 1], wl[P], xlast[P];
-    CGP_UNROLL for (int r = 0; r < D - 1; r++) xb[r] = has_pts ? p.sig_xi[lane * D + r] : 0.;
-    CGP_UNROLL for (int c = 0; c < P; c++) {
-        wl[c] = has_pts ? p.sig_w[lane + c * nb] : 0.;
-        xlast[c] = p.sig_xi[(c * nb) * D + (D - 1)];
+    constexpr int CNT = 32 / HS;
+    CGP_UNROLL for (int k = 0; k < NA; k++) red[k][lane] = a[k];
+    __syncwarp();
+    const int k = lane % KP, h = lane / KP;
+    CGP_UNROLL for (int k0 = 0; k0 < NA; k0 += KP) {
+        const int kk = k0 + k;
+        const bool ok = kk < NA;
+        double v[CNT];
+        CGP_UNROLL for (int j = 0; j < CNT; j++) v[j] = red[ok ? kk : 0][h * CNT + j];
+        CGP_UNROLL for (int w2 = 1; w2 < CNT; w2 <<= 1)
+            CGP_UNROLL for (int j = 0; j + w2 < CNT; j += 2 * w2) v[j] += v[j + w2];
+        double sacc = v[0];
+        if (HS == 2) sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+        if (ok && h == 0) res[kk] = sacc;
     }
-    double Wl = 0.;
-    CGP_UNROLL for (int c = 0; c < P; c++) Wl += wl[c];
-    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
-    const int64_t T = p.T;
-    const bool store_state = io.mfs != nullptr;
-    const bool store_nell = io.nell != nullptr;
-    double carry = 0.;                 // cumulative nll up to the last flushed step
-    double Sk = 1., rk = 0.;           // (S, r) of the step this lane is responsible for
-    double yv = (lane < T) ? __ldg(y + lane) : 0.;      // 32 measurements per load, broadcast by shuffle
-    for (int64_t t = 0; t < T; t++) {
-        const int slot = (int)(t & 31);
-        const double yt = __shfl_sync(0xffffffffu, yv, slot);
-        if (slot == 31 && t + 1 < T) yv = (t + 1 + lane < T) ? __ldg(y + t + 1 + lane) : 0.;
-        // ---- sigma points of this lane
-        double L[NS];
-        if constexpr (DBG == 3) { CGP_UNROLL for (int i = 0; i < NS; i++) L[i] = Pc[i]; }
-        else chol_lower_sym_rsqrt<D>(Pc, L);
-        double chi[D];
+    __syncwarp();
+    CGP_UNROLL for (int k2 = 0; k2 < NA; k2 += 2) {
+        if (k2 + 1 < NA) {
+            const double2 v = *reinterpret_cast<const double2 *>(&res[k2]);
+            tot[k2] = v.x; tot[k2 + 1] = v.y;
+        } else {
+            tot[k2] = res[k2];
+        }
+    }
+}
+
+// Per-lane slice of a Gauss-Hermite table with P nodes per dimension (quadratures.py:157-196, dimension 0 fastest):
+// lane l owns base index l < nb = P^(D-1); its P points l + c nb share xi[0..D-2] and differ in the last coordinate.
+template <int D, int P> struct GhLane {
+    double xb[D - 1], wl[P], xlast[P], Wl;
+    CGP_DEV void load(const CgpProblem &p, int lane) {
+        int nb = 1;
+        CGP_UNROLL for (int i = 0; i < D - 1; i++) nb *= P;
+        const bool has = lane < nb;
+        CGP_UNROLL for (int r = 0; r < D - 1; r++) xb[r] = has ? p.sig_xi[lane * D + r] : 0.;
+        Wl = 0.;
+        CGP_UNROLL for (int c = 0; c < P; c++) {
+            wl[c] = has ? p.sig_w[lane + c * nb] : 0.;
+            xlast[c] = p.sig_xi[(c * nb) * D + (D - 1)];
+            Wl += wl[c];
+        }
+    }
+    // chi[0..D-2] of the lane's base index and the partial dot product of the last row
+    CGP_DEV void points(const double (&m)[D], const double (&L)[NSym<D>::value], double (&chi)[D], double &slast) const {
         CGP_UNROLL for (int r = 0; r < D - 1; r++) {
             double s = L[sidx(r, 0)] * xb[0];
             CGP_UNROLL for (int c = 1; c <= r; c++) s = fma(L[sidx(r, c)], xb[c], s);
             chi[r] = m[r] + s;
         }
-        double slast = L[sidx(D - 1, 0)] * xb[0];
+        slast = L[sidx(D - 1, 0)] * xb[0];
         CGP_UNROLL for (int c = 1; c < D - 1; c++) slast = fma(L[sidx(D - 1, c)], xb[c], slast);
+    }
+};
+
+// Discrete-time prediction (filters_smoothers.py:88-121) for ModelLCD<NH>: one warp, lane = base index.
+template <int NH, int P, int DBG = 0> struct GhPredictLCD {
+    using Model = ModelLCD<NH>;
+    static constexpr int D = Model::D, V = Model::V, NS = NSym<D>::value, NA = D + NS;
+    Model mdl;
+    GhLane<D, P> tab;
+    CGP_DEV void load(const CgpProblem &p, int64_t b, int lane) {
+        mdl.load(p.consts + b * p.consts_stride, p.dt);
+        tab.load(p, lane);
+    }
+    CGP_DEV void predict(double (*red)[33], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&mp)[D],
+                         double (&Pp)[NS]) const {
+        double L[NS];
+        if constexpr (DBG == 3) { CGP_UNROLL for (int i = 0; i < NS; i++) L[i] = Pc[i]; }
+        else chol_lower_sym_rsqrt<D>(Pc, L);
+        double chi[D], slast;
+        tab.points(m, L, chi, slast);
         typename Model::Trig trig;
         if constexpr (DBG == 2) { CGP_UNROLL for (int k = 0; k < NH; k++) { trig.c[k] = 0.99 + 1e-3 * chi[V]; trig.s[k] = 0.05; } }
         else trig = mdl.template prep_v<true>(chi[V]);
         // weighted sums over this lane's P points: only chi[D-1] and the Matern rows ev[V], ev[V+1] differ between
-        // them, so the sums factor through W = sum w_c (precomputed), S_t = sum w_c ev[V+t]_c and three quadratic terms
+        // them, so the sums factor through W = sum w_c, S_t = sum w_c ev[V+t]_c and three quadratic terms
         double a[NA];
         {
             double ev[D], S0 = 0., S1 = 0., q00 = 0., q10 = 0., q11 = 0.;
             CGP_UNROLL for (int c = 0; c < P; c++) {
-                chi[D - 1] = m[D - 1] + fma(L[sidx(D - 1, D - 1)], xlast[c], slast);
+                chi[D - 1] = m[D - 1] + fma(L[sidx(D - 1, D - 1)], tab.xlast[c], slast);
                 if (c == 0) mdl.mean_with(trig, chi, ev); else mdl.mean_tail(chi, ev);
-                const double w = wl[c];
+                const double w = tab.wl[c];
                 S0 = fma(w, ev[V], S0);
                 S1 = fma(w, ev[V + 1], S1);
                 q00 = fma(w, ev[V] * ev[V] + mdl.sig(V, V), q00);
                 q10 = fma(w, ev[V + 1] * ev[V] + mdl.sig(V + 1, V), q10);
                 q11 = fma(w, ev[V + 1] * ev[V + 1] + mdl.sig(V + 1, V + 1), q11);
             }
-            CGP_UNROLL for (int r = 0; r < V; r++) a[r] = Wl * ev[r];
+            CGP_UNROLL for (int r = 0; r < V; r++) a[r] = tab.Wl * ev[r];
             a[V] = S0; a[V + 1] = S1;
             CGP_UNROLL for (int r = 0; r < V; r++) CGP_UNROLL for (int q = 0; q <= r; q++) {
                 double v = ev[r] * ev[q];
                 if (Model::has_sig(r, q)) v += mdl.sig(r, q);
-                a[D + sidx(r, q)] = Wl * v;
+                a[D + sidx(r, q)] = tab.Wl * v;
             }
             CGP_UNROLL for (int q = 0; q < V; q++) {
                 a[D + sidx(V, q)] = ev[q] * S0;
@@ -142,41 +157,116 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
             }
             a[D + sidx(V, V)] = q00; a[D + sidx(V + 1, V)] = q10; a[D + sidx(V + 1, V + 1)] = q11;
         }
-        // ---- combine the 32 lanes' partial sums through shared memory (fixed tree order)
         double tot[NA];
         if constexpr (DBG == 1) { CGP_UNROLL for (int k = 0; k < NA; k++) tot[k] = a[k] * 27.; }
-        else {
-        CGP_UNROLL for (int k = 0; k < NA; k++) red[k][lane] = a[k];
-        __syncwarp();
-        {
-            const int k = lane % KP, h = lane / KP;
-            constexpr int CNT = 32 / HS;
-            CGP_UNROLL for (int k0 = 0; k0 < NA; k0 += KP) {
-                const int kk = k0 + k;
-                double v[CNT];
-                const bool ok = kk < NA;
-                CGP_UNROLL for (int j = 0; j < CNT; j++) v[j] = red[ok ? kk : 0][h * CNT + j];
-                CGP_UNROLL for (int w2 = 1; w2 < CNT; w2 <<= 1)
-                    CGP_UNROLL for (int j = 0; j + w2 < CNT; j += 2 * w2) v[j] += v[j + w2];
-                double s = v[0];
-                if (HS == 2) s += __shfl_xor_sync(0xffffffffu, s, 16);
-                if (ok && h == 0) res[kk] = s;
-            }
-        }
-        __syncwarp();
-        CGP_UNROLL for (int k = 0; k < NA; k += 2) {
-            if (k + 1 < NA) {
-                const double2 v = *reinterpret_cast<const double2 *>(&res[k]);
-                tot[k] = v.x; tot[k + 1] = v.y;
-            } else {
-                tot[k] = res[k];
-            }
-        }
-        }
-        double mp[D], Pp[NS];
+        else warp_sum_smem<NA>(a, red, res, lane, tot);
         CGP_UNROLL for (int r = 0; r < D; r++) mp[r] = tot[r];
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++)
             Pp[sidx(r, q)] = fma(-mp[r], mp[q], tot[D + sidx(r, q)]);
+    }
+};
+
+// rhs of the continuous-discrete sigma-point moment ODE (filters_smoothers.py:124-137) for ModelSDE<NH>, one warp:
+//   dm = sum_i w_i a(chi_i),   Q = sum_i w_i (chi_i - m) a(chi_i)^T,   dP = Q + Q^T + b b^T.
+// The drift's chirp rows depend on chi[0..V] only (shared by the lane's P points); a[V] = chi[D-1] and
+// a[V+1] = -gamma^2 chi[V] - 2 gamma chi[D-1] vary with the last coordinate.
+template <int NH, int P> struct GhRhsSDE {
+    using Model = ModelSDE<NH>;
+    static constexpr int D = Model::D, V = Model::V, NS = NSym<D>::value, NA = D + D * D;
+    Model mdl;
+    GhLane<D, P> tab;
+    double Qc[NS];
+    CGP_DEV void load(const CgpProblem &p, int64_t b, int lane) {
+        mdl.load(p.consts + b * p.consts_stride);
+        tab.load(p, lane);
+        load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
+    }
+    CGP_DEV void rhs(double (*red)[33], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&dm)[D],
+                     double (&dP)[NS]) const {
+        double L[NS];
+        chol_lower_sym_rsqrt<D>(Pc, L);
+        double chi[D], slast;
+        tab.points(m, L, chi, slast);
+        const double w = (kTwoPi * fast_softplus_warp(chi[V])) * mdl.fs;
+        double f[D];
+        chi[D - 1] = 0.;
+        mdl.drift_w(w, chi, f);                         // f[0..V-1] final; f[V], f[V+1] recomputed per point below
+        double S2 = 0., S3 = 0., DL = 0., q2 = 0., q3 = 0.;
+        CGP_UNROLL for (int c = 0; c < P; c++) {
+            const double cl = m[D - 1] + fma(L[sidx(D - 1, D - 1)], tab.xlast[c], slast);
+            const double f2 = cl, f3 = fma(-mdl.tg, cl, -mdl.g2 * chi[V]);
+            const double dl = cl - m[D - 1], wc = tab.wl[c];
+            S2 = fma(wc, f2, S2);
+            S3 = fma(wc, f3, S3);
+            DL = fma(wc, dl, DL);
+            q2 = fma(wc, dl * f2, q2);
+            q3 = fma(wc, dl * f3, q3);
+        }
+        double a[NA];
+        CGP_UNROLL for (int r = 0; r < V; r++) a[r] = tab.Wl * f[r];
+        a[V] = S2; a[V + 1] = S3;
+        CGP_UNROLL for (int r = 0; r < D - 1; r++) {
+            const double dr = chi[r] - m[r];
+            CGP_UNROLL for (int c = 0; c < V; c++) a[D + r * D + c] = tab.Wl * (dr * f[c]);
+            a[D + r * D + V] = dr * S2;
+            a[D + r * D + V + 1] = dr * S3;
+        }
+        CGP_UNROLL for (int c = 0; c < V; c++) a[D + (D - 1) * D + c] = DL * f[c];
+        a[D + (D - 1) * D + V] = q2;
+        a[D + (D - 1) * D + V + 1] = q3;
+        double tot[NA];
+        warp_sum_smem<NA>(a, red, res, lane, tot);
+        CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = tot[r];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+            dP[sidx(r, c)] = (tot[D + r * D + c] + tot[D + c * D + r]) + Qc[sidx(r, c)];
+    }
+};
+
+// sgp_filter (filters_smoothers.py:446-490, Pred = GhPredictLCD) / cd_sgp_filter (:534-582, Pred = GhRhsSDE + RK4) with a
+// Gauss-Hermite table whose P^(D-1) base indices fit one warp.  ONE WARP PER CHIRP; mean, covariance and Cholesky
+// factor are replicated in every lane.
+//
+// Output staging: lane 0 drops (m, P) of each step into a 32-step shared-memory ring and lane (t mod 32) keeps (S, r)
+// of step t; every 32 steps the warp evaluates the 32 nll increments in SIMD (one log / sqrt / div per lane instead of
+// one per step on the critical path), accumulates them in the reference's sequential order, and writes mfs / Pfs /
+// nell with coalesced 16-byte stores.
+template <class Pred, bool CD, bool H_E1>
+__global__ void __launch_bounds__(32) gh_warp_filter_kernel(const CgpProblem p, const FilterIO io) {
+    constexpr int D = Pred::D, NS = NSym<D>::value, NA = Pred::NA, DD = D * D, REC = D + DD;
+    __shared__ double red[NA][33];
+    __shared__ __align__(16) double res[(NA + 1) & ~1];
+    __shared__ __align__(16) double ring[32][REC];
+    __shared__ double nl[32];
+    const int lane = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    Pred pred;
+    pred.load(p, b, lane);
+    double m[D], Pc[NS], H[D];
+    load_vec<D>(p.m0 + b * p.m0_stride, m);
+    load_sym<D>(p.P0 + b * p.P0_stride, Pc);
+    CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
+    const int64_t T = p.T;
+    const bool store_state = io.mfs != nullptr;
+    const bool store_nell = io.nell != nullptr;
+    const double dt = p.dt;
+    double carry = 0.;                 // cumulative nll up to the last flushed step
+    double Sk = 1., rk = 0.;           // (S, r) of the step this lane is responsible for
+    double yv = (lane < T) ? __ldg(y + lane) : 0.;      // 32 measurements per load, broadcast by shuffle
+    for (int64_t t = 0; t < T; t++) {
+        const int slot = (int)(t & 31);
+        const double yt = __shfl_sync(0xffffffffu, yv, slot);
+        if (slot == 31 && t + 1 < T) yv = (t + 1 + lane < T) ? __ldg(y + t + 1 + lane) : 0.;
+        double mp[D], Pp[NS];
+        if constexpr (CD) {
+            CGP_UNROLL for (int i = 0; i < D; i++) mp[i] = m[i];
+            CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = Pc[i];
+            rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+                pred.rhs(red, res, lane, mm, PP, dm, dP);
+            }, mp, Pp, dt);
+        } else {
+            pred.predict(red, res, lane, m, Pc, mp, Pp);
+        }
         // ---- measurement update (filters_smoothers.py:55-68)
         double S, resid;
         linear_update_fast<D, H_E1>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
@@ -210,6 +300,80 @@ __global__ void __launch_bounds__(32) ghf_filter_kernel(const CgpProblem p, cons
         }
     }
     if (store_nell && io.nell_last_only && lane == 0) io.nell[b] = carry;
+}
+
+// cd_sgp_smoother (filters_smoothers.py:585-632) for ModelSDE<NH> with a Gauss-Hermite table: one warp per chirp, RK4
+// backwards in time.  rhs (:615-621): Gm = Pf^{-1} gamma (hoisted out of the 4 stages), (_m, _P) = cd_sgp_common(m, P),
+// dm = _m + Gm^T (m - mf),  dP = _P + Gm^T P + P Gm - 2 gamma.   Results go through a 32-step ring like the filter.
+template <int NH, int P>
+__global__ void __launch_bounds__(32) cd_ghs_warp_kernel(const CgpProblem p, const SmootherIO io) {
+    using Rhs = GhRhsSDE<NH, P>;
+    constexpr int D = Rhs::D, NS = NSym<D>::value, NA = Rhs::NA, DD = D * D, REC = D + DD;
+    __shared__ double red[NA][33];
+    __shared__ __align__(16) double res[(NA + 1) & ~1];
+    __shared__ __align__(16) double ring[32][REC];
+    const int lane = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const int64_t T = p.T;
+    Rhs rhs;
+    rhs.load(p, b, lane);
+    double Qf[D][D];
+    sym_to_full<D>(rhs.Qc, Qf);
+    double ms[D], Ps[NS];
+    load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
+    load_sym<D>(io.Pfs + (b * T + T - 1) * DD, Ps);
+    if (lane == 0) {
+        store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
+        store_sym<D>(io.Pss + (b * T + T - 1) * DD, Ps);
+    }
+    const double ndt = -p.dt;
+    // walk backwards; ring slot s holds step t with (t & 31) == s; flush when a 32-aligned block is complete
+    for (int64_t t = T - 2; t >= 0; t--) {
+        double mf[D], Pf[D][D], Lf[D][D], rinv[D], Gm[D][D];
+        load_vec<D>(io.mfs + (b * T + t) * D, mf);
+        load_mat<D>(io.Pfs + (b * T + t) * DD, Pf);
+        chol_lower_rsqrt<D>(Pf, Lf, rinv);
+        CGP_UNROLL for (int c = 0; c < D; c++) {       // Gm = Pf^{-1} gamma, column by column
+            double col[D];
+            CGP_UNROLL for (int i = 0; i < D; i++) col[i] = Qf[i][c];
+            chol_solve_vec_rinv<D>(Lf, rinv, col);
+            CGP_UNROLL for (int i = 0; i < D; i++) Gm[i][c] = col[i];
+        }
+        rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+            double _m[D], _P[NS], W[D][D];
+            rhs.rhs(red, res, lane, mm, PP, _m, _P);
+            CGP_UNROLL for (int r = 0; r < D; r++) {
+                double s = Gm[0][r] * (mm[0] - mf[0]);
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[k][r], mm[k] - mf[k], s);
+                dm[r] = _m[r] + s;
+            }
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) {      // W = Gm^T P
+                double s = Gm[0][r] * PP[sidx(0, c)];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[k][r], PP[sidx(k, c)], s);
+                W[r][c] = s;
+            }
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+                dP[sidx(r, c)] = ((_P[sidx(r, c)] + W[r][c]) + W[c][r]) - 2 * rhs.Qc[sidx(r, c)];
+        }, ms, Ps, ndt);
+        const int slot = (int)(t & 31);
+        if (lane == 0) {
+            store_vec<D>(&ring[slot][0], ms);
+            store_sym<D>(&ring[slot][D], Ps);
+        }
+        if (slot == 0 || t == 0) {
+            // steps [t, hi] are in the ring (hi = last step of this 32-block that is < T-1)
+            const int64_t hi = ((t | 31) < T - 2) ? (t | 31) : (T - 2);
+            const int n = (int)(hi - t + 1);
+            __syncwarp();
+            double2 *dm2 = reinterpret_cast<double2 *>(io.mss + (b * T + t) * D);
+            for (int i = lane; i < n * (D / 2); i += 32)
+                dm2[i] = *reinterpret_cast<const double2 *>(&ring[(slot + i / (D / 2)) & 31][2 * (i % (D / 2))]);
+            double2 *dP2 = reinterpret_cast<double2 *>(io.Pss + (b * T + t) * DD);
+            for (int i = lane; i < n * (DD / 2); i += 32)
+                dP2[i] = *reinterpret_cast<const double2 *>(&ring[(slot + i / (DD / 2)) & 31][D + 2 * (i % (DD / 2))]);
+            __syncwarp();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ smoother sweep, warp per chirp

@@ -27,6 +27,15 @@ int launch_cd_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s
         if constexpr (Model::kLinear) {
             return launch_cd_sgp_one<Model, 32, 0>(p, io, s);
         } else {
+            if constexpr (Model::NH == 1) {
+                // chirp SDE, Gauss-Hermite order 3: tuned warp-per-chirp kernel (27 base indices, one per lane)
+                if (share) {
+                    using Rhs = GhRhsSDE<1, 3>;
+                    if (p.h_unit_index == 1) gh_warp_filter_kernel<Rhs, true, true><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    else gh_warp_filter_kernel<Rhs, true, false><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    return check_launch();
+                }
+            }
             if (share) return launch_cd_sgp_one<Model, 32, 3>(p, io, s);
             if (g == 8) return launch_cd_sgp_one<Model, 8, 0>(p, io, s);
             if (g == 16) return launch_cd_sgp_one<Model, 16, 0>(p, io, s);

@@ -30,8 +30,9 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
             if constexpr (Model::NH == 1) {
                 // headline path: chirp model, Gauss-Hermite order 3 -> 27 base indices, one per lane
                 if (share) {
-                    if (p.h_unit_index == 1) ghf_filter_kernel<1, 3, true><<<(unsigned)p.B, 32, 0, s>>>(p, io);
-                    else ghf_filter_kernel<1, 3, false><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    using Pred = GhPredictLCD<1, 3>;
+                    if (p.h_unit_index == 1) gh_warp_filter_kernel<Pred, false, true><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    else gh_warp_filter_kernel<Pred, false, false><<<(unsigned)p.B, 32, 0, s>>>(p, io);
                     return check_launch();
                 }
             }

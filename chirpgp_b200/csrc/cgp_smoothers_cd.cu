@@ -27,6 +27,12 @@ int launch_cd_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream
         if constexpr (Model::kLinear) {
             return launch_one<Model, 32, 0>(p, io, s);
         } else {
+            if constexpr (Model::NH == 1) {
+                if (share && aligned16(io.mss) && aligned16(io.Pss)) {
+                    cd_ghs_warp_kernel<1, 3><<<(unsigned)p.B, 32, 0, s>>>(p, io);
+                    return check_launch();
+                }
+            }
             if (share) return launch_one<Model, 32, 3>(p, io, s);
             if (g == 8) return launch_one<Model, 8, 0>(p, io, s);
             if (g == 16) return launch_one<Model, 16, 0>(p, io, s);

@@ -7,9 +7,9 @@
 using namespace cgp;
 template <int DBG> float run(const CgpProblem &p, const FilterIO &io) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    ghf_filter_kernel<1, 3, true, DBG><<<(unsigned)p.B, 32>>>(p, io);
+    gh_warp_filter_kernel<GhPredictLCD<1, 3, DBG>, false, true><<<(unsigned)p.B, 32>>>(p, io);
     cudaEventRecord(e0);
-    ghf_filter_kernel<1, 3, true, DBG><<<(unsigned)p.B, 32>>>(p, io);
+    gh_warp_filter_kernel<GhPredictLCD<1, 3, DBG>, false, true><<<(unsigned)p.B, 32>>>(p, io);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("DBG=%d  %8.3f ms  %7.0f cycles/step  (%s)\n", DBG, ms, ms * 1e-3 * 1.965e9 / p.T, cudaGetErrorString(cudaGetLastError()));
