@@ -502,4 +502,202 @@ __global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProble
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CD-EKF / CD-EKS, 16 lanes per chirp
+// cd_ekf (filters_smoothers.py:352-397) and cd_eks (:400-443) for the chirp SDE (d = 4) when the batch is too small to
+// fill the GPU with one thread per chirp: a HALF-WARP owns one chirp, lane (i, j) = (l / 4, l % 4) holds the covariance
+// entry P_ij, the mean is replicated.  X = J P needs column j of P (shuffles from lanes (k, j)) and the sparse row i of
+// the drift Jacobian; dP = X + X^T + b b^T needs X_ji (one shuffle).  Exactly the thread-per-chirp arithmetic, spread
+// over 16 lanes; the 16 entries of a step are written with one coalesced 128-byte store.
+struct HalfWarp {
+    int l, i, j, base;          // lane within the half-warp, row, column, first lane of the half within the warp
+    CGP_DEV explicit HalfWarp(int lane) : l(lane & 15), i((lane & 15) >> 2), j(lane & 3), base(lane & 16) {}
+    CGP_DEV double get(double v, int src) const { return __shfl_sync(0xffffffffu, v, base + src); }
+    CGP_DEV double sum16(double v) const {
+        CGP_UNROLL for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        return v;
+    }
+};
+
+// row i of the drift Jacobian of the chirp SDE (models.py:104-110): J = [[-lam, -w, -w' u1, 0], [w, -lam, w' u0, 0],
+// [0, 0, 0, 1], [0, 0, -gamma^2, -2 gamma]]
+CGP_DEV void chirp_drift_and_jrow(const ModelSDE<1> &mdl, const HalfWarp &hw, const double (&m)[4], double (&a)[4], double (&jr)[4]) {
+    double gv, sg;
+    softplus_and_sigmoid(m[2], gv, sg);
+    const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
+    mdl.drift_w(w, m, a);
+    const bool r0 = hw.i == 0, r1 = hw.i == 1, r2 = hw.i == 2;
+    jr[0] = r0 ? -mdl.lam : (r1 ? w : 0.);
+    jr[1] = r0 ? -w : (r1 ? -mdl.lam : 0.);
+    jr[2] = r0 ? -dw * m[1] : (r1 ? dw * m[0] : (r2 ? 0. : -mdl.g2));
+    jr[3] = (r0 || r1) ? 0. : (r2 ? 1. : -mdl.tg);
+}
+// (A P)_ij for the lane's (i, j), with `arow` = row i of A and P distributed one entry per lane
+CGP_DEV double row_times_P(const HalfWarp &hw, const double (&arow)[4], double Pe) {
+    double s = arow[0] * hw.get(Pe, hw.j);
+    CGP_UNROLL for (int k = 1; k < 4; k++) s = fma(arow[k], hw.get(Pe, 4 * k + hw.j), s);
+    return s;
+}
+template <class Ode> CGP_DEV void rk4_step_lane(Ode &&ode, double (&m)[4], double &Pe, double dt) {
+    double km[4], kP, am[4], aP, tm[4], tP;
+    ode(m, Pe, km, kP);
+    CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = km[q]; tm[q] = m[q] + dt * km[q] * 0.5; }
+    aP = kP; tP = Pe + dt * kP * 0.5;
+    ode(tm, tP, km, kP);
+    CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = am[q] + 2 * km[q]; tm[q] = m[q] + dt * km[q] * 0.5; }
+    aP = aP + 2 * kP; tP = Pe + dt * kP * 0.5;
+    ode(tm, tP, km, kP);
+    CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = am[q] + 2 * km[q]; tm[q] = m[q] + dt * km[q]; }
+    aP = aP + 2 * kP; tP = Pe + dt * kP;
+    ode(tm, tP, km, kP);
+    CGP_UNROLL for (int q = 0; q < 4; q++) m[q] = m[q] + dt * (am[q] + km[q]) / 6;
+    Pe = Pe + dt * (aP + kP) / 6;
+}
+
+template <int NH>   // NH == 1: the chirp SDE (d = 4 -> 16 covariance entries -> half a warp)
+__global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, const FilterIO io) {
+    static_assert(NH == 1, "16 lanes per chirp need d == 4");
+    using Model = ModelSDE<1>;
+    constexpr int D = 4;
+    __shared__ double nl[2][16];
+    const int lane = threadIdx.x;
+    const HalfWarp hw(lane);
+    const int half = lane >> 4;
+    const int64_t gid = (int64_t)blockIdx.x * 2 + half;
+    const bool active = gid < p.B;
+    const int64_t b = active ? gid : p.B - 1;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride);
+    double m[D], H[D];
+    load_vec<D>(p.m0 + b * p.m0_stride, m);
+    CGP_UNROLL for (int q = 0; q < D; q++) H[q] = p.H[q];
+    // exactly symmetric covariance: read the lower triangle only (what the packed-symmetric kernels do)
+    const int ii = hw.i > hw.j ? hw.i : hw.j, jj = hw.i > hw.j ? hw.j : hw.i;
+    double Pe = (p.P0 + b * p.P0_stride)[ii * D + jj];
+    const double Qe = (p.Qc + b * p.Qc_stride)[ii * D + jj];
+    const double hi = H[0] * (hw.i == 0) + H[1] * (hw.i == 1) + H[2] * (hw.i == 2) + H[3] * (hw.i == 3);
+    const double hj = H[0] * (hw.j == 0) + H[1] * (hw.j == 1) + H[2] * (hw.j == 2) + H[3] * (hw.j == 3);
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
+    const int64_t T = p.T;
+    const bool store_state = io.mfs != nullptr && active;
+    const bool store_nell = io.nell != nullptr && active;
+    const double dt = p.dt, Xi = p.Xi;
+    double carry = 0., Sk = 1., rk = 0.;
+    double yv = (hw.l < T) ? __ldg(y + hw.l) : 0.;
+    for (int64_t t = 0; t < T; t++) {
+        const int slot = (int)(t & 15);
+        const double yt = hw.get(yv, slot);
+        if (slot == 15 && t + 1 < T) yv = (t + 1 + hw.l < T) ? __ldg(y + t + 1 + hw.l) : 0.;
+        rk4_step_lane([&](const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+            double jr[D];
+            chirp_drift_and_jrow(mdl, hw, mm, dm, jr);
+            const double X = row_times_P(hw, jr, PP);
+            const double Xt = hw.get(X, 4 * hw.j + hw.i);
+            dP = (Xt + X) + Qe;                                  // P J^T + J P + b b^T  (filters_smoothers.py:385)
+        }, m, Pe, dt);
+        // ---- measurement update (filters_smoothers.py:55-68): c = P h, S = h^T c + Xi
+        double cr = Pe * hj;                                     // row sums: c_i = sum_j P_ij h_j
+        cr += __shfl_xor_sync(0xffffffffu, cr, 1);
+        cr += __shfl_xor_sync(0xffffffffu, cr, 2);
+        double c[D];
+        CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
+        double S = H[0] * c[0];
+        CGP_UNROLL for (int q = 1; q < D; q++) S = fma(H[q], c[q], S);
+        S += Xi;
+        double pred = H[0] * m[0];
+        CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], m[q], pred);
+        const double rS = fast_rcp(S), resid = yt - pred;
+        double K[D];
+        CGP_UNROLL for (int q = 0; q < D; q++) K[q] = c[q] * rS;
+        CGP_UNROLL for (int q = 0; q < D; q++) m[q] = fma(K[q], resid, m[q]);
+        const double Ki = hw.i == 0 ? K[0] : (hw.i == 1 ? K[1] : (hw.i == 2 ? K[2] : K[3]));
+        const double Kj = hw.j == 0 ? K[0] : (hw.j == 1 ? K[1] : (hw.j == 2 ? K[2] : K[3]));
+        Pe = fma(-(Ki * Kj), S, Pe);
+        (void)hi;
+        if (hw.l == slot) { Sk = S; rk = resid; }
+        if (store_state) {
+            io.Pfs[(b * T + t) * (D * D) + hw.l] = Pe;
+            if (hw.l < D) io.mfs[(b * T + t) * D + hw.l] = hw.l == 0 ? m[0] : (hw.l == 1 ? m[1] : (hw.l == 2 ? m[2] : m[3]));
+        }
+        if (slot == 15 || t == T - 1) {
+            const int n = slot + 1;
+            const int64_t t0 = t - slot;
+            nl[half][hw.l] = hw.l < n ? nll_increment(Sk, rk) : 0.;
+            __syncwarp();
+            if (hw.l == 0) {
+                double cc = carry;
+                for (int q = 0; q < n; q++) { cc = cc + nl[half][q]; nl[half][q] = cc; }
+            }
+            __syncwarp();
+            carry = nl[half][n - 1];
+            if (store_nell && !io.nell_last_only && hw.l < n) io.nell[b * T + t0 + hw.l] = nl[half][hw.l];
+            __syncwarp();
+        }
+    }
+    if (store_nell && io.nell_last_only && hw.l == 0) io.nell[b] = carry;
+}
+
+// cd_eks: rhs (filters_smoothers.py:427-432) gamma = b b^T, M = J_a(m) + (Pf^{-1} gamma)^T, dm = a(m) + gamma Pf^{-1} (m - mf),
+// dP = M P + P M^T - gamma.  chol(Pf) and Pf^{-1} gamma are formed once per step (replicated in the lanes).
+template <int NH>
+__global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, const SmootherIO io) {
+    static_assert(NH == 1, "16 lanes per chirp need d == 4");
+    using Model = ModelSDE<1>;
+    constexpr int D = 4, DD = 16;
+    const int lane = threadIdx.x;
+    const HalfWarp hw(lane);
+    const int64_t gid = (int64_t)blockIdx.x * 2 + (lane >> 4);
+    const bool active = gid < p.B;
+    const int64_t b = active ? gid : p.B - 1;
+    const int64_t T = p.T;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride);
+    double Qf[D][D];
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) {
+        const int rr = r > c ? r : c, cc = r > c ? c : r;
+        Qf[r][c] = (p.Qc + b * p.Qc_stride)[rr * D + cc];
+    }
+    const int ii = hw.i > hw.j ? hw.i : hw.j, jj = hw.i > hw.j ? hw.j : hw.i;
+    const double Qe = (p.Qc + b * p.Qc_stride)[ii * D + jj];
+    double ms[D];
+    load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
+    double Pe = io.Pfs[(b * T + T - 1) * DD + ii * D + jj];
+    if (active) {
+        io.Pss[(b * T + T - 1) * DD + hw.l] = Pe;
+        if (hw.l < D) io.mss[(b * T + T - 1) * D + hw.l] = io.mfs[(b * T + T - 1) * D + hw.l];
+    }
+    const double ndt = -p.dt;
+    for (int64_t t = T - 2; t >= 0; t--) {
+        double mf[D], Pf[D][D], Lf[D][D], rinv[D], xrow[D];
+        load_vec<D>(io.mfs + (b * T + t) * D, mf);
+        load_mat<D>(io.Pfs + (b * T + t) * DD, Pf);
+        chol_lower_rsqrt<D>(Pf, Lf, rinv);
+        {   // column i of X = Pf^{-1} gamma^T  ->  row i of X^T, the constant part of M's row i
+            double col[D];
+            CGP_UNROLL for (int q = 0; q < D; q++)
+                col[q] = hw.i == 0 ? Qf[q][0] : (hw.i == 1 ? Qf[q][1] : (hw.i == 2 ? Qf[q][2] : Qf[q][3]));
+            chol_solve_vec_rinv<D>(Lf, rinv, col);
+            CGP_UNROLL for (int q = 0; q < D; q++) xrow[q] = col[q];
+        }
+        rk4_step_lane([&](const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+            double jr[D], a[D], z[D];
+            chirp_drift_and_jrow(mdl, hw, mm, a, jr);
+            CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xrow[q];
+            CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
+            chol_solve_vec_rinv<D>(Lf, rinv, z);
+            CGP_UNROLL for (int r = 0; r < D; r++) {
+                double s = Qf[r][0] * z[0];
+                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Qf[r][k], z[k], s);
+                dm[r] = a[r] + s;
+            }
+            const double Y = row_times_P(hw, jr, PP);
+            const double Yt = hw.get(Y, 4 * hw.j + hw.i);
+            dP = (Y + Yt) - Qe;
+        }, ms, Pe, ndt);
+        if (active) {
+            io.Pss[(b * T + t) * DD + hw.l] = Pe;
+            if (hw.l < D) io.mss[(b * T + t) * D + hw.l] = hw.l == 0 ? ms[0] : (hw.l == 1 ? ms[1] : (hw.l == 2 ? ms[2] : ms[3]));
+        }
+    }
+}
+
 }  // namespace cgp

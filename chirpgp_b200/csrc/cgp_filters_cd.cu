@@ -3,7 +3,15 @@
 
 namespace cgp {
 
+// Below this many chirps one thread per chirp cannot fill the GPU (148 SMs x 4 sub-partitions x a few warps); the
+// 16-lanes-per-chirp kernels give each chirp 16x the issue slots and a 16x shorter matrix-product chain.
+static const int64_t kLaneKernelMaxB = 40000;
+
 int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    if (p.model == CGP_MODEL_SDE && p.num_harmonics == 1 && p.d == 4 && p.B <= kLaneKernelMaxB) {
+        cd_ekf_lane_kernel<1><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        return check_launch();
+    }
     return dispatch_sde(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         const int block = 128;

@@ -4,6 +4,10 @@
 namespace cgp {
 
 int launch_cd_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    if (p.model == CGP_MODEL_SDE && p.num_harmonics == 1 && p.d == 4 && p.B <= 40000) {
+        cd_eks_lane_kernel<1><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        return check_launch();
+    }
     return dispatch_sde(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         const int block = 64;
