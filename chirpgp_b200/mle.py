@@ -21,7 +21,7 @@ from . import _native as N
 from .filters_smoothers import _device, _problem, _ptr, _h_unit_index
 from .models import LCDModel, NC_LCD
 
-__all__ = ['ekf_nll', 'fit_mle']
+__all__ = ['ekf_nll', 'filter_nll', 'fit_mle']
 
 _F64 = torch.float64
 
@@ -121,33 +121,79 @@ def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = Fals
     return nll.reshape(out_shape)
 
 
+def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None) -> torch.Tensor:
+    """Final cumulative nll of ANY of the five filters, evaluated by its kernel in nll-only mode (nothing but one double
+    per problem is stored): ``method`` in {'kf', 'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter'}; ``model_args`` are the
+    leading model arguments of that filter (e.g. ``(m_and_cov,)`` or ``(drift, dispersion)``).  Not differentiable by
+    autograd -- ``fit_mle`` differentiates it by central differences over a candidate batch (one launch)."""
+    from . import filters_smoothers as fs
+    dt = float(dt)
+    if method in ('kf', 'ekf', 'sgp_filter'):
+        model = fs._disc_model(model_args[0], int(m0.shape[-1]), dt) if method != 'kf' else model_args[0]
+        consts = fs._consts_on_device(model, dt, fs._device(), *((dt,) if method != 'kf' else ()))
+        return fs._run_filter(method, model, consts, H, Xi, m0, P0, dt, ys, sgps=sgps, store=False, last_only=True)
+    if method in ('cd_ekf', 'cd_sgp_filter'):
+        model = fs._sde_model(model_args[0], int(m0.shape[-1]))
+        b = model_args[1]
+        Qc = fs._qc(fs._dispersion_matrix(b, m0) if method == 'cd_ekf' else b)
+        return fs._run_filter(method, model, model.consts(), H, Xi, m0, P0, dt, ys, sgps=sgps, Qc=Qc, store=False,
+                              last_only=True)
+    raise ValueError('unknown filter %r' % method)
+
+
 def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optional[Callable] = None, maxiter: int = 200,
-            reduce_group=None):
-    """L-BFGS-B maximum-likelihood fit driving the nll / adjoint kernels -- the role of
-    ``jaxopt.ScipyMinimize(method='L-BFGS-B', fun=obj_func).run(init_theta)`` (demos/ekfs_mle.py:48-49).
+            reduce_group=None, method: str = 'ekf', sgps=None, fd_step: float = 1e-6):
+    """L-BFGS-B maximum-likelihood fit driving the nll kernels -- the role of
+    ``jaxopt.ScipyMinimize(method='L-BFGS-B', fun=obj_func).run(init_theta)`` (demos/ekfs_mle.py:48-49 and the other
+    ``*_mle.py`` demos / tetralith jobs).
 
     build_model(params) -> (drift, dispersion, m_and_cov, m0, P0, H') as chirpgp_b200.models.build_*; ``transform`` maps
     the unconstrained theta to params (default: the reference's softplus ``g``).  The objective is the SUM of the nll over
     all chirps in ``ys`` (this rank's shard when torch.distributed is initialised: the scalar objective and its 6-vector
     gradient are then summed over ranks with one all-reduce -- the only collective on this path).
 
+    method='ekf' uses the hand-written adjoint kernel.  The other filters ('sgp_filter' with ``sgps``, 'cd_ekf',
+    'cd_sgp_filter') have no adjoint kernel yet: their gradient is taken by central differences, with all 2P + 1
+    perturbed parameter sets evaluated as ONE candidate batch against the shared signals (nll-only kernels).
+
     Returns (theta_opt (numpy), scipy OptimizeResult); ``result.success`` follows the reference's convention
     (tetralith/jobs/ekfs_mle.py:49, :75-78: a failed fit is reported, not raised)."""
     import scipy.optimize
+    from .distributed import allreduce_objective
     from .models import g as _g
     transform = transform or _g
     dev = _device()
     ys_t = _as_dev(ys, dev)
+    ys2 = ys_t.reshape(-1, ys_t.shape[-1])
 
-    def fun(theta_np):
+    def fun_adjoint(theta_np):
         theta = torch.tensor(theta_np, dtype=_F64, device=dev, requires_grad=True)
         _, _, m_and_cov, m0, P0, _ = build_model(transform(theta))
         val = ekf_nll(m_and_cov, H, Xi, m0, P0, dt, ys_t).sum()
         grad, = torch.autograd.grad(val, theta)
-        from .distributed import allreduce_objective
         v, gr = allreduce_objective(val.detach(), grad, group=reduce_group)
         return float(v.cpu()), gr.cpu().numpy().copy()
 
+    def fun_fd(theta_np):
+        n = theta_np.shape[0]
+        h = fd_step * np.maximum(1., np.abs(theta_np))
+        cand = np.tile(theta_np, (2 * n + 1, 1))
+        for i in range(n):
+            cand[1 + 2 * i, i] += h[i]
+            cand[2 + 2 * i, i] -= h[i]
+        drift, dispersion, m_and_cov, m0, P0, _ = build_model(transform(torch.as_tensor(cand)))
+        if method in ('ekf', 'sgp_filter'):
+            margs = (m_and_cov,)
+        else:
+            margs = (drift, dispersion if method == 'cd_ekf' else dispersion.matrix())
+        total = torch.zeros(2 * n + 1, dtype=_F64, device=dev)
+        for row in ys2:                                   # every chirp against the 2P + 1 candidates
+            total = total + filter_nll(method, margs, H, Xi, m0, P0, dt, row, sgps=sgps)
+        grad = (total[1::2] - total[2::2]) / torch.as_tensor(2 * h, device=dev)
+        v, gr = allreduce_objective(total[0], grad, group=reduce_group)
+        return float(v.cpu()), gr.cpu().numpy().copy()
+
+    fun = fun_adjoint if method == 'ekf' else fun_fd
     res = scipy.optimize.minimize(fun, np.asarray(init_theta, dtype=np.float64), jac=True, method='L-BFGS-B',
                                   options={'maxiter': maxiter})
     return res.x, res

@@ -106,3 +106,36 @@ def test_candidate_grid_and_fit():
     theta, res = mle.fit_mle(cg.build_chirp_model, theta0, H, 0.1, dt, ys[:1], maxiter=15)
     assert res.fun < float(mle.ekf_nll(*[cg.build_chirp_model(gfun(torch.tensor(theta0)))[k] for k in (2,)], H, 0.1,
                                        *cg.build_chirp_model(gfun(torch.tensor(theta0)))[3:5], dt, ys[:1]).sum())
+
+
+def test_fd_gradient_mle_for_sigma_point_and_cd_filters(golden):
+    """The MLE demos of the sigma-point / continuous-discrete filters (demos/ghfs_mle.py:54-61, cd_ekfs_mle.py,
+    cd_ghfs_mle.py) take jax.grad of their nll; here those objectives are differentiated by central differences over a
+    candidate batch.  Check objective and gradient against the reference's jax.grad fixtures."""
+    z = golden('chirp')
+    H, Xi, dt, ys = z['H'], float(z['Xi']), float(z['dt']), z['ys']
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    cases = [('sgp_filter', sg, z['grad_sgp_filter_gh3'], z['sgp_filter_gh3_2'][-1]),
+             ('cd_ekf', None, z['grad_cd_ekf'], z['cd_ekf_2'][-1])]
+    for method, sgps, want_grad, want_val in cases:
+        calls = []
+
+        def spy(fun, x0, jac, method, options):
+            v, gr = fun(np.asarray(x0))
+            calls.append((v, gr))
+
+            class R:
+                x, success = np.asarray(x0), True
+                fun_ = v
+            return R()
+
+        import scipy.optimize
+        orig = scipy.optimize.minimize
+        scipy.optimize.minimize = spy
+        try:
+            mle.fit_mle(cg.build_chirp_model, z['theta'], H, Xi, dt, ys, method=method, sgps=sgps)
+        finally:
+            scipy.optimize.minimize = orig
+        v, gr = calls[0]
+        npt.assert_allclose(v, want_val, rtol=1e-10)
+        npt.assert_allclose(gr, want_grad, rtol=2e-5, atol=1e-6)
