@@ -313,10 +313,17 @@ template <int NH_> struct ModelLCD {
     template <bool WARP_UNIFORM = false> CGP_DEV Trig prep_v(double uv) const {
         Trig t;
         double w = (kTwoPi * (WARP_UNIFORM ? fast_softplus_warp(uv) : fast_softplus(uv))) * fs;
+        double s1, c1;
+        fast_sincos(dt * w, &s1, &c1);
+        double sk = s1, ck = c1;
         CGP_UNROLL for (int k = 0; k < NH; k++) {
-            double sn, cs;
-            fast_sincos((dt * (double)(k + 1)) * w, &sn, &cs);
-            t.c[k] = cs * e; t.s[k] = sn * e;
+            // harmonic k + 1 rotates by (k + 1) theta: angle addition instead of NH sincos evaluations
+            // (the reference evaluates cos/sin(dt k w) per harmonic, models.py:371-372; the difference is <= k ulp)
+            if (k > 0) {
+                const double cn = fma(ck, c1, -(sk * s1)), sn = fma(sk, c1, ck * s1);
+                ck = cn; sk = sn;
+            }
+            t.c[k] = ck * e; t.s[k] = sk * e;
         }
         return t;
     }
@@ -422,6 +429,29 @@ template <int NH_> struct ModelSDE {
 template <int G> CGP_DEV double group_allreduce(double v) {
     CGP_UNROLL for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
+}
+
+// Shared-memory variant for many values per lane: NA values x G lanes are transposed through `sm`
+// ([NA][G + 1] partials followed by NA results), every lane sums NA / G of them in a fixed tree order and all lanes
+// read the totals back.  ~ (NA + 2 NA / G * G/2 ...) instructions instead of 3 NA log2(G) for the butterfly.
+template <int NA, int G> struct GroupSmem { static constexpr int kDoubles = NA * (G + 1) + ((NA + 1) & ~1); };
+template <int NA, int G> CGP_DEV void group_sum_smem(double (&a)[NA], double *sm, int lane) {
+    constexpr int PITCH = G + 1;
+    double *res = sm + NA * PITCH;
+    CGP_UNROLL for (int k = 0; k < NA; k++) sm[k * PITCH + lane] = a[k];
+    __syncwarp();
+    CGP_UNROLL for (int k0 = 0; k0 < NA; k0 += G) {
+        const int k = k0 + lane;
+        const bool ok = k < NA;
+        double v[G];
+        CGP_UNROLL for (int j = 0; j < G; j++) v[j] = sm[(ok ? k : 0) * PITCH + j];
+        CGP_UNROLL for (int w2 = 1; w2 < G; w2 <<= 1)
+            CGP_UNROLL for (int j = 0; j + w2 < G; j += 2 * w2) v[j] += v[j + w2];
+        if (ok) res[k] = v[0];
+    }
+    __syncwarp();
+    CGP_UNROLL for (int k = 0; k < NA; k++) a[k] = res[k];
+    __syncwarp();
 }
 
 }  // namespace cgp

@@ -22,7 +22,7 @@ int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
 
 template <class Model, int G, int P>
 static int launch_cd_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
-    const int block = 128;
+    const int block = GroupCfg<Model, G, true>::kBlock;
     sgp_filter_kernel<Model, G, P, true><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
     return check_launch();
 }

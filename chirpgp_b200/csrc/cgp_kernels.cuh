@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(128) cd_ekf_thread_kernel(const CgpProblem p, 
 template <class Model, int G, int P, bool CROSS>
 CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n,
                          int lane, const double (&m)[Model::D], const double (&Pc)[NSym<Model::D>::value],
-                         double (&mp)[Model::D], double (&Pp)[NSym<Model::D>::value], double (&Dx)[Model::D][Model::D]) {
+                         double (&mp)[Model::D], double (&Pp)[NSym<Model::D>::value], double (&Dx)[Model::D][Model::D],
+                         double *gsm = nullptr) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     double L[NS];
     chol_lower_sym_rsqrt<D>(Pc, L);
@@ -246,6 +247,18 @@ CGP_DEV void sgp_moments(const Model &mdl, const double *__restrict__ sw, const 
             accumulate(i, chi, ev);
         }
     }
+    if constexpr (G > 1 && !CROSS) {
+        if (gsm) {                                     // many values: transpose through shared memory
+            double a[D + NS];
+            CGP_UNROLL for (int r = 0; r < D; r++) a[r] = am[r];
+            CGP_UNROLL for (int i = 0; i < NS; i++) a[D + i] = aP[i];
+            group_sum_smem<D + NS, G>(a, gsm, lane);
+            CGP_UNROLL for (int r = 0; r < D; r++) mp[r] = a[r];
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
+                Pp[sidx(r, c)] = a[D + sidx(r, c)] - mp[r] * mp[c];
+            return;
+        }
+    }
     CGP_UNROLL for (int r = 0; r < D; r++) mp[r] = group_allreduce<G>(am[r]);
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
         Pp[sidx(r, c)] = group_allreduce<G>(aP[sidx(r, c)]) - mp[r] * mp[c];
@@ -261,7 +274,7 @@ template <class Model, int G, int P>
 CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const double *__restrict__ sxi, int n,
                         int lane, const double (&Qc)[NSym<Model::D>::value], const double (&m)[Model::D],
                         const double (&Pc)[NSym<Model::D>::value], double (&dm)[Model::D],
-                        double (&dP)[NSym<Model::D>::value]) {
+                        double (&dP)[NSym<Model::D>::value], double *gsm = nullptr) {
     constexpr int D = Model::D, NS = NSym<D>::value;
     double L[NS];
     chol_lower_sym_rsqrt<D>(Pc, L);
@@ -306,17 +319,45 @@ CGP_DEV void cd_sgp_ode(const Model &mdl, const double *__restrict__ sw, const d
             accumulate(i, chi, f);
         }
     }
-    CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = group_allreduce<G>(am[r]);
-    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = group_allreduce<G>(aQ[r][c]);
+    bool summed = false;
+    if constexpr (G > 1) {
+        if (gsm) {
+            double a[D + D * D];
+            CGP_UNROLL for (int r = 0; r < D; r++) a[r] = am[r];
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) a[D + r * D + c] = aQ[r][c];
+            group_sum_smem<D + D * D, G>(a, gsm, lane);
+            CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r];
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = a[D + r * D + c];
+            summed = true;
+        }
+    }
+    if (!summed) {
+        CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = group_allreduce<G>(am[r]);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) aQ[r][c] = group_allreduce<G>(aQ[r][c]);
+    }
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
         dP[sidx(r, c)] = (aQ[r][c] + aQ[c][r]) + Qc[sidx(r, c)];
 }
 
 // ================================================================================================ group-per-chirp filters
+// Launch shape of the group-per-chirp kernels: the shared-memory reduction is used when a lane holds >= 24 partial
+// sums (d >= 6); the block shrinks to 64 threads when 128 would need more than 40 KB of static shared memory.
+template <class Model, int G, bool CD> struct GroupCfg {
+    static constexpr int D = Model::D;
+    static constexpr int NA = CD ? D + D * D : D + NSym<D>::value;
+    static constexpr bool kSmem = G > 1 && NA >= 24;
+    static constexpr int kPerGroup = GroupSmem<NA, G>::kDoubles;
+    static constexpr int kBlock = (kSmem && (128 / G) * kPerGroup * 8 > 40960) ? 64 : 128;
+    static constexpr int kGroups = kBlock / G;
+};
+
 // sgp_filter (filters_smoothers.py:446-490) and cd_sgp_filter (:534-582)
 template <class Model, int G, int P, bool CD>
-__global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, const FilterIO io) {
+__global__ void __launch_bounds__(GroupCfg<Model, G, CD>::kBlock) sgp_filter_kernel(const CgpProblem p, const FilterIO io) {
     constexpr int D = Model::D, NS = NSym<D>::value;
+    using Cfg = GroupCfg<Model, G, CD>;
+    __shared__ double gsm_all[Cfg::kSmem ? Cfg::kGroups * Cfg::kPerGroup : 1];
+    double *gsm = Cfg::kSmem ? gsm_all + (threadIdx.x / G) * Cfg::kPerGroup : nullptr;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     const bool active = gid < p.B;
@@ -347,11 +388,11 @@ __global__ void __launch_bounds__(128) sgp_filter_kernel(const CgpProblem p, con
             CGP_UNROLL for (int i = 0; i < D; i++) mp[i] = m[i];
             CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = Pc[i];
             rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
-                cd_sgp_ode<Model, G, P>(mdl, sw, sxi, n, lane, Qc, mm, PP, dm, dP);
+                cd_sgp_ode<Model, G, P>(mdl, sw, sxi, n, lane, Qc, mm, PP, dm, dP, gsm);
             }, mp, Pp, dt);
         } else {
             double dummy[D][D];
-            sgp_moments<Model, G, P, false>(mdl, sw, sxi, n, lane, m, Pc, mp, Pp, dummy);
+            sgp_moments<Model, G, P, false>(mdl, sw, sxi, n, lane, m, Pc, mp, Pp, dummy, gsm);
         }
         acc = acc + linear_update_sym<D>(mp, Pp, H, p.Xi, yt, m, Pc);
         if (store) {
@@ -532,8 +573,11 @@ __global__ void __launch_bounds__(64) cd_eks_thread_kernel(const CgpProblem p, c
 //   rhs (:615-621): Gm = Pf^{-1} gamma;  (_m, _P) = cd_sgp_common(m, P);
 //                   dm = _m + Gm^T (m - mf);   dP = _P + Gm^T P + P Gm - 2 gamma.
 template <class Model, int G, int P>
-__global__ void __launch_bounds__(128) cd_sgp_smoother_kernel(const CgpProblem p, const SmootherIO io) {
+__global__ void __launch_bounds__(GroupCfg<Model, G, true>::kBlock) cd_sgp_smoother_kernel(const CgpProblem p, const SmootherIO io) {
     constexpr int D = Model::D, NS = NSym<D>::value;
+    using Cfg = GroupCfg<Model, G, true>;
+    __shared__ double gsm_all[Cfg::kSmem ? Cfg::kGroups * Cfg::kPerGroup : 1];
+    double *gsm = Cfg::kSmem ? gsm_all + (threadIdx.x / G) * Cfg::kPerGroup : nullptr;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     const bool active = gid < p.B;
@@ -562,7 +606,7 @@ __global__ void __launch_bounds__(128) cd_sgp_smoother_kernel(const CgpProblem p
         chol_solve_mat<D>(Lf, Qf, Gm);                // Gm = Pf^{-1} gamma
         rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
             double _m[D], _P[NS], W[D][D];
-            cd_sgp_ode<Model, G, P>(mdl, p.sig_w, p.sig_xi, n, lane, Qc, mm, PP, _m, _P);
+            cd_sgp_ode<Model, G, P>(mdl, p.sig_w, p.sig_xi, n, lane, Qc, mm, PP, _m, _P, gsm);
             CGP_UNROLL for (int r = 0; r < D; r++) {
                 double s = Gm[0][r] * (mm[0] - mf[0]);
                 CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Gm[k][r], mm[k] - mf[k], s);

@@ -18,7 +18,7 @@ int launch_cd_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
 
 template <class Model, int G, int P>
 static int launch_one(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
-    const int block = 128;
+    const int block = GroupCfg<Model, G, true>::kBlock;
     cd_sgp_smoother_kernel<Model, G, P><<<(unsigned)ceil_div(p.B * G, block), block, 0, s>>>(p, io);
     return check_launch();
 }
