@@ -700,4 +700,103 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------ smoother sweep, d = 4, 16 lanes per chirp
+// Same recursion as smoother_sweep_warp_kernel, for d = 4: lane (i, j) of a half-warp holds Ps_ij, the two small matrix
+// products exchange their operands with shuffles (no shared-memory round trips on the dependency chain), and the 16
+// entries of a step are written with one coalesced 128-byte store.  Tiles of the gain records and of (mf, Pf) are
+// staged with cp.async, double buffered, per half-warp.
+template <int TS_, int NSTAGE>
+__global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = 4, DD = 16, R = 2 * DD + D, TS = TS_, TILE = TS * (R + D + DD);
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x;
+    const HalfWarp hw(lane);
+    const int half = lane >> 4;
+    const int64_t gid = (int64_t)blockIdx.x * 2 + half;
+    const bool active = gid < p.B;
+    const int64_t b = active ? gid : p.B - 1;
+    const int64_t T = p.T;
+    double *my = smem + half * (NSTAGE * TILE);
+    const double *__restrict__ ws = io.ws + b * T * R;
+    const double *__restrict__ mfs = io.mfs + b * T * D;
+    const double *__restrict__ Pfs = io.Pfs + b * T * DD;
+    double *__restrict__ mss = io.mss + b * T * D;
+    double *__restrict__ Pss = io.Pss + b * T * DD;
+    double Pe = Pfs[(T - 1) * DD + hw.l];
+    double ms[D];
+    CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mfs[(T - 1) * D + q];
+    if (active) {
+        Pss[(T - 1) * DD + hw.l] = Pe;
+        if (hw.l < D) mss[(T - 1) * D + hw.l] = mfs[(T - 1) * D + hw.l];
+    }
+    if (T < 2) return;
+    auto issue_tile = [&](int buf, int64_t lo, int n) {
+        double *dst = my + buf * TILE;
+        const double *s0 = ws + lo * R;
+        for (int i = hw.l; i < n * R / 2; i += 16) cp_async16(dst + 2 * i, s0 + 2 * i);
+        const double *s1 = mfs + lo * D;
+        for (int i = hw.l; i < n * D / 2; i += 16) cp_async16(dst + TS * R + 2 * i, s1 + 2 * i);
+        const double *s2 = Pfs + lo * DD;
+        for (int i = hw.l; i < n * DD / 2; i += 16) cp_async16(dst + TS * (R + D) + 2 * i, s2 + 2 * i);
+        cp_async_commit();
+    };
+    // NSTAGE-deep cp.async pipeline over tiles walking backwards from step T-2; empty commit groups keep the group
+    // count uniform at the tail
+    int64_t hi = T - 1;                 // steps [lo, hi) of the tile being consumed
+    int64_t next_hi = T - 1;            // upper end of the next tile to issue
+    int buf = 0, ibuf = 0;
+    CGP_UNROLL for (int st = 0; st < NSTAGE - 1; st++) {
+        if (next_hi > 0) {
+            const int n = (int)(next_hi < TS ? next_hi : TS);
+            issue_tile(ibuf, next_hi - n, n);
+            next_hi -= n;
+        } else {
+            cp_async_commit();
+        }
+        ibuf = (ibuf + 1) % NSTAGE;
+    }
+    while (hi > 0) {
+        const int n = (int)(hi < TS ? hi : TS);
+        const int64_t lo = hi - n;
+        if (next_hi > 0) {
+            const int nn = (int)(next_hi < TS ? next_hi : TS);
+            issue_tile(ibuf, next_hi - nn, nn);
+            next_hi -= nn;
+        } else {
+            cp_async_commit();
+        }
+        ibuf = (ibuf + 1) % NSTAGE;
+        cp_async_wait<NSTAGE - 1>();
+        __syncwarp();
+        const double *tw = my + buf * TILE, *tm = tw + TS * R, *tP = tm + TS * D;
+        double *pP = Pss + (lo + n - 1) * DD, *pm = mss + (lo + n - 1) * D;
+        for (int jj = n - 1; jj >= 0; jj--) {
+            const double *Gm = tw + jj * R, *mp = Gm + DD, *Pp = mp + D;
+            // rows i and j of the gain (each lane needs both), this lane's Pp / Pf entries, mf, mp
+            double gi[D], gj[D];
+            CGP_UNROLL for (int k = 0; k < D; k++) { gi[k] = Gm[hw.i * D + k]; gj[k] = Gm[hw.j * D + k]; }
+            const double X = Pe - Pp[hw.l];                                        // (Ps - Pp)_ij
+            double t1 = gi[0] * hw.get(X, hw.j);                                   // (G X)_ij = sum_k G_ik X_kj
+            CGP_UNROLL for (int k = 1; k < D; k++) t1 = fma(gi[k], hw.get(X, 4 * k + hw.j), t1);
+            double t2 = hw.get(t1, 4 * hw.i) * gj[0];                              // (T1 G^T)_ij = sum_k T1_ik G_jk
+            CGP_UNROLL for (int k = 1; k < D; k++) t2 = fma(hw.get(t1, 4 * hw.i + k), gj[k], t2);
+            Pe = tP[jj * DD + hw.l] + t2;
+            // ms = mf + G (ms - mp): lane (i, .) forms row i, the four rows are then gathered from lanes (k, 0)
+            double msi = gi[0] * (ms[0] - mp[0]);
+            CGP_UNROLL for (int k = 1; k < D; k++) msi = fma(gi[k], ms[k] - mp[k], msi);
+            msi = tm[jj * D + hw.i] + msi;
+            CGP_UNROLL for (int k = 0; k < D; k++) ms[k] = hw.get(msi, 4 * k);
+            if (active) {
+                pP[hw.l] = Pe;
+                if (hw.j == 0) pm[hw.i] = msi;
+            }
+            pP -= DD;
+            pm -= D;
+        }
+        __syncwarp();
+        hi = lo;
+        buf = (buf + 1) % NSTAGE;
+    }
+}
+
 }  // namespace cgp

@@ -8,6 +8,12 @@ namespace cgp {
 template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
     if constexpr (D % 2 == 0) {
         if (aligned16(io.ws) && aligned16(io.mfs) && aligned16(io.Pfs) && aligned16(io.mss) && aligned16(io.Pss)) {
+            if constexpr (D == 4) {
+                constexpr int TS = 8, NSTAGE = 4;
+                const size_t smem = sizeof(double) * 2 * NSTAGE * TS * (2 * 16 + 4 + 4 + 16);
+                smoother_sweep_lane4_kernel<TS, NSTAGE><<<(unsigned)ceil_div(p.B, 2), 32, smem, s>>>(p, io);
+                return check_launch();
+            }
             using Cfg = SweepCfg<D>;
             smoother_sweep_warp_kernel<D><<<(unsigned)p.B, 32, Cfg::smem_bytes(), s>>>(p, io);
             return check_launch();
