@@ -346,12 +346,12 @@ def run_ours(args):
                     'what': 'pinned host ys -> cg.sgp_filter -> cg.sgp_smoother -> pinned host (mss, Pss); steps issued on '
                             'two alternating streams so the D2H copy of one step overlaps the filter of the next'},
             'gpu_launches': args.steps * 3,
-            'kernels_per_step': ['ghf_filter_kernel<1,3>', 'sgp_gain_kernel<ModelLCD<1>,3>', 'smoother_sweep_warp_kernel<4>'],
-            'roofline': {'bound': 'hbm', 'kernel': 'ghf_filter_kernel<1,3> (sgp_filter, warp per chirp)', 'achieved': ach_gbs,
+            'kernels_per_step': ['gh_warp_filter_kernel<GhPredictLCD<1,3>>', 'sgp_gain_kernel<ModelLCD<1>,3>', 'smoother_sweep_lane4_kernel'],
+            'roofline': {'bound': 'hbm', 'kernel': 'gh_warp_filter_kernel<GhPredictLCD<1,3>> (sgp_filter, warp per chirp)', 'achieved': ach_gbs,
                          'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': NCU_TRAFFIC_BYTES,
                          'peak_source': hbm_src, 'kernel_ms': ms_filter,
                          'algorithmic_bytes_per_step': BYTES_FILTER},
-            'roofline_fp64': {'bound': 'fp64', 'kernel': 'ghf_filter_kernel<1,3>', 'achieved': ach_tf, 'peak': fp64_peak,
+            'roofline_fp64': {'bound': 'fp64', 'kernel': 'gh_warp_filter_kernel<GhPredictLCD<1,3>>', 'achieved': ach_tf, 'peak': fp64_peak,
                               'unit': 'TFLOP/s', 'frac': ach_tf / fp64_peak if fp64_peak else None,
                               'flops_per_step': flops_per_step('sgp_filter'),
                               'peak_source': 'DFMA-only kernel measured in this run',
