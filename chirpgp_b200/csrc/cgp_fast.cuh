@@ -799,4 +799,104 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProbl
     }
 }
 
+// ------------------------------------------------------------------------------------------------ smoother sweep, d = 8, one warp per chirp
+// Lane (i, jq) = (l / 4, l % 4) holds the two covariance entries (i, jq) and (i, jq + 4); the 8 x 8 products take their
+// operands by shuffle: (G X)_ij needs column j of X (lanes (k, j % 4), slot j / 4), (T1 G^T)_ij needs row i of T1 (the
+// four lanes of row i, both slots).  Gain rows come from the cp.async-staged tile in shared memory.
+template <int TS_, int NSTAGE>
+__global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = 8, DD = 64, R = 2 * DD + D, TS = TS_, TILE = TS * (R + D + DD);
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x, li = lane >> 2, jq = lane & 3;
+    const int64_t b = blockIdx.x;
+    const int64_t T = p.T;
+    const double *__restrict__ ws = io.ws + b * T * R;
+    const double *__restrict__ mfs = io.mfs + b * T * D;
+    const double *__restrict__ Pfs = io.Pfs + b * T * DD;
+    double *__restrict__ mss = io.mss + b * T * D;
+    double *__restrict__ Pss = io.Pss + b * T * DD;
+    const int ea = li * D + jq, eb = ea + 4;
+    double Pa = Pfs[(T - 1) * DD + ea], Pb = Pfs[(T - 1) * DD + eb];
+    double ms[D];
+    CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mfs[(T - 1) * D + q];
+    Pss[(T - 1) * DD + ea] = Pa;
+    Pss[(T - 1) * DD + eb] = Pb;
+    if (lane < D) mss[(T - 1) * D + lane] = mfs[(T - 1) * D + lane];
+    if (T < 2) return;
+    auto issue_tile = [&](int buf, int64_t lo, int n) {
+        double *dst = smem + buf * TILE;
+        const double *s0 = ws + lo * R;
+        for (int i = lane; i < n * R / 2; i += 32) cp_async16(dst + 2 * i, s0 + 2 * i);
+        const double *s1 = mfs + lo * D;
+        for (int i = lane; i < n * D / 2; i += 32) cp_async16(dst + TS * R + 2 * i, s1 + 2 * i);
+        const double *s2 = Pfs + lo * DD;
+        for (int i = lane; i < n * DD / 2; i += 32) cp_async16(dst + TS * (R + D) + 2 * i, s2 + 2 * i);
+        cp_async_commit();
+    };
+    int64_t hi = T - 1, next_hi = T - 1;
+    int buf = 0, ibuf = 0;
+    CGP_UNROLL for (int st = 0; st < NSTAGE - 1; st++) {
+        if (next_hi > 0) {
+            const int n = (int)(next_hi < TS ? next_hi : TS);
+            issue_tile(ibuf, next_hi - n, n);
+            next_hi -= n;
+        } else {
+            cp_async_commit();
+        }
+        ibuf = (ibuf + 1) % NSTAGE;
+    }
+    while (hi > 0) {
+        const int n = (int)(hi < TS ? hi : TS);
+        const int64_t lo = hi - n;
+        if (next_hi > 0) {
+            const int nn = (int)(next_hi < TS ? next_hi : TS);
+            issue_tile(ibuf, next_hi - nn, nn);
+            next_hi -= nn;
+        } else {
+            cp_async_commit();
+        }
+        ibuf = (ibuf + 1) % NSTAGE;
+        cp_async_wait<NSTAGE - 1>();
+        __syncwarp();
+        const double *tw = smem + buf * TILE, *tm = tw + TS * R, *tP = tm + TS * D;
+        double *pP = Pss + (lo + n - 1) * DD, *pm = mss + (lo + n - 1) * D;
+        for (int jj = n - 1; jj >= 0; jj--) {
+            const double *Gm = tw + jj * R, *mp = Gm + DD, *Pp = mp + D;
+            double gi[D], ga[D], gb[D];
+            CGP_UNROLL for (int k = 0; k < D; k++) { gi[k] = Gm[li * D + k]; ga[k] = Gm[jq * D + k]; gb[k] = Gm[(jq + 4) * D + k]; }
+            const double Xa = Pa - Pp[ea], Xb = Pb - Pp[eb];
+            double ta = gi[0] * __shfl_sync(0xffffffffu, Xa, jq), tb = gi[0] * __shfl_sync(0xffffffffu, Xb, jq);
+            CGP_UNROLL for (int k = 1; k < D; k++) {
+                ta = fma(gi[k], __shfl_sync(0xffffffffu, Xa, 4 * k + jq), ta);
+                tb = fma(gi[k], __shfl_sync(0xffffffffu, Xb, 4 * k + jq), tb);
+            }
+            double ua = 0., ub = 0.;
+            CGP_UNROLL for (int k = 0; k < 4; k++) {                  // T1_ik for k < 4 sits in slot a of lane (i, k)
+                const double t1 = __shfl_sync(0xffffffffu, ta, 4 * li + k);
+                ua = (k == 0) ? t1 * ga[0] : fma(t1, ga[k], ua);
+                ub = (k == 0) ? t1 * gb[0] : fma(t1, gb[k], ub);
+            }
+            CGP_UNROLL for (int k = 0; k < 4; k++) {                  // k + 4: slot b
+                const double t1 = __shfl_sync(0xffffffffu, tb, 4 * li + k);
+                ua = fma(t1, ga[k + 4], ua);
+                ub = fma(t1, gb[k + 4], ub);
+            }
+            Pa = tP[jj * DD + ea] + ua;
+            Pb = tP[jj * DD + eb] + ub;
+            double msi = gi[0] * (ms[0] - mp[0]);
+            CGP_UNROLL for (int k = 1; k < D; k++) msi = fma(gi[k], ms[k] - mp[k], msi);
+            msi = tm[jj * D + li] + msi;
+            CGP_UNROLL for (int k = 0; k < D; k++) ms[k] = __shfl_sync(0xffffffffu, msi, 4 * k);
+            pP[ea] = Pa;
+            pP[eb] = Pb;
+            if (jq == 0) pm[li] = msi;
+            pP -= DD;
+            pm -= D;
+        }
+        __syncwarp();
+        hi = lo;
+        buf = (buf + 1) % NSTAGE;
+    }
+}
+
 }  // namespace cgp

@@ -14,6 +14,12 @@ template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &
                 smoother_sweep_lane4_kernel<TS, NSTAGE><<<(unsigned)ceil_div(p.B, 2), 32, smem, s>>>(p, io);
                 return check_launch();
             }
+            if constexpr (D == 8) {
+                constexpr int TS = 4, NSTAGE = 4;
+                const size_t smem = sizeof(double) * NSTAGE * TS * (2 * 64 + 8 + 8 + 64);
+                smoother_sweep_lane8_kernel<TS, NSTAGE><<<(unsigned)p.B, 32, smem, s>>>(p, io);
+                return check_launch();
+            }
             using Cfg = SweepCfg<D>;
             smoother_sweep_warp_kernel<D><<<(unsigned)p.B, 32, Cfg::smem_bytes(), s>>>(p, io);
             return check_launch();
