@@ -9,45 +9,6 @@
 
 namespace cgp {
 
-// measurement update on packed-symmetric covariance with one reciprocal; H generic or the unit vector e_1.
-// Returns the innovation variance S and residual r = y - H mp; the nll increment is formed from them later
-// (nll_increment), off the critical path of the state recursion.
-template <int D, bool H_E1>
-CGP_DEV void linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym<D>::value], const double (&H)[D], double Xi,
-                                double y, double (&mf)[D], double (&Pf)[NSym<D>::value], double &S_out, double &r_out) {
-    double PH[D], S, pred;
-    if constexpr (H_E1) {
-        CGP_UNROLL for (int i = 0; i < D; i++) PH[i] = Pp[sidx(i, 1)];
-        S = PH[1] + Xi;
-        pred = mp[1];
-    } else {
-        CGP_UNROLL for (int i = 0; i < D; i++) {
-            double s = Pp[sidx(i, 0)] * H[0];
-            CGP_UNROLL for (int j = 1; j < D; j++) s = fma(Pp[sidx(i, j)], H[j], s);
-            PH[i] = s;
-        }
-        S = PH[0] * H[0];
-        CGP_UNROLL for (int j = 1; j < D; j++) S = fma(PH[j], H[j], S);
-        S += Xi;
-        pred = H[0] * mp[0];
-        CGP_UNROLL for (int i = 1; i < D; i++) pred = fma(H[i], mp[i], pred);
-    }
-    const double rS = fast_rcp(S);
-    double K[D];
-    CGP_UNROLL for (int i = 0; i < D; i++) K[i] = PH[i] * rS;
-    const double r = y - pred;
-    CGP_UNROLL for (int i = 0; i < D; i++) mf[i] = fma(K[i], r, mp[i]);
-    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j <= i; j++)
-        Pf[sidx(i, j)] = fma(-(K[i] * K[j]), S, Pp[sidx(i, j)]);
-    S_out = S;
-    r_out = r;
-}
-// -norm.logpdf(y, pred, sqrt(S)) in jax.scipy.stats.norm.logpdf's operation order (filters_smoothers.py:44-45)
-CGP_DEV double nll_increment(double S, double r) {
-    const double sc = sqrt(S), sc2 = sc * sc;
-    return (log(kTwoPi * sc2) + r * r / sc2) * 0.5;
-}
-
 // ------------------------------------------------------------------------------------------------ warp-per-chirp sigma-point filters
 // All 32 lanes' partial sums a[0..NA) are combined through shared memory in a fixed tree order; every lane gets
 // the same totals.  red: [NA][33] doubles, res: [NA rounded up to even] doubles (16-byte aligned).

@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, CD>::kBlock) sgp_filter_ker
     constexpr int D = Model::D, NS = NSym<D>::value;
     using Cfg = GroupCfg<Model, G, CD>;
     __shared__ double gsm_all[Cfg::kSmem ? Cfg::kGroups * Cfg::kPerGroup : 1];
+    __shared__ double nl_all[G > 1 ? Cfg::kBlock : 1];            // nll increments of G consecutive steps, per group
     double *gsm = Cfg::kSmem ? gsm_all + (threadIdx.x / G) * Cfg::kPerGroup : nullptr;
+    double *nl = nl_all + (G > 1 ? (threadIdx.x / G) * G : 0);
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     const bool active = gid < p.B;
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, CD>::kBlock) sgp_filter_ker
     const double *__restrict__ sw = p.sig_w;
     const double *__restrict__ sxi = p.sig_xi;
     const double dt = p.dt;
-    double acc = 0.;
+    double acc = 0., Sk = 1., rk = 0.;
     double ynext = __ldg(y);
     for (int64_t t = 0; t < T; t++) {
         const double yt = ynext;
@@ -394,12 +396,34 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, CD>::kBlock) sgp_filter_ker
             double dummy[D][D];
             sgp_moments<Model, G, P, false>(mdl, sw, sxi, n, lane, m, Pc, mp, Pp, dummy, gsm);
         }
-        acc = acc + linear_update_sym<D>(mp, Pp, H, p.Xi, yt, m, Pc);
+        double S, resid;
+        linear_update_fast<D, false>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
         if (store) {
             store_vec<D>(io.mfs + (b * T + t) * D, m);
             store_sym<D>(io.Pfs + (b * T + t) * (D * D), Pc);
         }
-        if (store_nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+        if constexpr (G == 1) {
+            acc = acc + nll_increment(S, resid);
+            if (store_nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+        } else {
+            // lane (t mod G) keeps (S, r) of step t; every G steps the increments are evaluated in SIMD (one log / sqrt /
+            // divide per lane instead of one per step) and accumulated in the reference's sequential order
+            const int slot = (int)(t % G);
+            if (lane == slot) { Sk = S; rk = resid; }
+            if (slot == G - 1 || t == T - 1) {
+                const int cnt = slot + 1;
+                nl[lane] = lane < cnt ? nll_increment(Sk, rk) : 0.;
+                __syncwarp();
+                if (lane == 0) {
+                    double c = acc;
+                    for (int j = 0; j < cnt; j++) { c = c + nl[j]; nl[j] = c; }
+                }
+                __syncwarp();
+                acc = nl[cnt - 1];
+                if (io.nell != nullptr && active && !io.nell_last_only && lane < cnt) io.nell[b * T + (t - slot) + lane] = nl[lane];
+                __syncwarp();
+            }
+        }
     }
     if (store_nell && io.nell_last_only) io.nell[b] = acc;
 }
