@@ -510,8 +510,9 @@ template <class Ode> CGP_DEV void rk4_step_lane(Ode &&ode, double (&m)[4], doubl
     CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = am[q] + 2 * km[q]; tm[q] = m[q] + dt * km[q]; }
     aP = aP + 2 * kP; tP = Pe + dt * kP;
     ode(tm, tP, km, kP);
-    CGP_UNROLL for (int q = 0; q < 4; q++) m[q] = m[q] + dt * (am[q] + km[q]) / 6;
-    Pe = Pe + dt * (aP + kP) / 6;
+    constexpr double kSixth = 1. / 6.;
+    CGP_UNROLL for (int q = 0; q < 4; q++) m[q] = m[q] + dt * (am[q] + km[q]) * kSixth;
+    Pe = Pe + dt * (aP + kP) * kSixth;
 }
 
 template <int NH>   // NH == 1: the chirp SDE (d = 4 -> 16 covariance entries -> half a warp)

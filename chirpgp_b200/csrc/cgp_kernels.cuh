@@ -105,8 +105,10 @@ CGP_DEV void rk4_step(Ode &&ode, double (&m)[D], double (&P)[NSym<D>::value], do
     CGP_UNROLL for (int i = 0; i < D; i++) { am[i] = am[i] + 2 * km[i]; tm[i] = m[i] + dt * km[i]; }
     CGP_UNROLL for (int i = 0; i < NS; i++) { aP[i] = aP[i] + 2 * kP[i]; tP[i] = P[i] + dt * kP[i]; }
     ode(tm, tP, km, kP);
-    CGP_UNROLL for (int i = 0; i < D; i++) m[i] = m[i] + dt * (am[i] + km[i]) / 6;
-    CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = P[i] + dt * (aP[i] + kP[i]) / 6;
+    // dt (k1 + 2 k2 + 2 k3 + k4) / 6 with the division by 6 as a multiplication by the rounded reciprocal (<= 1 ulp)
+    constexpr double kSixth = 1. / 6.;
+    CGP_UNROLL for (int i = 0; i < D; i++) m[i] = m[i] + dt * (am[i] + km[i]) * kSixth;
+    CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = P[i] + dt * (aP[i] + kP[i]) * kSixth;
 }
 
 // cd_ekf (filters_smoothers.py:352-397): Model = ModelLinearSDE<D> | ModelSDE<NH>
