@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libchirpgp_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 CGP_MODEL_LINEAR_DISC, CGP_MODEL_LCD, CGP_MODEL_LINEAR_SDE, CGP_MODEL_SDE = 0, 1, 2, 3
-CGP_SIGMA_GENERIC, CGP_SIGMA_GAUSS_HERMITE = 0, 1
+CGP_SIGMA_GENERIC, CGP_SIGMA_GAUSS_HERMITE, CGP_SIGMA_CUBATURE = 0, 1, 2
 ABI_VERSION = 1
 
 _ERRORS = {-1: 'CGP_ERR_BAD_ARG', -2: 'CGP_ERR_UNSUPPORTED (no kernel compiled for this model / state dimension)',

@@ -861,4 +861,104 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProbl
     }
 }
 
+// ------------------------------------------------------------------------------------------------ cubature smoother gains, thread per (chirp, step)
+// sgp_smoother's time-parallel half (filters_smoothers.py:520-527) for the spherical cubature rule (quadratures.py:139-150:
+// points m +- sqrt(d) L e_j, equal weights) at larger d, where the generic kernel runs out of registers (d = 8: 36 + 36 + 64
+// accumulators).  Uses the structure of the rule:
+//   * chi_j+- = m +- s l_j needs only column j of L = chol(Pf): L lives in shared memory, one column is read per pair;
+//   * the cross-covariance  D = sum_p w chi_p f_p^T - m mp^T  equals  s w sum_j l_j (f_j+ - f_j-)^T  (the m mp^T terms cancel
+//     identically; evaluating this form avoids the reference's cancellation instead of reproducing it -- the difference is
+//     the reference's own rounding noise, ~1e-13 relative), so  G = D Pp^{-1} = s w sum_j l_j z_j^T  with  Pp z_j = f_j+ - f_j-.
+// D is accumulated in shared memory (rank-one updates l_j (f_j+ - f_j-)^T touch only rows r >= j), the rows of G are then
+// solved in registers against chol(Pp).
+template <int NH>
+__global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, const SmootherIO io) {
+    using Model = ModelLCD<NH>;
+    constexpr int D = Model::D, NS = NSym<D>::value, BLK = 64;
+    extern __shared__ __align__(16) double cg_smem[];
+    double (*Ls)[BLK] = reinterpret_cast<double (*)[BLK]>(cg_smem);                    // chol(Pf), element-major: conflict-free
+    double (*Ds)[BLK] = reinterpret_cast<double (*)[BLK]>(cg_smem + NS * BLK);         // s w sum_j l_j (f_j+ - f_j-)^T
+    const int tid = threadIdx.x;
+    const int64_t Tm1 = p.T - 1;
+    const int64_t item = (int64_t)blockIdx.x * BLK + tid;
+    if (item >= p.B * Tm1) return;
+    const int64_t b = item / Tm1, t = item - b * Tm1;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double m[D];
+    load_vec<D>(io.mfs + (b * p.T + t) * D, m);
+    double *__restrict__ rec = io.ws + (b * p.T + t) * ws_record<D>();      // [G | mp | Pp]
+    {
+        double Pf[NS], L[NS];
+        load_sym<D>(io.Pfs + (b * p.T + t) * (D * D), Pf);
+        chol_lower_sym_rsqrt<D>(Pf, L);
+        CGP_UNROLL for (int i = 0; i < NS; i++) Ls[i][tid] = L[i];
+    }
+    CGP_UNROLL for (int i = 0; i < D * D; i++) Ds[i][tid] = 0.;
+    const double w = __ldg(p.sig_w);                         // equal weights 1 / (2 d)
+    double am[D], aP[NS];
+    CGP_UNROLL for (int i = 0; i < D; i++) am[i] = 0.;
+    CGP_UNROLL for (int i = 0; i < NS; i++) aP[i] = 0.;
+    auto accumulate = [&](const double (&ev)[D]) {
+        CGP_UNROLL for (int r = 0; r < D; r++) am[r] = fma(w, ev[r], am[r]);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++) {
+            double v = ev[r] * ev[c];
+            if (Model::has_sig(r, c)) v += mdl.sig(r, c);
+            aP[sidx(r, c)] = fma(w, v, aP[sidx(r, c)]);
+        }
+    };
+    CGP_UNROLL for (int j = 0; j < D; j++) {
+        const double sp = __ldg(p.sig_xi + j * D + j), sn = __ldg(p.sig_xi + (D + j) * D + j);   // +sqrt(d), -sqrt(d)
+        double lj[D], chi[D], evp[D], evn[D];
+        CGP_UNROLL for (int r = j; r < D; r++) lj[r] = Ls[sidx(r, j)][tid];
+        CGP_UNROLL for (int r = 0; r < D; r++) chi[r] = (r >= j) ? m[r] + lj[r] * sp : m[r];
+        mdl.mean(chi, evp);
+        accumulate(evp);
+        CGP_UNROLL for (int r = 0; r < D; r++) chi[r] = (r >= j) ? m[r] + lj[r] * sn : m[r];
+        mdl.mean(chi, evn);
+        accumulate(evn);
+        const double sw = sp * w;
+        CGP_UNROLL for (int c = 0; c < D; c++) evp[c] = (evp[c] - evn[c]) * sw;
+        CGP_UNROLL for (int r = j; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
+            Ds[r * D + c][tid] = fma(lj[r], evp[c], Ds[r * D + c][tid]);
+    }
+    // mp, Pp of the record; chol(Pp) into the registers the accumulators leave behind
+    CGP_UNROLL for (int r = 0; r < D; r++) rec[D * D + r] = am[r];
+    double Lq[NS], rinv[D];
+    {
+        double Pps[NS];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++) Pps[sidx(r, c)] = aP[sidx(r, c)] - am[r] * am[c];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c += 2)
+            *reinterpret_cast<double2 *>(rec + D * D + D + r * D + c) = make_double2(Pps[sidx(r, c)], Pps[sidx(r, c + 1)]);
+        CGP_UNROLL for (int j = 0; j < D; j++) {             // chol_lower_sym_rsqrt, keeping 1 / L_jj
+            double sacc = Pps[sidx(j, j)];
+            CGP_UNROLL for (int k = 0; k < j; k++) sacc = fma(-Lq[sidx(j, k)], Lq[sidx(j, k)], sacc);
+            const double r = fast_rsqrt(sacc);
+            rinv[j] = r;
+            Lq[sidx(j, j)] = sacc * r;
+            CGP_UNROLL for (int i = j + 1; i < D; i++) {
+                double tacc = Pps[sidx(i, j)];
+                CGP_UNROLL for (int k = 0; k < j; k++) tacc = fma(-Lq[sidx(i, k)], Lq[sidx(j, k)], tacc);
+                Lq[sidx(i, j)] = tacc * r;
+            }
+        }
+    }
+    // G = D Pp^{-1}: row r of G solves Pp g = (row r of D)^T
+    CGP_UNROLL for (int r = 0; r < D; r++) {
+        double z[D];
+        CGP_UNROLL for (int c = 0; c < D; c++) z[c] = Ds[r * D + c][tid];
+        CGP_UNROLL for (int i = 0; i < D; i++) {
+            double sacc = z[i];
+            CGP_UNROLL for (int k = 0; k < i; k++) sacc = fma(-Lq[sidx(i, k)], z[k], sacc);
+            z[i] = sacc * rinv[i];
+        }
+        CGP_UNROLL for (int i = D - 1; i >= 0; i--) {
+            double sacc = z[i];
+            CGP_UNROLL for (int k = i + 1; k < D; k++) sacc = fma(-Lq[sidx(k, i)], z[k], sacc);
+            z[i] = sacc * rinv[i];
+        }
+        CGP_UNROLL for (int c = 0; c < D; c += 2) *reinterpret_cast<double2 *>(rec + r * D + c) = make_double2(z[c], z[c + 1]);
+    }
+}
+
 }  // namespace cgp

@@ -54,6 +54,12 @@ int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t 
             const unsigned grid = (unsigned)ceil_div(items, block);
             if constexpr (Model::kLinear) {
                 sgp_gain_kernel<Model, 0><<<grid, block, 0, s>>>(p, io);
+            } else if (p.sigma_kind == CGP_SIGMA_CUBATURE && p.n_sigma == 2 * Model::D && Model::D >= 6) {
+                constexpr int D = Model::D;
+                const size_t smem = sizeof(double) * 64 * (D * (D + 1) / 2 + D * D);
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(cubature_gain_kernel<Model::NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cubature_gain_kernel<Model::NH><<<(unsigned)ceil_div(items, 64), 64, smem, s>>>(p, io);
             } else {
                 if (share) sgp_gain_kernel<Model, 3><<<grid, block, 0, s>>>(p, io);
                 else sgp_gain_kernel<Model, 0><<<grid, block, 0, s>>>(p, io);

@@ -117,7 +117,10 @@ def _sigma_tables(sgps, dev):
     hit = _sigma_cache.get(key)
     if hit is None:
         from .quadratures import SigmaPoints
-        order = SigmaPoints(int(xi.shape[1]), int(w.shape[0]), w, None, xi).gauss_hermite_order()
+        sp = SigmaPoints(int(xi.shape[1]), int(w.shape[0]), w, None, xi)
+        order = sp.gauss_hermite_order()
+        if order == 0 and sp.is_cubature():
+            order = -1                               # marks the cubature rule
         hit = (torch.as_tensor(w).to(dev), torch.as_tensor(xi).to(dev), order)
         _sigma_cache[key] = hit
     return hit
@@ -220,8 +223,9 @@ def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, X
         w, xi, order = sig
         p.n_sigma = int(w.shape[0])
         p.sig_w, p.sig_xi = _ptr(w), _ptr(xi)
-        p.sigma_kind = N.CGP_SIGMA_GAUSS_HERMITE if order else N.CGP_SIGMA_GENERIC
-        p.gh_order = order
+        p.sigma_kind = (N.CGP_SIGMA_GAUSS_HERMITE if order > 0 else
+                        (N.CGP_SIGMA_CUBATURE if order < 0 else N.CGP_SIGMA_GENERIC))
+        p.gh_order = max(order, 0)
     p.Xi, p.dt = float(Xi), float(dt)
     return p
 

@@ -90,6 +90,12 @@ class SigmaPoints(NamedTuple):
                 break
         return 0
 
+    def is_cubature(self) -> bool:
+        """True if this table is bit-identical to ``cubature(d)`` (lets the host pick kernels that use its structure)."""
+        ref = SigmaPoints.cubature(int(self.d))
+        return (int(self.n_points) == ref.n_points and np.array_equal(ref.xi, np.asarray(self.xi))
+                and np.array_equal(ref.w, np.asarray(self.w)))
+
     # host-side helpers with the reference's names (quadratures.py:198-231); NumPy only, never on the hot path
     def gen_sigma_points(self, m, chol_of_P):
         return np.asarray(m) + np.einsum('ij,...j->...i', np.asarray(chol_of_P), self.xi)

@@ -46,7 +46,8 @@ enum {
 /* sigma-point table layout hints (results do not depend on them; they select a kernel specialisation) */
 enum {
     CGP_SIGMA_GENERIC = 0,
-    CGP_SIGMA_GAUSS_HERMITE = 1 /* table is bit-identical to quadratures.py:157-196 with `gh_order` nodes/dim */
+    CGP_SIGMA_GAUSS_HERMITE = 1, /* table is bit-identical to quadratures.py:157-196 with `gh_order` nodes/dim */
+    CGP_SIGMA_CUBATURE = 2       /* table is bit-identical to quadratures.py:139-150 (2d points +-sqrt(d) e_j)       */
 };
 
 enum {
