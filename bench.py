@@ -118,12 +118,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_sample(n_chirps: int, nthreads: int = 0):
     """Times the CPU restatement of the reference path (oracle/, OpenMP over chirps) on `n_chirps` chirps of the
-    same workload; returns (steps/s, seconds, threads)."""
+    same workload (more than 1000: the 1000 synthetic chirps repeated); returns (steps/s, seconds, threads)."""
     from oracle import oracle as orc
     from chirpgp_b200.quadratures import SigmaPoints
     from chirpgp_b200 import toymodels
     orc.build()
-    _, ys, _ = toymodels.synthetic_batch(n_chirps, T, DT, Xi=XI, seed=2)
+    _, ys, _ = toymodels.synthetic_batch(min(n_chirps, B_PER_GPU), T, DT, Xi=XI, seed=2)
+    if n_chirps > ys.shape[0]:
+        ys = np.tile(ys, (-(-n_chirps // ys.shape[0]), 1))[:n_chirps]
     spec = orc.ChirpSpec(PARAMS[0], PARAMS[1], PARAMS[3], PARAMS[4])
     m0, P0, H = orc.chirp_m0_P0_H(PARAMS[2], PARAMS[3], PARAMS[4], PARAMS[5])
     sg = SigmaPoints.gauss_hermite(D, 3)
@@ -144,7 +146,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     rate, _, _ = cpu_sample(max(2 * cores, 16))                 # calibrate, then ~8 s of CPU work per timed step
-    n_chirps = int(min(1000, max(2 * cores, rate * 8. / T)))
+    n_chirps = int(min(8000, max(2 * cores, rate * 8. / T)))
     for _ in range(args.warmup):
         cpu_sample(max(cores, 4))
     vals, secs = [], []
@@ -353,7 +355,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             rate, _, _ = cpu_sample(max(2 * cores, 16))         # calibrate, then ~12 s of CPU work
-            n = int(min(1000, max(2 * cores, rate * 12. / T)))
+            n = int(min(8000, max(2 * cores, rate * 12. / T)))
             v, sec, threads = cpu_sample(n)
             cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                    'sample': '%d chirps x %d steps, GHF+GHS, oracle/ C restatement with OpenMP (%.1f s)' % (n, T, sec)}
