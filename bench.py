@@ -145,7 +145,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rate, _, _ = cpu_sample(max(2 * cores, 16))                 # calibrate, then ~8 s of CPU work per timed step
+    cpu_sample(max(2 * cores, 16))                              # spin up the OpenMP team
+    rate, _, _ = cpu_sample(max(4 * cores, 32))                 # calibrate, then ~8 s of CPU work per timed step
     n_chirps = int(min(8000, max(2 * cores, rate * 8. / T)))
     for _ in range(args.warmup):
         cpu_sample(max(cores, 4))
@@ -354,7 +355,8 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            rate, _, _ = cpu_sample(max(2 * cores, 16))         # calibrate, then ~12 s of CPU work
+            cpu_sample(max(2 * cores, 16))                      # spin up the OpenMP team
+            rate, _, _ = cpu_sample(max(4 * cores, 32))         # calibrate, then ~12 s of CPU work
             n = int(min(8000, max(2 * cores, rate * 12. / T)))
             v, sec, threads = cpu_sample(n)
             cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
