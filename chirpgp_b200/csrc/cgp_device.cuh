@@ -206,6 +206,12 @@ template <int D> CGP_DEV void lower_to_full(const double (&S)[NSym<D>::value], d
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) F[r][c] = (c <= r) ? S[sidx(r, c)] : 0.;
 }
 
+// -norm.logpdf(y, pred, sqrt(S)) in jax.scipy.stats.norm.logpdf's operation order (filters_smoothers.py:44-45):
+// (log(2 pi sc^2) + r^2 / sc^2) / 2 with sc = sqrt(S); sqrt, log and the division through the short-chain routines.
+CGP_DEV double nll_increment(double S, double r) {
+    const double sc = sqrt(S), sc2 = sc * sc;
+    return fma(r * r, fast_rcp(sc2), fast_log_pos(kTwoPi * sc2)) * 0.5;
+}
 // ------------------------------------------------------------------------------------------------ measurement update
 // filters_smoothers.py:55-68; returns the nll increment  (log(2 pi sc^2) + (y - pred)^2 / sc^2) / 2, sc = sqrt(S)
 template <int D>
@@ -218,19 +224,19 @@ CGP_DEV double linear_update(const double (&mp)[D], const double (&Pp)[D][D], co
         S = (j == 0) ? hp * H[0] : fma(hp, H[j], S);
     }
     S += Xi;
+    const double rS = fast_rcp(S);                    // K = Pp h / S with one reciprocal (<= 1 ulp per entry)
     double K[D];
     CGP_UNROLL for (int i = 0; i < D; i++) {
         double s = Pp[i][0] * H[0];
         CGP_UNROLL for (int j = 1; j < D; j++) s = fma(Pp[i][j], H[j], s);
-        K[i] = s / S;
+        K[i] = s * rS;
     }
     double pred = H[0] * mp[0];
     CGP_UNROLL for (int i = 1; i < D; i++) pred = fma(H[i], mp[i], pred);
     double r = y - pred;
     CGP_UNROLL for (int i = 0; i < D; i++) mf[i] = fma(K[i], r, mp[i]);
     CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) Pf[i][j] = Pp[i][j] - (K[i] * K[j]) * S;
-    double sc = sqrt(S), sc2 = sc * sc;
-    return (log(kTwoPi * sc2) + r * r / sc2) * 0.5;
+    return nll_increment(S, r);
 }
 // same on packed-symmetric covariances (exactly symmetric inputs stay exactly symmetric)
 template <int D>
@@ -245,16 +251,16 @@ CGP_DEV double linear_update_sym(const double (&mp)[D], const double (&Pp)[NSym<
     double S = PH[0] * H[0];
     CGP_UNROLL for (int j = 1; j < D; j++) S = fma(PH[j], H[j], S);
     S += Xi;
+    const double rS = fast_rcp(S);
     double K[D];
-    CGP_UNROLL for (int i = 0; i < D; i++) K[i] = PH[i] / S;
+    CGP_UNROLL for (int i = 0; i < D; i++) K[i] = PH[i] * rS;
     double pred = H[0] * mp[0];
     CGP_UNROLL for (int i = 1; i < D; i++) pred = fma(H[i], mp[i], pred);
     double r = y - pred;
     CGP_UNROLL for (int i = 0; i < D; i++) mf[i] = fma(K[i], r, mp[i]);
     CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j <= i; j++)
         Pf[sidx(i, j)] = Pp[sidx(i, j)] - (K[i] * K[j]) * S;
-    double sc = sqrt(S), sc2 = sc * sc;
-    return (log(kTwoPi * sc2) + r * r / sc2) * 0.5;
+    return nll_increment(S, r);
 }
 
 // measurement update on packed-symmetric covariance with one reciprocal; H generic or the unit vector e_1.
@@ -289,11 +295,6 @@ CGP_DEV void linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym<D
         Pf[sidx(i, j)] = fma(-(K[i] * K[j]), S, Pp[sidx(i, j)]);
     S_out = S;
     r_out = r;
-}
-// -norm.logpdf(y, pred, sqrt(S)) in jax.scipy.stats.norm.logpdf's operation order (filters_smoothers.py:44-45)
-CGP_DEV double nll_increment(double S, double r) {
-    const double sc = sqrt(S), sc2 = sc * sc;
-    return (log(kTwoPi * sc2) + r * r / sc2) * 0.5;
 }
 
 // ------------------------------------------------------------------------------------------------ models
