@@ -36,12 +36,13 @@ N_SIGMA = 81
 METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
 UNIT = 'steps/s'
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one ghf_filter_kernel launch (ncu --set full, profiles/r1_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 494_872_504      # 25.5 MB read + 469.3 MB written; algorithmic: 552.8 MB (nell + ys counted, L2 absorbs part)
+# dram__bytes_read.sum + dram__bytes_write.sum of one gh_duo_filter_kernel launch (ncu --set full, profiles/r1_ncu_summary.txt)
+NCU_TRAFFIC_BYTES = 1_402_062_456    # 26.1 MB read + 1375.9 MB written: 552.8 MB algorithmic + 904.6 MB smoother workspace
 
 # algorithmic bytes / flops per chirp time-step (DESIGN.md "Roofline accounting")
 BYTES_FILTER = 8 + 8 * (D + D * D + 1)          # ys in, mf + Pf + nell out                      = 176
 BYTES_SMOOTHER = 2 * 8 * (D + D * D)            # mf, Pf in; ms, Ps out                          = 320
+BYTES_WORKSPACE = 8 * (2 * D * D + D)           # [G | mp | Pp] record the filter leaves for the sweep  = 288 (not algorithmic)
 FLOPS_FILTER = 9403                             # sgp_filter, d=4, n=81, counting convention v1
 FLOPS_SMOOTHER = 13668                          # sgp_smoother
 
@@ -377,13 +378,15 @@ def run_ours(args):
                     'ms_per_step_wall_clock': ms_e2e_wall, 'ms_single_step_latency': ms_e2e_single,
                     'what': 'pinned host ys -> cg.sgp_filter -> cg.sgp_smoother -> pinned host (mss, Pss); steps issued on '
                             'two alternating streams so the D2H copy of one step overlaps the filter of the next'},
-            'gpu_launches': args.steps * 3,
-            'kernels_per_step': ['gh_warp_filter_kernel<GhPredictLCD<1,3>>', 'sgp_gain_kernel<ModelLCD<1>,3>', 'smoother_sweep_lane4_kernel'],
-            'roofline': {'bound': 'hbm', 'kernel': 'gh_warp_filter_kernel<GhPredictLCD<1,3>> (sgp_filter, warp per chirp)', 'achieved': ach_gbs,
+            'gpu_launches': args.steps * 2,
+            'kernels_per_step': ['gh_duo_filter_kernel (sgp_filter + smoother gains)', 'smoother_sweep_lane4_kernel (sgp_smoother)'],
+            'roofline': {'bound': 'hbm', 'kernel': 'gh_duo_filter_kernel (sgp_filter + smoother gains, producer/consumer warp pair per chirp)',
+                         'achieved': ach_gbs,
                          'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': NCU_TRAFFIC_BYTES,
                          'peak_source': hbm_src, 'kernel_ms': ms_filter,
-                         'algorithmic_bytes_per_step': BYTES_FILTER},
-            'roofline_fp64': {'bound': 'fp64', 'kernel': 'gh_warp_filter_kernel<GhPredictLCD<1,3>>', 'achieved': ach_tf, 'peak': fp64_peak,
+                         'algorithmic_bytes_per_step': BYTES_FILTER, 'workspace_bytes_per_step': BYTES_WORKSPACE,
+                         'note': 'latency-bound, not bandwidth-bound: see roofline_fp64 and DESIGN.md section 4'},
+            'roofline_fp64': {'bound': 'fp64', 'kernel': 'gh_duo_filter_kernel', 'achieved': ach_tf, 'peak': fp64_peak,
                               'unit': 'TFLOP/s', 'frac': ach_tf / fp64_peak if fp64_peak else None,
                               'flops_per_step': flops_per_step('sgp_filter'),
                               'peak_source': 'DFMA-only kernel measured in this run',

@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 
 CGP_MODEL_LINEAR_DISC, CGP_MODEL_LCD, CGP_MODEL_LINEAR_SDE, CGP_MODEL_SDE = 0, 1, 2, 3
 CGP_SIGMA_GENERIC, CGP_SIGMA_GAUSS_HERMITE, CGP_SIGMA_CUBATURE = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _ERRORS = {-1: 'CGP_ERR_BAD_ARG', -2: 'CGP_ERR_UNSUPPORTED (no kernel compiled for this model / state dimension)',
            -3: 'CGP_ERR_WORKSPACE'}
@@ -39,6 +39,7 @@ FILTER_FUNCS = ('kf', 'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
 SMOOTHER_FUNCS = ('rts', 'eks', 'sgp_smoother', 'cd_eks', 'cd_sgp_smoother')
 EXPORTED = (['cgp_abi_version', 'cgp_workspace_bytes'] + ['cgp_%s_f64' % f for f in FILTER_FUNCS + SMOOTHER_FUNCS]
             + ['cgp_ekf_nll_default_ckpt', 'cgp_ekf_nll_workspace_bytes', 'cgp_ekf_nll_fwd_f64', 'cgp_ekf_nll_bwd_f64',
+               'cgp_sgp_filter_gains_fused', 'cgp_sgp_filter_gains_f64', 'cgp_smoother_sweep_f64',
                'cgp_bench_dfma', 'cgp_test_math'])
 
 _lib = None
@@ -76,6 +77,14 @@ def lib():
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.c_size_t, C.c_void_p]
+        L.cgp_sgp_filter_gains_fused.restype = C.c_int
+        L.cgp_sgp_filter_gains_fused.argtypes = [C.POINTER(CgpProblem)]
+        L.cgp_sgp_filter_gains_f64.restype = C.c_int
+        L.cgp_sgp_filter_gains_f64.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_size_t, C.c_void_p]
+        L.cgp_smoother_sweep_f64.restype = C.c_int
+        L.cgp_smoother_sweep_f64.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p]
         L.cgp_ekf_nll_default_ckpt.restype = C.c_int64
         L.cgp_ekf_nll_default_ckpt.argtypes = [C.c_int64]
         L.cgp_ekf_nll_workspace_bytes.restype = C.c_size_t

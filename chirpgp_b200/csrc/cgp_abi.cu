@@ -77,8 +77,35 @@ int cgp_cd_sgp_filter_f64(const CgpProblem *p, const double *ys, double *mfs, do
 
 size_t cgp_workspace_bytes(const char *fn, const CgpProblem *p) {
     if (!fn || !p) return 0;
-    if (!strcmp(fn, "rts") || !strcmp(fn, "eks") || !strcmp(fn, "sgp_smoother")) return disc_ws_bytes(p);
+    if (!strcmp(fn, "rts") || !strcmp(fn, "eks") || !strcmp(fn, "sgp_smoother") || !strcmp(fn, "sgp_filter_gains") ||
+        !strcmp(fn, "smoother_sweep"))
+        return disc_ws_bytes(p);
     return 0;
+}
+
+int cgp_sgp_filter_gains_fused(const CgpProblem *p) {
+    if (!p) return 0;
+    return sgp_filter_fuses_gains(*p) ? 1 : 0;
+}
+int cgp_sgp_filter_gains_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell, int last_only,
+                             void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_filter(p, ys, mfs, Pfs);
+    if (rc) return rc;
+    if ((rc = check_sigma(p))) return rc;
+    if (!mfs || !Pfs) return CGP_ERR_BAD_ARG;
+    if (!ws || ws_bytes < disc_ws_bytes(p)) return CGP_ERR_WORKSPACE;
+    if (sgp_filter_fuses_gains(*p) && aligned16(ws))
+        return launch_sgp_filter(*p, FilterIO{ys, mfs, Pfs, nell, last_only, (double *)ws}, (cudaStream_t)stream);
+    rc = launch_sgp_filter(*p, FilterIO{ys, mfs, Pfs, nell, last_only}, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_sgp_gains(*p, SmootherIO{mfs, Pfs, nullptr, nullptr, (double *)ws}, (cudaStream_t)stream);
+}
+int cgp_smoother_sweep_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss, void *ws,
+                           size_t ws_bytes, void *stream) {
+    if (!p || p->B < 1 || p->T < 1 || p->d < 1) return CGP_ERR_BAD_ARG;
+    if (!mfs || !Pfs || !mss || !Pss || mss == mfs || Pss == Pfs) return CGP_ERR_BAD_ARG;
+    if (!ws || ws_bytes < disc_ws_bytes(p)) return CGP_ERR_WORKSPACE;
+    return launch_smoother_sweep(*p, SmootherIO{mfs, Pfs, mss, Pss, (double *)ws}, (cudaStream_t)stream);
 }
 
 int cgp_rts_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss, void *ws,

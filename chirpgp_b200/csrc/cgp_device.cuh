@@ -291,8 +291,9 @@ CGP_DEV void linear_update_fast(const double (&mp)[D], const double (&Pp)[NSym<D
     CGP_UNROLL for (int i = 0; i < D; i++) K[i] = PH[i] * rS;
     const double r = y - pred;
     CGP_UNROLL for (int i = 0; i < D; i++) mf[i] = fma(K[i], r, mp[i]);
+    // Pf = Pp - K K^T S (:66) with K_j S = (Pp h)_j: one fma per entry (K_i (Pp h)_j instead of (K_i K_j) S, <= 1 ulp apart)
     CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j <= i; j++)
-        Pf[sidx(i, j)] = fma(-(K[i] * K[j]), S, Pp[sidx(i, j)]);
+        Pf[sidx(i, j)] = fma(-K[i], PH[j], Pp[sidx(i, j)]);
     S_out = S;
     r_out = r;
 }

@@ -1,6 +1,6 @@
 // cgp_dispatch.cuh -- runtime (model, d, group size) -> compiled kernel instance.
 #pragma once
-#include "cgp_fast.cuh"
+#include "cgp_duo.cuh"
 
 namespace cgp {
 
@@ -83,6 +83,9 @@ int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s);
 int launch_cd_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s);
 int launch_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s);
 int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t s);
+int launch_sgp_gains(const CgpProblem &p, const SmootherIO &io, cudaStream_t s);
+int launch_smoother_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_t s);
+bool sgp_filter_fuses_gains(const CgpProblem &p);
 int launch_cd_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s);
 int launch_cd_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t s);
 

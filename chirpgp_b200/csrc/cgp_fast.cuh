@@ -42,6 +42,25 @@ CGP_DEV void warp_sum_smem(const double (&a)[NA], double (*red)[33], double *res
     }
 }
 
+// NB <= 8 partial sums e[] per lane -> totals at dst[0..NB) (shared memory).  red2 is [NB][36]: FOUR lanes per sum, lane
+// 4 k + h adds the partials h, h + 4, ..., h + 28 of sum k in a fixed tree and two shuffle steps join the four quarters
+// (pitch 36 = 4 mod 16 keeps the 16 lanes of a half-warp on 16 different banks).
+// The caller has stored red2[k][lane] = e[k] and synchronised the warp.
+constexpr int kSmallSumPitch = 36;
+template <int NB> CGP_DEV void small_sums_tail(double (*red2)[kSmallSumPitch], double *dst, int lane) {
+    static_assert(NB <= 8, "four lanes per sum");
+    const int k = lane >> 2, h = lane & 3;
+    const bool ok = k < NB;
+    double v[8];
+    CGP_UNROLL for (int j = 0; j < 8; j++) v[j] = red2[ok ? k : 0][h + 4 * j];
+    CGP_UNROLL for (int w2 = 1; w2 < 8; w2 <<= 1)
+        CGP_UNROLL for (int j = 0; j + w2 < 8; j += 2 * w2) v[j] += v[j + w2];
+    double sacc = v[0];
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+    if (ok && h == 0) dst[k] = sacc;
+}
+
 // Per-lane slice of a Gauss-Hermite table with P nodes per dimension (quadratures.py:157-196, dimension 0 fastest):
 // lane l owns base index l < nb = P^(D-1); its P points l + c nb share xi[0..D-2] and differ in the last coordinate.
 template <int D, int P> struct GhLane {
@@ -80,8 +99,27 @@ template <int NH, int P, int DBG = 0> struct GhPredictLCD {
         mdl.load(p.consts + b * p.consts_stride, p.dt);
         tab.load(p, lane);
     }
+    // Cross-covariance of the smoother (filters_smoothers.py:525), D = sum_i w_i chi_i mu_i^T - m mp^T = L E with
+    // E = sum_i w_i xi_i mu_i^T (chi_i = m + L xi_i).  Which of the D*D entries of E need the quadrature:
+    //   * the Matern rows mu[V], mu[V+1] are LINEAR in chi, so their columns of D are F P exactly in exact arithmetic (the
+    //     rule integrates polynomials of degree <= 2 exactly: sum w xi = 0, sum w xi xi^T = I); they are formed from the
+    //     filtering covariance when the gain is evaluated (gain_record);
+    //   * the chirp rows mu[0..V-1] do not depend on chi[D-1], hence not on xi[D-1]: E[D-1][0..V-1] = 0.
+    // Left: NE = (D-1) V sums, E[c][q] = sum_l xb_l[c] W_l ev_l[q] over the base indices l (the reference's 81-term sums up
+    // to rounding: ~1e-16 relative, six orders below the algorithm's summation-order noise, tests/test_noise_floor.py).
+    static constexpr int NE = (D - 1) * V;
+    static CGP_DEV void cross_partials(const GhLane<D, P> &tab, const double (&ev)[V], double (&ec)[NE]) {
+        CGP_UNROLL for (int c = 0; c < D - 1; c++)
+            CGP_UNROLL for (int q = 0; q < V; q++) ec[c * V + q] = tab.xb[c] * (tab.Wl * ev[q]);
+    }
     CGP_DEV void predict(double (*red)[33], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&mp)[D],
                          double (&Pp)[NS]) const {
+        predict_impl<false>(red, res, nullptr, lane, m, Pc, mp, Pp);
+    }
+    // EXPORT: the cross sums are formed by another warp (cgp_duo.cuh); this lane leaves ev[0..V-1] at xop[0..V-1][lane].
+    template <bool EXPORT>
+    CGP_DEV void predict_impl(double (*red)[33], double *res, double (*xop)[33], int lane, const double (&m)[D],
+                              const double (&Pc)[NS], double (&mp)[D], double (&Pp)[NS]) const {
         double L[NS];
         if constexpr (DBG == 3) { CGP_UNROLL for (int i = 0; i < NS; i++) L[i] = Pc[i]; }
         else chol_lower_sym_rsqrt<D>(Pc, L);
@@ -117,6 +155,9 @@ template <int NH, int P, int DBG = 0> struct GhPredictLCD {
                 a[D + sidx(V + 1, q)] = ev[q] * S1;
             }
             a[D + sidx(V, V)] = q00; a[D + sidx(V + 1, V)] = q10; a[D + sidx(V + 1, V + 1)] = q11;
+            if constexpr (EXPORT) {
+                CGP_UNROLL for (int q = 0; q < V; q++) xop[q][lane] = ev[q];
+            }
         }
         double tot[NA];
         if constexpr (DBG == 1) { CGP_UNROLL for (int k = 0; k < NA; k++) tot[k] = a[k] * 27.; }
@@ -182,6 +223,66 @@ template <int NH, int P> struct GhRhsSDE {
             dP[sidx(r, c)] = (tot[D + r * D + c] + tot[D + c * D + r]) + Qc[sidx(r, c)];
     }
 };
+
+// Smoother workspace record [G | mp | Pp] of one step (filters_smoothers.py:520-527, :81-82) for ModelLCD<NH> from
+//   Ein  (D-1) x V cross sums (GhPredictLCD::cross_partials),
+//   tot  D + NSym moment totals (sum_i w_i mu_i | sum_i w_i (mu_i mu_i^T + Sigma), packed lower),
+//   Pq   packed filtering covariance the prediction started from,
+//   f    the Matern transition block [f00, f01, f10, f11] (models.py:61-73).
+// L = chol(Pq);  D[:, q] = L E[:, q] for the chirp columns,  D[:, V+t] = f_t0 P[:, V] + f_t1 P[:, V+1] for the linear ones;
+// mp = tot[0..D),  Pp = tot - mp mp^T;  G = D Pp^{-1} (row r of G solves Pp g = D_r^T).
+// `rec` may alias Ein / tot (everything is read before anything is written).
+template <int NH>
+CGP_DEV void gain_record(const double *Ein, const double *tot, const double (&Pq)[NSym<2 * NH + 2>::value], const double (&f)[4],
+                         double *rec) {
+    constexpr int D = 2 * NH + 2, V = D - 2, NS = NSym<D>::value, DD = D * D, NE = (D - 1) * V;
+    double E[NE], mp[D], Pp[NS], L[NS];
+    chol_lower_sym_rsqrt<D>(Pq, L);
+    load_vec<NE>(Ein, E);
+    load_vec<D>(tot, mp);
+    {
+        double tp[NS];
+        load_vec<NS>(tot + D, tp);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++)
+            Pp[sidx(r, q)] = fma(-mp[r], mp[q], tp[sidx(r, q)]);              // as GhPredictLCD::predict_impl
+    }
+    double Lq[NS], rinv[D];
+    CGP_UNROLL for (int j = 0; j < D; j++) {                 // chol_lower_sym_rsqrt, keeping 1 / L_jj
+        double sacc = Pp[sidx(j, j)];
+        CGP_UNROLL for (int k = 0; k < j; k++) sacc = fma(-Lq[sidx(j, k)], Lq[sidx(j, k)], sacc);
+        const double r = fast_rsqrt(sacc);
+        rinv[j] = r;
+        Lq[sidx(j, j)] = sacc * r;
+        CGP_UNROLL for (int i = j + 1; i < D; i++) {
+            double tacc = Pp[sidx(i, j)];
+            CGP_UNROLL for (int k = 0; k < j; k++) tacc = fma(-Lq[sidx(i, k)], Lq[sidx(j, k)], tacc);
+            Lq[sidx(i, j)] = tacc * r;
+        }
+    }
+    CGP_UNROLL for (int r = 0; r < D; r++) {
+        double z[D];
+        CGP_UNROLL for (int q = 0; q < V; q++) {             // chirp columns of row r of D = L E  (E[D-1][.] = 0)
+            double sacc = L[sidx(r, 0)] * E[q];
+            CGP_UNROLL for (int k = 1; k <= r && k < D - 1; k++) sacc = fma(L[sidx(r, k)], E[k * V + q], sacc);
+            z[q] = sacc;
+        }
+        z[V] = fma(f[1], Pq[sidx(r, V + 1)], f[0] * Pq[sidx(r, V)]);
+        z[V + 1] = fma(f[3], Pq[sidx(r, V + 1)], f[2] * Pq[sidx(r, V)]);
+        CGP_UNROLL for (int i = 0; i < D; i++) {
+            double sacc = z[i];
+            CGP_UNROLL for (int k = 0; k < i; k++) sacc = fma(-Lq[sidx(i, k)], z[k], sacc);
+            z[i] = sacc * rinv[i];
+        }
+        CGP_UNROLL for (int i = D - 1; i >= 0; i--) {
+            double sacc = z[i];
+            CGP_UNROLL for (int k = i + 1; k < D; k++) sacc = fma(-Lq[sidx(k, i)], z[k], sacc);
+            z[i] = sacc * rinv[i];
+        }
+        store_vec<D>(rec + r * D, z);
+    }
+    store_vec<D>(rec + DD, mp);
+    store_sym<D>(rec + DD + D, Pp);
+}
 
 // sgp_filter (filters_smoothers.py:446-490, Pred = GhPredictLCD) / cd_sgp_filter (:534-582, Pred = GhRhsSDE + RK4) with a
 // Gauss-Hermite table whose P^(D-1) base indices fit one warp.  ONE WARP PER CHIRP; mean, covariance and Cholesky

@@ -21,7 +21,15 @@ static int launch_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t 
     return check_launch();
 }
 
-int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+// The filter kernel that also fills the smoother workspace exists for the headline configuration (chirp LCD model,
+// Gauss-Hermite order 3, warp per chirp); everything else runs the filter and then the time-parallel gain kernel.
+bool sgp_filter_fuses_gains(const CgpProblem &p) {
+    return p.model == CGP_MODEL_LCD && p.num_harmonics == 1 && p.d == 4 && use_share(p);
+}
+
+int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s) {
+    FilterIO io = io_in;
+    if (io.ws != nullptr && (io.mfs == nullptr || !sgp_filter_fuses_gains(p) || !aligned16(io.ws))) io.ws = nullptr;
     const bool share = use_share(p);
     const int g = group_size(p, share);
     return dispatch_disc(p, [&](auto tag) {
@@ -31,7 +39,7 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
         } else {
             // Very large batches are FP64-throughput-bound: one thread per chirp (all sigma points serially, no
             // replicated work, no shuffles) issues ~2.4x fewer FP64 warp-instructions per step than a warp per chirp.
-            if (p.B >= kThreadPerChirpMinB) {
+            if (p.B >= kThreadPerChirpMinB && io.ws == nullptr) {
                 if (share) return launch_sgp_one<Model, 1, 3>(p, io, s);
                 return launch_sgp_one<Model, 1, 0>(p, io, s);
             }
@@ -39,6 +47,12 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
                 // headline path: chirp model, Gauss-Hermite order 3 -> 27 base indices, one per lane
                 if (share) {
                     using Pred = GhPredictLCD<1, 3>;
+                    if (io.ws != nullptr) {
+                        // filter + smoother gains: producer / consumer warp pair per chirp (cgp_duo.cuh)
+                        if (p.h_unit_index == 1) gh_duo_filter_kernel<true><<<(unsigned)p.B, 64, 0, s>>>(p, io);
+                        else gh_duo_filter_kernel<false><<<(unsigned)p.B, 64, 0, s>>>(p, io);
+                        return check_launch();
+                    }
                     if (p.h_unit_index == 1) gh_warp_filter_kernel<Pred, false, true><<<(unsigned)p.B, 32, 0, s>>>(p, io);
                     else gh_warp_filter_kernel<Pred, false, false><<<(unsigned)p.B, 32, 0, s>>>(p, io);
                     return check_launch();

@@ -22,6 +22,7 @@ struct FilterIO {
     double *__restrict__ Pfs;
     double *__restrict__ nell;
     int nell_last_only;
+    double *__restrict__ ws = nullptr;     // fused filter + smoother gains: SmootherIO::ws records, filled by the filter
 };
 struct SmootherIO {
     const double *__restrict__ mfs;

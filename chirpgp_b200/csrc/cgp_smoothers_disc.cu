@@ -44,7 +44,8 @@ int launch_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
     });
 }
 
-int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+// Time-parallel half of sgp_smoother (filters_smoothers.py:520-527): fills io.ws for steps 0 .. T-2.
+int launch_sgp_gains(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
     const bool share = use_share(p);
     return dispatch_disc(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
@@ -64,11 +65,29 @@ int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t 
                 if (share) sgp_gain_kernel<Model, 3><<<grid, block, 0, s>>>(p, io);
                 else sgp_gain_kernel<Model, 0><<<grid, block, 0, s>>>(p, io);
             }
-            int rc = check_launch();
-            if (rc) return rc;
+            return check_launch();
         }
-        return launch_sweep<Model::D>(p, io, s);
+        return 0;
     });
+}
+
+// Sequential half (filters_smoothers.py:83-84) on a filled workspace; needs only B, T, d of the problem.
+int launch_smoother_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    switch (p.d) {
+        case 1: return launch_sweep<1>(p, io, s);
+        case 2: return launch_sweep<2>(p, io, s);
+        case 3: return launch_sweep<3>(p, io, s);
+        case 4: return launch_sweep<4>(p, io, s);
+        case 6: return launch_sweep<6>(p, io, s);
+        case 8: return launch_sweep<8>(p, io, s);
+        default: return CGP_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_sgp_smoother(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
+    int rc = launch_sgp_gains(p, io, s);
+    if (rc) return rc;
+    return launch_smoother_sweep(p, io, s);
 }
 
 }  // namespace cgp

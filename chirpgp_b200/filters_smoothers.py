@@ -19,6 +19,7 @@ Differences that follow from running compiled kernels instead of traced Python c
   ``mfs`` (NumPy in -> NumPy out, CUDA tensor in -> CUDA tensors out, no host round trip).
 """
 import ctypes as C
+import os
 from typing import Tuple
 
 import numpy as np
@@ -32,6 +33,9 @@ __all__ = ['kf', 'rts', 'ekf', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smo
            'cd_sgp_smoother']
 
 _F64 = torch.float64
+
+# sgp_filter on CUDA tensors also produces the smoother gains (see `sgp_filter`); CHIRPGP_B200_FUSE_GAINS=0 turns it off
+FUSE_SMOOTHER_GAINS = os.environ.get('CHIRPGP_B200_FUSE_GAINS', '1') != '0'
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -230,7 +234,23 @@ def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, X
     return p
 
 
-def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, store=True, last_only=False):
+class _SmootherGains:
+    """Smoother workspace ([G | mp | Pp] per (chirp, step)) that a filter call produced together with (mfs, Pfs).  Rides
+    on the returned ``mfs`` tensor; the smoother uses it only if it is called with exactly those tensors, unmodified, and
+    the same model constants / sigma points / dt -- otherwise it recomputes the gains."""
+    __slots__ = ('ws', 'nbytes', 'mfs_ptr', 'Pfs_ptr', 'mfs_version', 'Pfs_ref', 'Pfs_version', 'consts', 'consts_version',
+                 'sig', 'dt', 'shape', 'smoother')
+
+    def matches(self, smoother, mfs, Pfs, consts, sig, dt):
+        return (self.smoother == smoother and mfs.data_ptr() == self.mfs_ptr and Pfs.data_ptr() == self.Pfs_ptr
+                and mfs._version == self.mfs_version and Pfs._version == self.Pfs_version
+                and tuple(mfs.shape) == self.shape
+                and consts.data_ptr() == self.consts.data_ptr() and consts._version == self.consts_version
+                and sig is self.sig and dt == self.dt)
+
+
+def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, store=True, last_only=False,
+                gains_for=None):
     dev = _device()
     L = N.lib()
     kind = _kind(ys)
@@ -269,15 +289,35 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
     Pfs = torch.empty((B, T, d, d), dtype=_F64, device=dev) if store else None
     nell = torch.empty((B,) if last_only else (B, T), dtype=_F64, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    rc = getattr(L, 'cgp_%s_f64' % name)(C.byref(p), _ptr(ys2), _ptr(mfs), _ptr(Pfs), _ptr(nell), int(last_only), stream)
-    N.check(rc, name)
+    rec = None
+    if gains_for is not None and store and kind[0] == 'torch' and kind[1] == dev and T > 1:
+        nbytes = L.cgp_workspace_bytes(b'sgp_filter_gains', C.byref(p))
+        try:
+            ws = torch.empty((max(nbytes, 8) // 8,), dtype=_F64, device=dev)
+        except torch.OutOfMemoryError:
+            ws = None                    # not enough memory to keep the gains: the smoother will recompute them
+        if ws is not None:
+            rc = L.cgp_sgp_filter_gains_f64(C.byref(p), _ptr(ys2), _ptr(mfs), _ptr(Pfs), _ptr(nell), int(last_only),
+                                            _ptr(ws), C.c_size_t(nbytes), stream)
+            N.check(rc, name)
+            rec = _SmootherGains()
+            rec.ws, rec.nbytes, rec.consts, rec.consts_version = ws, nbytes, consts_t, consts_t._version
+            rec.sig, rec.dt, rec.smoother = sig, float(dt), gains_for
+    if rec is None:
+        rc = getattr(L, 'cgp_%s_f64' % name)(C.byref(p), _ptr(ys2), _ptr(mfs), _ptr(Pfs), _ptr(nell), int(last_only), stream)
+        N.check(rc, name)
     if store:
         mfs = mfs.reshape(out_lead + (T, d))
         Pfs = Pfs.reshape(out_lead + (T, d, d))
     nell = nell.reshape(out_lead if last_only else out_lead + (T,))
     if not store:
         return _back(nell, kind)
-    return _back(mfs, kind), _back(Pfs, kind), _back(nell, kind)
+    mfs, Pfs = _back(mfs, kind), _back(Pfs, kind)
+    if rec is not None:
+        rec.mfs_ptr, rec.Pfs_ptr, rec.shape = mfs.data_ptr(), Pfs.data_ptr(), tuple(mfs.shape)
+        rec.mfs_version, rec.Pfs_version = mfs._version, Pfs._version
+        mfs._cgp_smoother_gains = rec
+    return mfs, Pfs, _back(nell, kind)
 
 
 def _run_smoother(name, model, consts, mfs, Pfs, dt, sgps=None, Qc=None):
@@ -306,11 +346,18 @@ def _run_smoother(name, model, consts, mfs, Pfs, dt, sgps=None, Qc=None):
     p = _problem(B, T, model_id, d, nh, consts_t, cs, None, 0, None, 0, None, Qc_t, Qs, sig, 0., dt)
     mss = torch.empty_like(m2)
     Pss = torch.empty_like(P2)
-    nbytes = L.cgp_workspace_bytes(name.encode(), C.byref(p))
-    ws = torch.empty((max(nbytes, 8) // 8,), dtype=_F64, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    rc = getattr(L, 'cgp_%s_f64' % name)(C.byref(p), _ptr(m2), _ptr(P2), _ptr(mss), _ptr(Pss), _ptr(ws),
-                                         C.c_size_t(nbytes), stream)
+    rec = getattr(mfs, '_cgp_smoother_gains', None) if isinstance(mfs, torch.Tensor) else None
+    if (rec is not None and isinstance(Pfs, torch.Tensor) and mfs_t.data_ptr() == mfs.data_ptr()
+            and rec.matches(name, mfs, Pfs, consts_t, sig, float(dt))):
+        # the filter call that produced (mfs, Pfs) already evaluated the gains: only the sequential sweep is left
+        rc = L.cgp_smoother_sweep_f64(C.byref(p), _ptr(m2), _ptr(P2), _ptr(mss), _ptr(Pss), _ptr(rec.ws),
+                                      C.c_size_t(rec.nbytes), stream)
+    else:
+        nbytes = L.cgp_workspace_bytes(name.encode(), C.byref(p))
+        ws = torch.empty((max(nbytes, 8) // 8,), dtype=_F64, device=dev)
+        rc = getattr(L, 'cgp_%s_f64' % name)(C.byref(p), _ptr(m2), _ptr(P2), _ptr(mss), _ptr(Pss), _ptr(ws),
+                                             C.c_size_t(nbytes), stream)
     N.check(rc, name)
     return _back(mss.reshape(out_lead + (T, d)), kind), _back(Pss.reshape(out_lead + (T, d, d)), kind)
 
@@ -347,11 +394,19 @@ def eks(cond_m_cov, mfs, Pfs, dt) -> Tuple:
     return _run_smoother('eks', model, _consts_on_device(model, dt, _device(), dt), mfs, Pfs, dt)
 
 
-def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys) -> Tuple:
-    """Sigma-point (Gauss--Hermite / cubature) filter (filters_smoothers.py:446-490)."""
+def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, *, smoother_gains=None) -> Tuple:
+    """Sigma-point (Gauss--Hermite / cubature) filter (filters_smoothers.py:446-490).
+
+    ``smoother_gains`` (extension; default: on for CUDA-tensor ``ys``, see ``FUSE_SMOOTHER_GAINS``): the filter kernel
+    also evaluates what ``sgp_smoother``'s reverse scan computes from the filtering result alone (:520-527 -- the
+    sigma-point prediction from (mf_k, Pf_k) is the one the filter makes for step k + 1) and leaves it in a device
+    workspace attached to the returned ``mfs``; ``sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt)`` on those very tensors
+    then only runs the sequential sweep (:83-84).  Any other input to the smoother takes the stand-alone path."""
     dt = float(dt)
     model = _disc_model(cond_m_cov, _state_dim(m0), dt)
-    return _run_filter('sgp_filter', model, _consts_on_device(model, dt, _device(), dt), H, Xi, m0, P0, dt, ys, sgps=sgps)
+    fuse = FUSE_SMOOTHER_GAINS if smoother_gains is None else bool(smoother_gains)
+    return _run_filter('sgp_filter', model, _consts_on_device(model, dt, _device(), dt), H, Xi, m0, P0, dt, ys, sgps=sgps,
+                       gains_for='sgp_smoother' if fuse else None)
 
 
 def sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt) -> Tuple:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CGP_ABI_VERSION 1
+#define CGP_ABI_VERSION 2
 
 /* model ids (chirpgp_b200/models.py uses the same numbers) */
 enum {
@@ -112,6 +112,20 @@ int cgp_cd_eks_f64(const CgpProblem *p, const double *mfs, const double *Pfs, do
                    void *workspace, size_t workspace_bytes, void *stream);       /* :400-443 */
 int cgp_cd_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
                             void *workspace, size_t workspace_bytes, void *stream); /* :585-632 */
+
+/* ---- fused filter + smoother gains.  sgp_smoother's reverse scan (:520-528) recomputes, from (mf_k, Pf_k), the sigma-point
+ * prediction that sgp_filter's step k+1 already made (:88-121, called from :483 and :523); only the last two lines of
+ * _gaussian_smoother_common (:83-84) depend on the smoothed state.  cgp_sgp_filter_gains_f64 is cgp_sgp_filter_f64 that
+ * additionally fills the smoother workspace ([G | mp | Pp] per (chirp, step), cgp_workspace_bytes("sgp_filter_gains")):
+ * inside the filter kernel where one exists (cgp_sgp_filter_gains_fused() == 1: chirp LCD model, Gauss-Hermite order 3),
+ * otherwise by running the time-parallel gain kernel after the filter.  cgp_smoother_sweep_f64 then finishes any of
+ * rts / eks / sgp_smoother from a filled workspace (:83-84 for k = T-2 .. 0, stacking :140-142); it reads B, T, d of the
+ * problem only.  Filter + sweep give the results of cgp_sgp_filter_f64 + cgp_sgp_smoother_f64 up to rounding. */
+int cgp_sgp_filter_gains_fused(const CgpProblem *p);
+int cgp_sgp_filter_gains_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+                             int nell_last_only, void *workspace, size_t workspace_bytes, void *stream);
+int cgp_smoother_sweep_f64(const CgpProblem *p, const double *mfs, const double *Pfs, double *mss, double *Pss,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- MLE path: EKF negative log-likelihood without per-step outputs, and its reverse-mode adjoint
  * (jax.grad of `ekf(...)[-1][-1]`, demos/ekfs_mle.py:42-49, tetralith/jobs/ekfs_mle.py:41-48).  LCD models only.

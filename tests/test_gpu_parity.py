@@ -271,3 +271,100 @@ def test_unknown_callable_raises():
     drift, disp, mc, m0, P0, H, spec = _chirp_setup()
     with pytest.raises(NotImplementedError):
         cg.ekf(lambda u, dt: (np.sin(u), np.eye(4)), H, 0.1, m0, P0, 1e-3, np.ones(4))
+
+
+# ---------------------------------------------------------------------------------------- fused filter + smoother gains
+def _cuda(x):
+    return torch.as_tensor(np.asarray(x, dtype=np.float64)).cuda()
+
+
+@pytest.mark.parametrize('T', [3141, 33, 32, 31, 2])
+def test_fused_gains_ghf_ghs_vs_oracle(batch, T):
+    """sgp_filter on CUDA tensors leaves the smoother gains on the returned mfs; sgp_smoother on those tensors runs the
+    sweep only.  Same parity bar against the oracle as the two-kernel smoother, for block-aligned and ragged lengths
+    (the filter flushes its gain records every 32 steps)."""
+    B, _, dt, ys = batch
+    ys = ys[:, :T]
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    f = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
+    rec = getattr(f[0], '_cgp_smoother_gains', None)
+    assert rec is not None, 'the filter did not produce smoother gains'
+    fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
+    _check_filter([x.cpu().numpy() for x in f], fo, ATOL_LONG)
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_smoother([x.cpu().numpy() for x in s], so, ATOL_LONG)
+    # the stand-alone smoother on the same filtering result (plain NumPy input: no attached gains) agrees to rounding
+    s2 = cg.sgp_smoother(mc, sg, f[0].cpu().numpy(), f[1].cpu().numpy(), dt)
+    _check_smoother([x.cpu().numpy() for x in s], s2, ATOL_LONG)
+    # the gain records themselves: fused kernel vs the time-parallel gain kernel, through the C ABI
+    import ctypes as C
+    from chirpgp_b200 import _native as N
+    from chirpgp_b200 import filters_smoothers as fs
+    L = N.lib()
+    consts = fs._consts_on_device(mc, dt, torch.device('cuda', 0), dt)
+    sig = fs._sigma_tables(sg, torch.device('cuda', 0))
+    p = fs._problem(B, T, N.CGP_MODEL_LCD, 4, 1, consts, 0, None, 0, None, 0, None, None, 0, sig, 0., dt)
+    assert L.cgp_sgp_filter_gains_fused(C.byref(p)) == 1
+    nbytes = L.cgp_workspace_bytes(b'sgp_smoother', C.byref(p))
+    ws = torch.zeros(nbytes // 8, dtype=torch.float64, device='cuda')
+    mss, Pss = torch.empty_like(f[0]), torch.empty_like(f[1])
+    rc = L.cgp_sgp_smoother_f64(C.byref(p), fs._ptr(f[0]), fs._ptr(f[1]), fs._ptr(mss), fs._ptr(Pss), fs._ptr(ws),
+                                C.c_size_t(nbytes), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    a = rec.ws.reshape(B, T, 36)[:, :T - 1].cpu().numpy()
+    b = ws.reshape(B, T, 36)[:, :T - 1].cpu().numpy()
+    _close(a[..., 16:], b[..., 16:], atol=ATOL_LONG)          # mp, Pp
+    _close(a[..., :16], b[..., :16], rtol=1e-7, atol=1e-9)    # G = D Pp^{-1}: conditioning of Pp amplifies rounding
+
+
+def test_fused_gains_are_dropped_when_inputs_change(batch):
+    B, T, dt, ys = batch
+    ys = ys[:4, :200]
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    args = (_cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
+    f = cg.sgp_filter(mc, sg, *args)
+    ref = cg.sgp_smoother(mc, sg, f[0].clone(), f[1].clone(), dt)            # clones carry no gains
+    # (a) modified in place -> version counter moves -> gains ignored, result follows the new data
+    f2 = cg.sgp_filter(mc, sg, *args)
+    f2[0].mul_(1.5)
+    want = cg.sgp_smoother(mc, sg, f2[0].clone(), f2[1].clone(), dt)
+    got = cg.sgp_smoother(mc, sg, f2[0], f2[1], dt)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # (b) another model -> constants differ -> gains ignored
+    _, _, mc2, *_ = cg.build_chirp_model(PARAMS * 1.1)
+    want = cg.sgp_smoother(mc2, sg, f[0].clone(), f[1].clone(), dt)
+    got = cg.sgp_smoother(mc2, sg, f[0], f[1], dt)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # (c) another sigma-point rule
+    cub = cg.SigmaPoints.cubature(4)
+    want = cg.sgp_smoother(mc, cub, f[0].clone(), f[1].clone(), dt)
+    got = cg.sgp_smoother(mc, cub, f[0], f[1], dt)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    # (d) untouched inputs use the gains and agree with the stand-alone smoother to rounding
+    got = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    _check_smoother([x.cpu().numpy() for x in got], [x.cpu().numpy() for x in ref], ATOL_LONG)
+    # (e) opt-out
+    f3 = cg.sgp_filter(mc, sg, *args, smoother_gains=False)
+    assert getattr(f3[0], '_cgp_smoother_gains', None) is None
+    assert torch.equal(f3[0], f[0]) and torch.equal(f3[1], f[1]) and torch.equal(f3[2], f[2])
+
+
+def test_filter_gains_abi_unfused_models(golden):
+    """cgp_sgp_filter_gains_f64 for a configuration without a fused kernel (harmonic d = 8, cubature): filter, then the
+    time-parallel gain kernel; the Python API gives the same smoother result either way."""
+    z = golden('harmonic')
+    drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(z['params'], num_harmonics=3)
+    dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
+    sg = cg.SigmaPoints.cubature(8)
+    f = cg.sgp_filter(mc, sg, H.cuda(), Xi, m0.cuda(), P0.cuda(), dt, _cuda(ys))
+    assert getattr(f[0], '_cgp_smoother_gains', None) is not None
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    for j in range(3):
+        _close(f[j].cpu().numpy(), z['sgp_filter_cub_%d' % j], rtol=NLL_RT if j == 2 else RT, atol=1e-9 if j == 2 else AT_D8)
+    s_ref = cg.sgp_smoother(mc, sg, z['sgp_filter_cub_0'], z['sgp_filter_cub_1'], dt)
+    for j in range(2):
+        _close(s[j].cpu().numpy(), s_ref[j], atol=AT_D8)
