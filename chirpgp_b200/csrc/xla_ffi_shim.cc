@@ -72,6 +72,31 @@ ffi::Error FilterImpl(cudaStream_t stream, std::string_view fn, int64_t model, i
     return status(rc, "chirpgp_b200 filter");
 }
 
+// sgp_filter that also fills the smoother workspace: ys [B,T] -> mfs, Pfs, nell, ws [B,T,2d^2+d]
+ffi::Error FilterGainsImpl(cudaStream_t stream, int64_t model, int64_t num_harmonics, int64_t sigma_kind, int64_t gh_order,
+                           int64_t ys_repeat, int64_t h_unit_index, double Xi, double dt, F64 ys, F64 consts, F64 m0, F64 P0,
+                           F64 H, F64 sig_w, F64 sig_xi, RF64 mfs, RF64 Pfs, RF64 nell, RF64 ws) {
+    const auto od = mfs->dimensions();
+    const int64_t d = od.back(), T = od[od.size() - 2], B = mfs->element_count() / (T * d);
+    const Attrs a{model, num_harmonics, sigma_kind, gh_order, ys_repeat, h_unit_index, Xi, dt};
+    CgpProblem p = make_problem(a, B, T, d, consts, m0.typed_data(), m0.element_count() / d, P0.typed_data(),
+                                P0.element_count() / (d * d), H.typed_data(), nullptr, 1, sig_w.typed_data(), sig_xi.typed_data(),
+                                sig_w.element_count());
+    return status(cgp_sgp_filter_gains_f64(&p, ys.typed_data(), mfs->typed_data(), Pfs->typed_data(), nell->typed_data(), 0,
+                                           ws->typed_data(), ws->element_count() * sizeof(double), stream),
+                  "chirpgp_b200 sgp_filter_gains");
+}
+// sequential half of rts / eks / sgp_smoother on a filled workspace: mfs, Pfs, ws -> mss, Pss
+ffi::Error SweepImpl(cudaStream_t stream, F64 mfs, F64 Pfs, F64 ws, RF64 mss, RF64 Pss) {
+    const auto od = mfs.dimensions();
+    const int64_t d = od.back(), T = od[od.size() - 2], B = mfs.element_count() / (T * d);
+    CgpProblem p{};
+    p.B = B; p.T = T; p.d = (int32_t)d;
+    return status(cgp_smoother_sweep_f64(&p, mfs.typed_data(), Pfs.typed_data(), mss->typed_data(), Pss->typed_data(),
+                                         const_cast<double *>(ws.typed_data()), ws.element_count() * sizeof(double), stream),
+                  "chirpgp_b200 smoother_sweep");
+}
+
 // smoothers: mfs, Pfs -> mss, Pss; `ws` is an extra result buffer XLA allocates as scratch ([B,T,2d^2+d] or [1])
 ffi::Error SmootherImpl(cudaStream_t stream, std::string_view fn, int64_t model, int64_t num_harmonics, int64_t sigma_kind,
                         int64_t gh_order, double dt, F64 mfs, F64 Pfs, F64 consts, F64 Qc, F64 sig_w, F64 sig_xi, RF64 mss,
@@ -125,6 +150,16 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpFilter, FilterImpl,
                                   .Attr<int64_t>("ys_repeat").Attr<int64_t>("h_unit_index").Attr<double>("Xi").Attr<double>("dt")
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
                                   .Ret<F64>().Ret<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpFilterGains, FilterGainsImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("model").Attr<int64_t>("num_harmonics").Attr<int64_t>("sigma_kind")
+                                  .Attr<int64_t>("gh_order").Attr<int64_t>("ys_repeat").Attr<int64_t>("h_unit_index")
+                                  .Attr<double>("Xi").Attr<double>("dt")
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpSmootherSweep, SweepImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpSmoother, SmootherImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>() CGP_COMMON_FILTER_ATTRS
                                   .Attr<double>("dt")

@@ -34,7 +34,7 @@ def _register():
     if not available():
         raise RuntimeError('chirpgp_b200.jax_ffi needs jax >= 0.4.38 and the XLA shim %s (see csrc/xla_ffi_shim.cc)' % _SHIM)
     lib = ctypes.CDLL(_SHIM)
-    for name in ('CgpFilter', 'CgpSmoother', 'CgpEkfNllFwd', 'CgpEkfNllBwd'):
+    for name in ('CgpFilter', 'CgpFilterGains', 'CgpSmoother', 'CgpSmootherSweep', 'CgpEkfNllFwd', 'CgpEkfNllBwd'):
         jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(getattr(lib, name)), platform='CUDA')
     _registered = True
 
@@ -57,6 +57,24 @@ def filter_call(fn, model, consts, H, Xi, m0, P0, dt, ys, Qc=None, sig=None, num
     return call(ys, consts, m0, P0, H, empty if Qc is None else Qc, w, xi, fn=fn, model=int(model),
                 num_harmonics=int(num_harmonics), sigma_kind=int(bool(gh_order)), gh_order=int(gh_order), ys_repeat=1,
                 h_unit_index=int(h_unit_index), Xi=float(Xi), dt=float(dt))
+
+
+def sgp_filter_smoother_call(model, consts, H, Xi, m0, P0, dt, ys, sig, num_harmonics=0, gh_order=0, h_unit_index=-1):
+    """sgp_filter + sgp_smoother as two custom calls that share the smoother workspace (cgp_sgp_filter_gains_f64 +
+    cgp_smoother_sweep_f64): ys (T,) -> (mfs, Pfs, n_ell, mss, Pss).  What `filtering(ys)` followed by
+    `smoothing(mfs, Pfs)` computes in the demos (demos/ghfs_mle.py:69-85), without evaluating the sigma points twice."""
+    _register()
+    d = m0.shape[-1]
+    T = ys.shape[-1]
+    lead = ys.shape[:-1]
+    w, xi = jnp.asarray(sig.w), jnp.asarray(sig.xi)
+    f = jax.ffi.ffi_call('CgpFilterGains', (_f64(lead + (T, d)), _f64(lead + (T, d, d)), _f64(lead + (T,)),
+                                            _f64(lead + (T, 2 * d * d + d))), vmap_method='broadcast_all')
+    mfs, Pfs, nell, ws = f(ys, consts, m0, P0, H, w, xi, model=int(model), num_harmonics=int(num_harmonics),
+                           sigma_kind=int(bool(gh_order)), gh_order=int(gh_order), ys_repeat=1,
+                           h_unit_index=int(h_unit_index), Xi=float(Xi), dt=float(dt))
+    mss, Pss = jax.ffi.ffi_call('CgpSmootherSweep', (_f64(mfs.shape), _f64(Pfs.shape)), vmap_method='broadcast_all')(mfs, Pfs, ws)
+    return mfs, Pfs, nell, mss, Pss
 
 
 def smoother_call(fn, model, consts, mfs, Pfs, dt, Qc=None, sig=None, num_harmonics=0, gh_order=0):
