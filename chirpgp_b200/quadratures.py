@@ -108,12 +108,24 @@ class SigmaPoints(NamedTuple):
 
 
 def gaussian_expectation(ms, chol_Ps, func=None, d: int = 1, order: int = 10, force_shape: bool = False):
-    """E[func(V)] for V ~ N(m, chol chol^T) by Gauss--Hermite (quadratures.py:234-274).
+    """E[func(V)] for V ~ N(m, chol chol^T) by Gauss--Hermite (quadratures.py:234-274): the post-processing step right
+    after the smoothers, e.g. ``gaussian_expectation(ms=mss[:, 2], chol_Ps=sqrt(Pss[:, 2, 2]),
+    force_shape=True)`` for the frequency estimate (demos/ghfs_mle.py:87-89).
 
-    Post-processing step *after* the hot path: vectorised NumPy on the host.
+    CUDA tensors with the default integrand (``func=None`` -> the softplus ``g``) and d = 1 are evaluated on the device by
+    ``cgp_gaussian_expectation_softplus_f64`` -- strided views into the smoother output are read in place, only the (T, 1)
+    result exists afterwards.  Everything else (NumPy inputs, a user ``func``, d > 1) is vectorised NumPy on the host.
     """
+    import torch
     from .models import g as _g
+    if (func is None and d == 1 and isinstance(ms, torch.Tensor) and ms.is_cuda and isinstance(chol_Ps, torch.Tensor)
+            and chol_Ps.is_cuda and ms.dtype == torch.float64 and chol_Ps.dtype == torch.float64):
+        return _gaussian_expectation_device(ms, chol_Ps, order)
     func = _g if func is None else func
+    if isinstance(ms, torch.Tensor):
+        ms = ms.detach().cpu().numpy()
+    if isinstance(chol_Ps, torch.Tensor):
+        chol_Ps = chol_Ps.detach().cpu().numpy()
     ms = np.asarray(ms, dtype=np.float64)
     chol_Ps = np.asarray(chol_Ps, dtype=np.float64)
     if force_shape:
@@ -122,3 +134,43 @@ def gaussian_expectation(ms, chol_Ps, func=None, d: int = 1, order: int = 10, fo
     sgps = SigmaPoints.gauss_hermite(d=d, order=order)
     chi = ms[:, None, :] + np.einsum('tij,sj->tsi', chol_Ps, sgps.xi)       # (T, s, d)
     return np.einsum('s,ts...->t...', sgps.w, np.asarray(func(chi)))
+
+
+def _gaussian_expectation_device(ms, chol_Ps, order: int):
+    """ms, chol_Ps: CUDA float64 tensors with the same number of elements (any shape: d = 1, so (T,), (T, 1), (T, 1, 1) are
+    the same thing; batches (B, T) are flattened).  Returns ms.shape + (1,) if ms has no trailing unit axis, like the
+    reference's (T, 1)."""
+    import ctypes as C
+    import torch
+    from . import _native as N
+    if ms.numel() != chol_Ps.numel():
+        raise ValueError('gaussian_expectation: ms has %d elements, chol_Ps %d' % (ms.numel(), chol_Ps.numel()))
+    out_shape = tuple(ms.shape) if (ms.dim() >= 2 and ms.shape[-1] == 1) else tuple(ms.shape) + (1,)
+
+    def flat(t):
+        """(data pointer, element stride) of a 1-d walk over t without copying when t is an evenly strided view."""
+        t = t.detach()
+        t = t.reshape(-1) if t.is_contiguous() else t.squeeze()
+        if t.dim() == 0:
+            t = t.reshape(1)
+        if t.dim() != 1 or (t.numel() > 1 and t.stride(0) < 1):
+            t = t.contiguous().reshape(-1)
+        return t, (int(t.stride(0)) if t.numel() > 1 else 1)
+
+    m1, ms_stride = flat(ms)
+    c1, sd_stride = flat(chol_Ps)
+    n = int(m1.numel())
+    sg = SigmaPoints.gauss_hermite(d=1, order=order)
+    w = np.ascontiguousarray(sg.w, dtype=np.float64)
+    xi = np.ascontiguousarray(np.asarray(sg.xi)[:, 0], dtype=np.float64)
+    out = torch.empty((n,), dtype=torch.float64, device=ms.device)
+    if n == 0:
+        return out.reshape(out_shape)
+    with torch.cuda.device(ms.device):
+        stream = C.c_void_p(torch.cuda.current_stream(ms.device).cuda_stream)
+        rc = N.lib().cgp_gaussian_expectation_softplus_f64(n, C.c_void_p(m1.data_ptr()), ms_stride, C.c_void_p(c1.data_ptr()),
+                                                           sd_stride, 0, w.ctypes.data_as(C.c_void_p),
+                                                           xi.ctypes.data_as(C.c_void_p), int(order),
+                                                           C.c_void_p(out.data_ptr()), stream)
+    N.check(rc, 'gaussian_expectation')
+    return out.reshape(out_shape)

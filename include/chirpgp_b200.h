@@ -143,6 +143,16 @@ int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll
                         size_t workspace_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,
                         double *Xi_bar, void *stream);
 
+/* ---- post-processing right after the smoothers: chirpgp.quadratures.gaussian_expectation (quadratures.py:234-274) for its
+ * default integrand g (softplus, models.py:50) and d = 1 -- the frequency estimate E[g(V_k)], V_k ~ N(ms_k, chol_k^2), every
+ * demo forms from the smoothing result (demos/ghfs_mle.py:87-89).  ms / sd are DEVICE pointers read with element strides
+ * (so they may point into mss / Pss: ms = mss + 2, stride d; sd = Pss + 2 d + 2, stride d*d, sd_is_variance = 1 applies the
+ * sqrt the callers apply); w_host / xi_host [order] are HOST pointers to the d = 1 Gauss-Hermite table of
+ * quadratures.py:157-196 (order <= 64); out [n] is a device pointer. */
+int cgp_gaussian_expectation_softplus_f64(int64_t n, const double *ms, int64_t ms_stride, const double *sd,
+                                          int64_t sd_stride, int sd_is_variance, const double *w_host,
+                                          const double *xi_host, int order, double *out, void *stream);
+
 /* ---- measurement utility: DFMA-only kernel (8 independent chains / thread) for the FP64 roofline denominator.
  * `out` holds blocks * 256 doubles.  Returns the flops issued (caller times the stream), < 0 on error. */
 double cgp_bench_dfma(double *out, int blocks, int iters, void *stream);

@@ -110,8 +110,8 @@ def test_candidate_grid_and_fit():
 
 def test_fd_gradient_mle_for_sigma_point_and_cd_filters(golden):
     """The MLE demos of the sigma-point / continuous-discrete filters (demos/ghfs_mle.py:54-61, cd_ekfs_mle.py,
-    cd_ghfs_mle.py) take jax.grad of their nll; here those objectives are differentiated by central differences over a
-    candidate batch.  Check objective and gradient against the reference's jax.grad fixtures."""
+    cd_ghfs_mle.py) take jax.grad of their nll; here those objectives are differentiated by five-point central differences
+    over a candidate batch.  Check objective and gradient against the reference's jax.grad fixtures."""
     z = golden('chirp')
     H, Xi, dt, ys = z['H'], float(z['Xi']), float(z['dt']), z['ys']
     sg = cg.SigmaPoints.gauss_hermite(4, 3)
@@ -138,4 +138,5 @@ def test_fd_gradient_mle_for_sigma_point_and_cd_filters(golden):
             scipy.optimize.minimize = orig
         v, gr = calls[0]
         npt.assert_allclose(v, want_val, rtol=1e-10)
-        npt.assert_allclose(gr, want_grad, rtol=2e-5, atol=1e-6)
+        # measured: 2.8e-7 (sgp_filter) -- the floor is the nll's own rounding noise (~1e-12 relative) divided by h
+        npt.assert_allclose(gr, want_grad, rtol=2e-6, atol=1e-7)

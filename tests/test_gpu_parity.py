@@ -368,3 +368,33 @@ def test_filter_gains_abi_unfused_models(golden):
     s_ref = cg.sgp_smoother(mc, sg, z['sgp_filter_cub_0'], z['sgp_filter_cub_1'], dt)
     for j in range(2):
         _close(s[j].cpu().numpy(), s_ref[j], atol=AT_D8)
+
+
+# ---------------------------------------------------------------------------------------- post-processing on the device
+def test_gaussian_expectation_device_vs_host(batch):
+    """quadratures.gaussian_expectation (quadratures.py:234-274) with the default integrand g on CUDA tensors: strided views
+    straight into the smoother output, against the host (NumPy) evaluation of the same formula and the closed form the
+    reference's own test uses (test/test_utils.py:84-95 checks exp; here: g(x) -> x for large x)."""
+    from chirpgp_b200.quadratures import gaussian_expectation
+    B, T, dt, ys = batch
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    f = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys[:3, :500]))
+    mss, Pss = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    for b in range(3):
+        got = gaussian_expectation(ms=mss[b, :, 2], chol_Ps=torch.sqrt(Pss[b, :, 2, 2]), force_shape=True)
+        assert got.is_cuda and tuple(got.shape) == (500, 1)
+        want = gaussian_expectation(ms=mss[b, :, 2].cpu().numpy(), chol_Ps=np.sqrt(Pss[b, :, 2, 2].cpu().numpy()), force_shape=True)
+        _close(got.cpu().numpy(), want, rtol=1e-13, atol=0)
+    # whole batch at once, other orders, the three softplus regimes (x < 3, 3 <= x <= 700, x > 700 -> +inf like the reference)
+    rng = np.random.default_rng(5)
+    m = np.concatenate([rng.uniform(-30, 3, 400), rng.uniform(3, 600, 400), [800., 705.]])
+    c = np.concatenate([rng.uniform(0., 2., 800), [0.5, 3.]])
+    for order in (1, 5, 10, 20):
+        got = gaussian_expectation(_cuda(m), _cuda(c), order=order, force_shape=True).cpu().numpy()
+        with np.errstate(over='ignore'):
+            want = gaussian_expectation(m, c, order=order, force_shape=True)
+        _close(got, want, rtol=1e-13, atol=0)
+    assert np.isinf(got[-2, 0])
+    big = gaussian_expectation(_cuda(np.array([50., 200.])), _cuda(np.array([1., 2.])), force_shape=True).cpu().numpy()
+    _close(big[:, 0], [50., 200.], rtol=1e-14, atol=0)          # E[g(V)] = E[V] = m to rounding when g is linear there
