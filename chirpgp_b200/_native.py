@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libchirpgp_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
-CGP_MODEL_LINEAR_DISC, CGP_MODEL_LCD, CGP_MODEL_LINEAR_SDE, CGP_MODEL_SDE = 0, 1, 2, 3
+CGP_MODEL_LINEAR_DISC, CGP_MODEL_LCD, CGP_MODEL_LINEAR_SDE, CGP_MODEL_SDE, CGP_MODEL_KPT = 0, 1, 2, 3, 4
 CGP_SIGMA_GENERIC, CGP_SIGMA_GAUSS_HERMITE, CGP_SIGMA_CUBATURE = 0, 1, 2
 ABI_VERSION = 2
 
@@ -35,7 +35,7 @@ class CgpProblem(C.Structure):
     ]
 
 
-FILTER_FUNCS = ('kf', 'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
+FILTER_FUNCS = ('kf', 'ekf', 'ekf_for_kpt', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
 SMOOTHER_FUNCS = ('rts', 'eks', 'sgp_smoother', 'cd_eks', 'cd_sgp_smoother')
 EXPORTED = (['cgp_abi_version', 'cgp_workspace_bytes'] + ['cgp_%s_f64' % f for f in FILTER_FUNCS + SMOOTHER_FUNCS]
             + ['cgp_ekf_nll_default_ckpt', 'cgp_ekf_nll_workspace_bytes', 'cgp_ekf_nll_fwd_f64', 'cgp_ekf_nll_bwd_f64',

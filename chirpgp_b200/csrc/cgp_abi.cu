@@ -52,6 +52,13 @@ int cgp_ekf_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs,
     if (rc) return rc;
     return launch_ekf(*p, FilterIO{ys, mfs, Pfs, nell, last_only}, (cudaStream_t)stream);
 }
+int cgp_ekf_for_kpt_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell, int last_only,
+                        void *stream) {
+    if (!p || p->B < 1 || p->T < 1 || !p->consts || !ys || !p->m0 || !p->P0 || p->ys_repeat < 1) return CGP_ERR_BAD_ARG;
+    if ((mfs == nullptr) != (Pfs == nullptr)) return CGP_ERR_BAD_ARG;
+    if (p->model != CGP_MODEL_KPT || p->d != p->num_harmonics + 2) return CGP_ERR_BAD_ARG;
+    return launch_ekf_kpt(*p, FilterIO{ys, mfs, Pfs, nell, last_only}, (cudaStream_t)stream);
+}
 int cgp_sgp_filter_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell, int last_only,
                        void *stream) {
     int rc = check_filter(p, ys, mfs, Pfs);

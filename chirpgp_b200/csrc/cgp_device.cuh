@@ -238,6 +238,30 @@ CGP_DEV double linear_update(const double (&mp)[D], const double (&Pp)[D][D], co
     CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) Pf[i][j] = Pp[i][j] - (K[i] * K[j]) * S;
     return nll_increment(S, r);
 }
+// measurement update of ekf_for_kpt (filters_smoothers.py:301-308): as linear_update with the measurement row H = dh/dx(mp)
+// and the predicted measurement pred = h(mp) given separately.
+template <int D>
+CGP_DEV double nonlinear_update(const double (&mp)[D], const double (&Pp)[D][D], const double (&H)[D], double pred, double Xi,
+                                double y, double (&mf)[D], double (&Pf)[D][D]) {
+    double S = 0.;
+    CGP_UNROLL for (int j = 0; j < D; j++) {
+        double hp = H[0] * Pp[0][j];
+        CGP_UNROLL for (int i = 1; i < D; i++) hp = fma(H[i], Pp[i][j], hp);
+        S = (j == 0) ? hp * H[0] : fma(hp, H[j], S);
+    }
+    S += Xi;
+    const double rS = fast_rcp(S);
+    double K[D];
+    CGP_UNROLL for (int i = 0; i < D; i++) {
+        double s = Pp[i][0] * H[0];
+        CGP_UNROLL for (int j = 1; j < D; j++) s = fma(Pp[i][j], H[j], s);
+        K[i] = s * rS;
+    }
+    const double r = y - pred;
+    CGP_UNROLL for (int i = 0; i < D; i++) mf[i] = fma(K[i], r, mp[i]);
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) Pf[i][j] = Pp[i][j] - (K[i] * K[j]) * S;
+    return nll_increment(S, r);
+}
 // same on packed-symmetric covariances (exactly symmetric inputs stay exactly symmetric)
 template <int D>
 CGP_DEV double linear_update_sym(const double (&mp)[D], const double (&Pp)[NSym<D>::value], const double (&H)[D], double Xi,

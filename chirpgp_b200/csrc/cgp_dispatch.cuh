@@ -6,7 +6,7 @@ namespace cgp {
 
 template <class T> struct Tag { using type = T; };
 
-// Compiled state dimensions.  Linear models: d in 1..4.  Chirp family: num_harmonics in 1..3 (d = 4, 6, 8).
+// Compiled state dimensions.  Linear models: d in 1..5 (5: rts after ekf_for_kpt with three harmonics).  Chirp family: num_harmonics in 1..3 (d = 4, 6, 8).
 template <class F> int dispatch_disc(const CgpProblem &p, F &&f) {
     if (p.model == CGP_MODEL_LINEAR_DISC) {
         switch (p.d) {
@@ -14,6 +14,7 @@ template <class F> int dispatch_disc(const CgpProblem &p, F &&f) {
             case 2: return f(Tag<ModelLinearDisc<2>>{});
             case 3: return f(Tag<ModelLinearDisc<3>>{});
             case 4: return f(Tag<ModelLinearDisc<4>>{});
+            case 5: return f(Tag<ModelLinearDisc<5>>{});
             default: return CGP_ERR_UNSUPPORTED;
         }
     }
@@ -78,6 +79,7 @@ inline int check_launch() {
 
 // entry points implemented in the individual translation units
 int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s);
+int launch_ekf_kpt(const CgpProblem &p, const FilterIO &io, cudaStream_t s);
 int launch_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s);
 int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s);
 int launch_cd_sgp_filter(const CgpProblem &p, const FilterIO &io, cudaStream_t s);

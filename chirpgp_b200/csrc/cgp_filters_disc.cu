@@ -12,6 +12,18 @@ int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     });
 }
 
+int launch_ekf_kpt(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    const int block = 128;
+    const unsigned grid = (unsigned)ceil_div(p.B, block);
+    switch (p.num_harmonics) {
+        case 1: ekf_kpt_thread_kernel<1><<<grid, block, 0, s>>>(p, io); break;
+        case 2: ekf_kpt_thread_kernel<2><<<grid, block, 0, s>>>(p, io); break;
+        case 3: ekf_kpt_thread_kernel<3><<<grid, block, 0, s>>>(p, io); break;
+        default: return CGP_ERR_UNSUPPORTED;
+    }
+    return check_launch();
+}
+
 static const int64_t kThreadPerChirpMinB = 30000;   // measured: 1.76 G vs 1.48 G filter steps/s at 64 000 chirps
 
 template <class Model, int G, int P>

@@ -71,6 +71,55 @@ __global__ void __launch_bounds__(128) ekf_thread_kernel(const CgpProblem p, con
     if (io.nell && io.nell_last_only) io.nell[b] = acc;
 }
 
+// ekf_for_kpt (filters_smoothers.py:267-314) with the measurement function of build_kpt_chirp_model (models.py:572-578):
+// state x = [omega, a_1 .. a_NH, phase], d = NH + 2; linear prediction with (F, Sigma) (consts = [F | Sigma]);
+//   h(x) = sum_k a_k sin(k g(x_0 + x_{d-1})),   H = jacfwd(h)(mp) in closed form:
+//   dh/dx_0 = dh/dx_{d-1} = g'(x_0 + x_{d-1}) sum_k k a_k cos(k phi),   dh/da_k = sin(k phi).       One thread per chirp.
+template <int NH>
+__global__ void __launch_bounds__(128) ekf_kpt_thread_kernel(const CgpProblem p, const FilterIO io) {
+    constexpr int D = NH + 2;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    ModelLinearDisc<D> mdl;
+    mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double m[D], P[D][D];
+    load_vec<D>(p.m0 + b * p.m0_stride, m);
+    load_mat<D>(p.P0 + b * p.P0_stride, P);
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
+    const int64_t T = p.T;
+    const bool store = io.mfs != nullptr;
+    double acc = 0.;
+    double ynext = __ldg(y);
+    for (int64_t t = 0; t < T; t++) {
+        const double yt = ynext;
+        if (t + 1 < T) ynext = __ldg(y + t + 1);
+        double mp[D], FP[D][D], Pp[D][D], H[D];
+        matvec<D>(mdl.F, m, mp);                      // _linear_predict :48-52
+        matmul<D>(mdl.F, P, FP);
+        matmul_nt<D>(FP, mdl.F, Pp);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Pp[r][c] += mdl.Sg[r][c];
+        double phi, dphi;
+        softplus_and_sigmoid(mp[0] + mp[D - 1], phi, dphi);
+        double pred = 0., dsum = 0.;
+        CGP_UNROLL for (int k = 1; k <= NH; k++) {
+            double sn, cs;
+            fast_sincos(phi * (double)k, &sn, &cs);
+            pred = (k == 1) ? mp[k] * sn : fma(mp[k], sn, pred);
+            dsum = (k == 1) ? mp[k] * (cs * (double)k) : fma(mp[k], cs * (double)k, dsum);
+            H[k] = sn;
+        }
+        H[0] = dsum * dphi;
+        H[D - 1] = H[0];
+        acc = acc + nonlinear_update<D>(mp, Pp, H, pred, p.Xi, yt, m, P);
+        if (store) {
+            store_vec<D>(io.mfs + (b * T + t) * D, m);
+            store_mat<D>(io.Pfs + (b * T + t) * (D * D), P);
+        }
+        if (io.nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+    }
+    if (io.nell && io.nell_last_only) io.nell[b] = acc;
+}
+
 // ---- continuous-discrete pieces on packed-symmetric covariances --------------------------------
 // rhs of the CD-EKF moment ODE (filters_smoothers.py:384-385): dm = a(m), dP = P J^T + J P + b b^T.
 // With P exactly symmetric (P J^T)_rc == (J P)_cr bit for bit, so one product X = J P suffices.

@@ -78,6 +78,7 @@ int launch_smoother_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_
         case 2: return launch_sweep<2>(p, io, s);
         case 3: return launch_sweep<3>(p, io, s);
         case 4: return launch_sweep<4>(p, io, s);
+        case 5: return launch_sweep<5>(p, io, s);
         case 6: return launch_sweep<6>(p, io, s);
         case 8: return launch_sweep<8>(p, io, s);
         default: return CGP_ERR_UNSUPPORTED;

@@ -4,7 +4,7 @@ CUDA kernels through the C ABI of include/chirpgp_b200.h.
 
 Same names, positional signatures and return tuples as the reference:
 
-    kf :145-148, rts :187-188, ekf :222-225, eks :317-318, cd_ekf :352-355, cd_eks :400-402,
+    kf :145-148, rts :187-188, ekf :222-225, ekf_for_kpt :267-270, eks :317-318, cd_ekf :352-355, cd_eks :400-402,
     sgp_filter :446-450, sgp_smoother :493-496, cd_sgp_filter :534-538, cd_sgp_smoother :585-588
 
 Differences that follow from running compiled kernels instead of traced Python closures:
@@ -26,10 +26,10 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .models import (LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, MODEL_LINEAR_DISC, MODEL_LCD,
-                     MODEL_LINEAR_SDE, MODEL_SDE)
+from .models import (LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, KPTMeasurement, MODEL_LINEAR_DISC,
+                     MODEL_LCD, MODEL_LINEAR_SDE, MODEL_SDE, MODEL_KPT)
 
-__all__ = ['kf', 'rts', 'ekf', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
+__all__ = ['kf', 'rts', 'ekf', 'ekf_for_kpt', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
            'cd_sgp_smoother']
 
 _F64 = torch.float64
@@ -385,6 +385,31 @@ def ekf(cond_m_cov, H, Xi, m0, P0, dt, ys) -> Tuple:
     dt = float(dt)
     model = _disc_model(cond_m_cov, _state_dim(m0), dt)
     return _run_filter('ekf', model, _consts_on_device(model, dt, _device(), dt), H, Xi, m0, P0, dt, ys)
+
+
+class _KPTModel:
+    """(F, Sigma) of the KPT model tagged for cgp_ekf_for_kpt_f64."""
+    model_id = MODEL_KPT
+
+    def __init__(self, lin: LinearDisc, num_harmonics: int):
+        self.lin, self.d, self.num_harmonics = lin, int(lin.d), int(num_harmonics)
+
+
+def ekf_for_kpt(F, Sigma, h, Xi, m0, P0, dt, ys) -> Tuple:
+    """Ad-hoc extended Kalman filter for the KPT model (filters_smoothers.py:267-314): linear prediction with (F, Sigma),
+    nonlinear scalar measurement ``h``.  ``h`` must be the tagged measurement function that
+    ``chirpgp_b200.models.build_kpt_chirp_model`` returns (its Jacobian is compiled into the kernel); smooth the result
+    with ``rts(F, Sigma, mfs, Pfs)`` as tetralith/jobs/kpt_mle.py:59-62 does."""
+    if not isinstance(h, KPTMeasurement):
+        raise NotImplementedError('chirpgp_b200.ekf_for_kpt: the measurement function must be the tagged callable of '
+                                  'chirpgp_b200.models.build_kpt_chirp_model (no CPU fallback)')
+    lin = LinearDisc(F, Sigma)
+    if int(lin.d) != h.num_harmonics + 2:
+        raise ValueError('KPT state dimension %d does not match %d harmonics' % (int(lin.d), h.num_harmonics))
+    model = _KPTModel(lin, h.num_harmonics)
+    dev = _device()
+    H_unused = torch.zeros(int(lin.d), dtype=_F64)
+    return _run_filter('ekf_for_kpt', model, _dev(lin.consts(), dev), H_unused, Xi, m0, P0, float(dt), ys)
 
 
 def eks(cond_m_cov, mfs, Pfs, dt) -> Tuple:

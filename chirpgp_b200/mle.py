@@ -123,8 +123,9 @@ def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = Fals
 
 def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None) -> torch.Tensor:
     """Final cumulative nll of ANY of the five filters, evaluated by its kernel in nll-only mode (nothing but one double
-    per problem is stored): ``method`` in {'kf', 'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter'}; ``model_args`` are the
-    leading model arguments of that filter (e.g. ``(m_and_cov,)`` or ``(drift, dispersion)``).  Not differentiable by
+    per problem is stored): ``method`` in {'kf', 'ekf', 'ekf_for_kpt', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter'};
+    ``model_args`` are the leading model arguments of that filter (e.g. ``(m_and_cov,)``, ``(drift, dispersion)`` or
+    ``(F, Sigma, h)``).  Not differentiable by
     autograd -- ``fit_mle`` differentiates it by fourth-order central differences over a candidate batch (one launch)."""
     from . import filters_smoothers as fs
     dt = float(dt)
@@ -132,6 +133,12 @@ def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None)
         model = fs._disc_model(model_args[0], int(m0.shape[-1]), dt) if method != 'kf' else model_args[0]
         consts = fs._consts_on_device(model, dt, fs._device(), *((dt,) if method != 'kf' else ()))
         return fs._run_filter(method, model, consts, H, Xi, m0, P0, dt, ys, sgps=sgps, store=False, last_only=True)
+    if method == 'ekf_for_kpt':
+        F, Sigma, h = model_args
+        lin = fs.LinearDisc(F, Sigma)
+        model = fs._KPTModel(lin, h.num_harmonics)
+        return fs._run_filter(method, model, fs._dev(lin.consts(), fs._device()), torch.zeros(int(lin.d), dtype=_F64), Xi, m0,
+                              P0, dt, ys, store=False, last_only=True)
     if method in ('cd_ekf', 'cd_sgp_filter'):
         model = fs._sde_model(model_args[0], int(m0.shape[-1]))
         b = model_args[1]
@@ -142,12 +149,13 @@ def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None)
 
 
 def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optional[Callable] = None, maxiter: int = 200,
-            reduce_group=None, method: str = 'ekf', sgps=None, fd_step: float = 2e-3):
+            reduce_group=None, method: str = 'ekf', sgps=None, fd_step: Optional[float] = None):
     """L-BFGS-B maximum-likelihood fit driving the nll kernels -- the role of
     ``jaxopt.ScipyMinimize(method='L-BFGS-B', fun=obj_func).run(init_theta)`` (demos/ekfs_mle.py:48-49 and the other
     ``*_mle.py`` demos / tetralith jobs).
 
-    build_model(params) -> (drift, dispersion, m_and_cov, m0, P0, H') as chirpgp_b200.models.build_*; ``transform`` maps
+    build_model(params) -> (drift, dispersion, m_and_cov, m0, P0, H') as chirpgp_b200.models.build_* (for
+    method='ekf_for_kpt': (F, Sigma, m0, P0, h) as build_kpt_chirp_model with fs bound, and ``H`` is ignored); ``transform`` maps
     the unconstrained theta to params (default: the reference's softplus ``g``).  The objective is the SUM of the nll over
     all chirps in ``ys`` (this rank's shard when torch.distributed is initialised: the scalar objective and its 6-vector
     gradient are then summed over ranks with one all-reduce -- the only collective on this path).
@@ -178,18 +186,26 @@ def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optiona
     def fun_fd(theta_np):
         # five-point central differences: (-f(+2h) + 8 f(+h) - 8 f(-h) + f(-2h)) / 12h, all 4P + 1 candidates in ONE batch.
         # On this hardware the candidates cost nothing extra (a single chirp leaves the GPU empty and the candidates run
-        # side by side), and with h ~ 2e-3 truncation (h^4) and round-off (eps |f| / h) both sit near 1e-10 relative.
+        # side by side), and truncation (h^4) and round-off (eps |f| / h) both sit near 1e-8 relative or below.
         n = theta_np.shape[0]
-        h = fd_step * np.maximum(1., np.abs(theta_np))
+        # step: the sigma-point objectives carry ~1e-12 relative summation noise (tests/test_noise_floor.py) and want the larger
+        # step; the EKF-type objectives are smooth to ~1e-15 and take the smaller one (truncation ~ h^4)
+        step = fd_step if fd_step is not None else (2e-3 if method in ('sgp_filter', 'cd_sgp_filter') else 1e-4)
+        h = step * np.maximum(1., np.abs(theta_np))
         cand = np.tile(theta_np, (4 * n + 1, 1))
         for i in range(n):
             for j, mult in enumerate((1., -1., 2., -2.)):
                 cand[1 + 4 * i + j, i] += mult * h[i]
-        drift, dispersion, m_and_cov, m0, P0, _ = build_model(transform(torch.as_tensor(cand)))
-        if method in ('ekf', 'sgp_filter'):
-            margs = (m_and_cov,)
+        built = build_model(transform(torch.as_tensor(cand)))
+        if method == 'ekf_for_kpt':                       # build_kpt_chirp_model: (F, Sigma, m0, P0, h)
+            F_, Sigma_, m0, P0, h_ = built
+            margs = (F_, Sigma_, h_)
         else:
-            margs = (drift, dispersion if method == 'cd_ekf' else dispersion.matrix())
+            drift, dispersion, m_and_cov, m0, P0, _ = built
+            if method in ('ekf', 'sgp_filter'):
+                margs = (m_and_cov,)
+            else:
+                margs = (drift, dispersion if method == 'cd_ekf' else dispersion.matrix())
         total = torch.zeros(4 * n + 1, dtype=_F64, device=dev)
         for row in ys2:                                   # every chirp against the 4P + 1 candidates
             total = total + filter_nll(method, margs, H, Xi, m0, P0, dt, row, sgps=sgps)

@@ -4,7 +4,7 @@ Mirrors the reference interface ``chirpgp.models`` (/root/reference/chirpgp/mode
 ``g`` :50, ``g_inv`` :53, ``model_chirp`` :76-119, ``model_harmonic_chirp`` :122-178, ``model_lascala`` :181-261,
 ``disc_chirp_lcd`` :264-311, ``disc_harmonic_chirp_lcd`` :332-386, ``disc_model_lascala_lcd`` :419-434,
 ``disc_m32`` :408-416, ``build_chirp_model`` :437-459, ``build_harmonic_chirp_model`` :462-494,
-``build_lascala_model`` :497-519.
+``build_lascala_model`` :497-519, ``build_kpt_chirp_model`` :522-580.
 
 The reference hands the filters *Python closures* and differentiates them with ``jax.jacfwd`` inside the scan.
 Here the drift / dispersion / conditional-mean functions are compiled into the CUDA kernels as device
@@ -25,15 +25,16 @@ import torch
 
 __all__ = ['g', 'g_inv', 'model_chirp', 'model_harmonic_chirp', 'model_lascala', 'disc_chirp_lcd',
            'disc_harmonic_chirp_lcd', 'disc_model_lascala_lcd', 'disc_m32', 'build_chirp_model',
-           'build_harmonic_chirp_model', 'build_lascala_model', 'LinearDisc', 'LinearSDE',
-           'LCDModel', 'SDEDrift', 'Dispersion',
-           'MODEL_LINEAR_DISC', 'MODEL_LCD', 'MODEL_LINEAR_SDE', 'MODEL_SDE', 'NC_LCD', 'NC_SDE']
+           'build_harmonic_chirp_model', 'build_lascala_model', 'build_kpt_chirp_model', 'LinearDisc', 'LinearSDE',
+           'LCDModel', 'SDEDrift', 'Dispersion', 'KPTMeasurement',
+           'MODEL_LINEAR_DISC', 'MODEL_LCD', 'MODEL_LINEAR_SDE', 'MODEL_SDE', 'MODEL_KPT', 'NC_LCD', 'NC_SDE']
 
 # model ids shared with include/chirpgp_b200.h
 MODEL_LINEAR_DISC = 0   # x_k = F x_{k-1} + q               consts = [F (d*d), Sigma (d*d)]
 MODEL_LCD = 1           # chirp / harmonic / La Scala LCD    consts = NC_LCD doubles, see LCDModel.consts
 MODEL_LINEAR_SDE = 2    # dx = A x dt + B dW                 consts = [A (d*d)]
 MODEL_SDE = 3           # chirp / harmonic / La Scala SDE    consts = NC_SDE doubles, see SDEDrift.consts
+MODEL_KPT = 4           # KPT model (ekf_for_kpt only)       consts = [F (d*d), Sigma (d*d)], d = num_harmonics + 2
 NC_LCD = 10
 NC_SDE = 4
 
@@ -341,3 +342,32 @@ def build_lascala_model(params):
     m0 = torch.stack([z, z, m0_v, z], dim=-1)
     m_and_cov = disc_model_lascala_lcd(ell, sigma)
     return drift, dispersion, m_and_cov, m0, P0, H
+
+
+class KPTMeasurement:
+    """Tagged measurement function of the KPT model (models.py:572-578): ``h(x) = sum_k x[k] sin(k g(x[0] + x[-1]))``,
+    k = 1 .. num_harmonics.  Callable on the host like the reference's closure; ``ekf_for_kpt`` recognises it and runs the
+    kernel that has ``h`` and its Jacobian compiled in."""
+
+    def __init__(self, num_harmonics: int):
+        self.num_harmonics = int(num_harmonics)
+
+    def __call__(self, x):
+        x = _t(x)
+        k = torch.arange(1, self.num_harmonics + 1, dtype=_F64, device=x.device)
+        return (x[..., 1:-1] * torch.sin(g(x[..., 0] + x[..., -1])[..., None] * k)).sum(-1)
+
+
+def build_kpt_chirp_model(params, fs: float, num_harmonics: int = 1):
+    """models.py:522-580 (Shi et al. 2017 Kalman pitch tracking).  params (..., 5) = q1, q2, p0, f0, a0 ->
+    (F, Sigma, m0, P0, h) with the state x = [omega, a_1 .. a_h, phase]."""
+    q1, q2, p0, f0, a0 = _split_params(params, 5)
+    d = num_harmonics + 2
+    eye = torch.eye(d, dtype=_F64, device=q1.device)
+    P0 = p0[..., None, None] * eye
+    m0 = torch.stack([2 * math.pi * f0 / fs] + [a0] * num_harmonics + [torch.zeros_like(a0)], dim=-1)
+    F = eye.clone()
+    F[-1, 0] = 1.
+    diag = torch.stack([(2 * math.pi * q1 / fs) ** 2] + [q2] * num_harmonics + [torch.zeros_like(q2)], dim=-1)
+    Sigma = torch.diag_embed(diag)
+    return F, Sigma, m0, P0, KPTMeasurement(num_harmonics)

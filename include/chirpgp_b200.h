@@ -37,8 +37,10 @@ enum {
     CGP_MODEL_LCD         = 1, /* chirp/harmonic/La Scala LCD, models.py:295-309,:369-384,:423-432:
                                   consts [e, F00,F01,F10,F11, q, S00,S01,S11, freq_scale]  (CGP_NC_LCD)          */
     CGP_MODEL_LINEAR_SDE  = 2, /* u -> A u: consts [A d*d]                                                        */
-    CGP_MODEL_SDE         = 3  /* chirp/harmonic drift, models.py:104-110,:164-168: consts
+    CGP_MODEL_SDE         = 3, /* chirp/harmonic drift, models.py:104-110,:164-168: consts
                                   [lam, gamma^2, 2 gamma, freq_scale]                       (CGP_NC_SDE)          */
+    CGP_MODEL_KPT         = 4  /* KPT model, models.py:522-580: linear prediction consts [F d*d | Sigma d*d], d = num_harmonics + 2,
+                                  measurement h(x) = sum_k x_k sin(k g(x_0 + x_{d-1}))      (cgp_ekf_for_kpt_f64 only)  */
 };
 #define CGP_NC_LCD 10
 #define CGP_NC_SDE 4
@@ -95,6 +97,9 @@ int cgp_ekf_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs,
                 int nell_last_only, void *stream);                   /* :222-264 */
 int cgp_sgp_filter_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
                        int nell_last_only, void *stream);            /* :446-490 (+ :88-121) */
+int cgp_ekf_for_kpt_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
+                        int nell_last_only, void *stream);           /* :267-314, model CGP_MODEL_KPT (H, n_sigma unused);
+                                                                        smooth its result with cgp_rts_f64 (same F, Sigma) */
 int cgp_cd_ekf_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,
                    int nell_last_only, void *stream);                /* :352-397 (+ quadratures.py:34-54) */
 int cgp_cd_sgp_filter_f64(const CgpProblem *p, const double *ys, double *mfs, double *Pfs, double *nell,

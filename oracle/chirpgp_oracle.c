@@ -491,6 +491,62 @@ int or_batch(int variant, int64_t B, int64_t T, const OrModel *proto, const doub
     return 0;
 }
 
+/* ---------------------------------------------------------------- KPT model
+ * ekf_for_kpt, filters_smoothers.py:267-314, with the measurement function of build_kpt_chirp_model, models.py:572-578:
+ *   state x = [omega, a_1 .. a_nh, phase] (d = nh + 2),  h(x) = sum_k a_k sin(k g(x_0 + x_{d-1})),  g = softplus (:50).
+ * Per step: (mp, Pp) = _linear_predict(F, Sigma) (:48-52, :299);  H = jacfwd(h)(mp) (:301) in closed form:
+ *   dh/dx_0 = dh/dx_{d-1} = g'(x_0 + x_{d-1}) sum_k k a_k cos(k phi),  dh/da_k = sin(k phi);
+ * S = H Pp H^T + Xi, K = Pp H^T / S, pred = h(mp), mf = mp + K (y - pred), Pf = Pp - K K^T S, n_ell -= logpdf (:302-308). */
+static void run_ekf_kpt(int d, int nh, const double *F, const double *Sigma, double Xi, const double *m0, const double *P0,
+                        int64_t T, const double *ys, double *mfs, double *Pfs, double *nell) {
+    int dd = d * d;
+    double mf[DMAX], Pf[DMAX * DMAX], mp[DMAX], Pp[DMAX * DMAX], T1[DMAX * DMAX], H[DMAX], HP[DMAX], K[DMAX];
+    memcpy(mf, m0, sizeof(double) * d);
+    memcpy(Pf, P0, sizeof(double) * dd);
+    double acc = 0.;
+    for (int64_t t = 0; t < T; t++) {
+        matvec(d, d, F, mf, mp);
+        matmul(d, d, d, F, Pf, T1);
+        matmul_nt(d, d, d, T1, F, Pp);
+        for (int i = 0; i < dd; i++) Pp[i] += Sigma[i];
+        double arg = mp[0] + mp[d - 1], phi = softplus_naive(arg), dphi = sigmoid(arg);
+        double pred = 0., dsum = 0.;
+        for (int k = 1; k <= nh; k++) {
+            double sn = sin(phi * k), cs = cos(phi * k);
+            pred += mp[k] * sn;
+            dsum += mp[k] * (cs * k);
+            H[k] = sn;
+        }
+        H[0] = dsum * dphi; H[d - 1] = dsum * dphi;
+        for (int j = 0; j < d; j++) { double sacc = 0.; for (int i = 0; i < d; i++) sacc += H[i] * Pp[i * d + j]; HP[j] = sacc; }
+        double S = 0.; for (int j = 0; j < d; j++) S += HP[j] * H[j];
+        S += Xi;
+        for (int i = 0; i < d; i++) { double sacc = 0.; for (int j = 0; j < d; j++) sacc += Pp[i * d + j] * H[j]; K[i] = sacc / S; }
+        for (int i = 0; i < d; i++) mf[i] = mp[i] + K[i] * (ys[t] - pred);
+        for (int i = 0; i < d; i++) for (int j = 0; j < d; j++) Pf[i * d + j] = Pp[i * d + j] - (K[i] * K[j]) * S;
+        double sc = sqrt(S), sc2 = sc * sc;
+        acc = acc + (log(2 * OR_PI * sc2) + (ys[t] - pred) * (ys[t] - pred) / sc2) / 2.;
+        if (mfs) memcpy(mfs + t * d, mf, sizeof(double) * d);
+        if (Pfs) memcpy(Pfs + t * dd, Pf, sizeof(double) * dd);
+        if (nell) nell[t] = acc;
+    }
+}
+/* B chirps; F, Sigma (d,d), m0 (d), P0 (d,d) shared or per chirp (stride 0 = shared) */
+int or_ekf_kpt_batch(int64_t B, int64_t T, int d, int nh, const double *F, const double *Sigma, int64_t FS_stride, double Xi,
+                     const double *m0, int64_t m0_stride, const double *P0, int64_t P0_stride, const double *ys,
+                     int64_t ys_stride, double *out_m, double *out_P, double *out_nell, int nthreads) {
+    if (d > DMAX || d != nh + 2) return -1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t bi = 0; bi < B; bi++)
+        run_ekf_kpt(d, nh, F + bi * FS_stride, Sigma + bi * FS_stride, Xi, m0 + bi * m0_stride, P0 + bi * P0_stride, T,
+                    ys + bi * ys_stride, out_m ? out_m + (size_t)bi * T * d : NULL,
+                    out_P ? out_P + (size_t)bi * T * d * d : NULL, out_nell ? out_nell + (size_t)bi * T : NULL);
+    return 0;
+}
+
 /* model probes used by the tests (test/test_models.py, test/test_m32.py analogues) */
 void or_m32_solution(double ell, double sigma, double dt, double *Ft, double *St) { m32_solution(ell, sigma, dt, Ft, St); }
 void or_disc_mean_cov(const OrModel *M, double dt, const double *u, double *mean, double *J, double *Sig) {

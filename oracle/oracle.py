@@ -201,6 +201,41 @@ def cd_sgp_smoother(spec, Bm, sgps, mfs, Pfs, dt, **kw):
     return _run('cd_sgp_smoother', spec, mfs=mfs, Pfs=Pfs, dt=dt, sgps=sgps, Bm=Bm, **kw)
 
 
+def ekf_for_kpt(F, Sigma, num_harmonics, Xi, m0, P0, ys, nthreads=0):
+    """filters_smoothers.py:267-314 with the measurement function of build_kpt_chirp_model (models.py:572-578).
+    ys (T,) or (B, T); F / Sigma / m0 / P0 shared or with a leading batch axis."""
+    L = lib()
+    F, Sigma, m0, P0, ys = _f64(F), _f64(Sigma), _f64(m0), _f64(P0), _f64(ys)
+    batched = ys.ndim == 2
+    ys2 = ys.reshape(-1, ys.shape[-1])
+    B, T = ys2.shape
+    d = m0.shape[-1]
+    fs_stride = d * d if F.ndim == 3 else 0
+    assert F.shape == Sigma.shape
+    out_m, out_P, out_n = np.empty((B, T, d)), np.empty((B, T, d, d)), np.empty((B, T))
+    rc = L.or_ekf_kpt_batch(C.c_int64(B), C.c_int64(T), C.c_int(d), C.c_int(int(num_harmonics)), _p(F), _p(Sigma),
+                            C.c_int64(fs_stride), C.c_double(float(Xi)), _p(m0), C.c_int64(d if m0.ndim == 2 else 0), _p(P0),
+                            C.c_int64(d * d if P0.ndim == 3 else 0), _p(ys2), C.c_int64(T), _p(out_m), _p(out_P), _p(out_n),
+                            C.c_int(nthreads))
+    assert rc == 0
+    if not batched:
+        return out_m[0], out_P[0], out_n[0]
+    return out_m, out_P, out_n
+
+
+def kpt_model(params, fs, num_harmonics=1):
+    """build_kpt_chirp_model (models.py:522-580) without the callable: F, Sigma, m0, P0 as NumPy arrays."""
+    q1, q2, p0, f0, a0 = [float(x) for x in params]
+    d = num_harmonics + 2
+    F = np.eye(d); F[-1, 0] = 1.
+    Sigma = np.zeros((d, d))
+    Sigma[0, 0] = (2 * math.pi * q1 / fs) ** 2
+    for k in range(1, num_harmonics + 1):
+        Sigma[k, k] = q2
+    m0 = np.array([2 * math.pi * f0 / fs] + [a0] * num_harmonics + [0.])
+    return F, Sigma, m0, p0 * np.eye(d)
+
+
 def chirp_m0_P0_H(delta, ell, sigma, m0_v, num_harmonics=1, kind='chirp'):
     """m0, P0, H of build_chirp_model (models.py:453-459) / build_harmonic_chirp_model (:484-494)."""
     h = num_harmonics

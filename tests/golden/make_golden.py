@@ -16,6 +16,7 @@ Inputs are stored next to outputs so the fixtures are self-contained.  Cases:
   lascala.npz        La Scala model (models.py:497-519)
   short.npz          T = 2 warm-up call (demos/ekfs_mle.py:65-66)
   tables.npz         sigma-point tables (bit-exact targets)
+  kpt.npz, kpt_h2.npz  ekf_for_kpt + rts on the KPT model (models.py:522-580), 1 and 2 harmonics, with jax.grad of the nll
 """
 import math
 import os
@@ -144,7 +145,45 @@ def nonlinear_case(name, builder, params, T, dt, ys, sigmas, with_grad, num_harm
     save(name, **out)
 
 
+def kpt_case(name, params, num_harmonics, T, dt, ys, Xi=0.1):
+    """ekf_for_kpt + rts on the KPT model (filters_smoothers.py:267-314, models.py:522-580; the pipeline of
+    tetralith/jobs/kpt_mle.py:39-62) and jax.grad of its nll w.r.t. theta (:39-42)."""
+    fsamp = 1. / dt
+    params_t = jnp.array(params)
+    F, Sigma, m0, P0, h = md.build_kpt_chirp_model(params_t, fsamp, num_harmonics=num_harmonics)
+    ys_t = jnp.asarray(ys)
+    out = dict(params=np.asarray(params), fs=fsamp, dt=dt, Xi=Xi, ys=np.asarray(ys), F=npy(jnp.asarray(F)), Sigma=npy(Sigma),
+               m0=npy(m0), P0=npy(P0), num_harmonics=num_harmonics)
+    f = fs.ekf_for_kpt(jnp.asarray(F), Sigma, h, Xi, m0, P0, dt, ys_t)
+    s = fs.rts(jnp.asarray(F), Sigma, f[0], f[1])
+    for j in range(3):
+        out['ekf_for_kpt_%d' % j] = npy(f[j])
+    for j in range(2):
+        out['rts_%d' % j] = npy(s[j])
+    out['h_at_m0'] = npy(h(m0))
+    theta = md.g_inv(params_t)
+
+    def obj(th):
+        F_, Sigma_, m0_, P0_, h_ = md.build_kpt_chirp_model(md.g(th), fsamp, num_harmonics=num_harmonics)
+        return fs.ekf_for_kpt(jnp.asarray(F_), Sigma_, h_, Xi, m0_, P0_, dt, ys_t)[-1][-1]
+
+    out['theta'] = npy(theta)
+    out['grad_ekf_for_kpt'] = npy(jax.grad(obj)(theta))
+    save(name, **out)
+
+
+def kpt_cases():
+    dt = 1e-3
+    _, ys3, _ = toy.synthetic_batch(3, 3141, dt, Xi=0.1, seed=2)
+    kpt_case('kpt', [0.02, 1e-3, 1e-2, 8., 1.], 1, 400, dt, ys3[0, 1200:1600])
+    _, ysh, _ = toy.synthetic_batch(2, 3141, dt, Xi=0.1, num_harmonics=3, seed=4)
+    kpt_case('kpt_h2', [0.05, 1e-3, 1e-2, 8., 0.7], 2, 250, dt, ysh[1, 1200:1450])
+
+
 def main():
+    if '--only-kpt' in sys.argv:       # added after the other fixtures were committed: leaves them untouched
+        kpt_cases()
+        return
     # sigma-point tables (bit-exact targets for chirpgp_b200.quadratures)
     tabs = {}
     for d, o in [(4, 3), (3, 4), (1, 5), (1, 10), (2, 3), (8, 2), (4, 5)]:
@@ -181,6 +220,7 @@ def main():
     hb2 = lambda p: md.build_harmonic_chirp_model(p, num_harmonics=2, freq_scale=1.7)
     nonlinear_case('harmonic2', hb2, [0.2, 0.15, 0.1, 0.7, 1.2, 5.], 120, dt, ysh[0, 1200:1320],
                    {'cub': qd.SigmaPoints.cubature(6)}, False, num_harmonics=2)
+    kpt_cases()
 
 
 if __name__ == '__main__':

@@ -140,3 +140,31 @@ def test_fd_gradient_mle_for_sigma_point_and_cd_filters(golden):
         npt.assert_allclose(v, want_val, rtol=1e-10)
         # measured: 2.8e-7 (sgp_filter) -- the floor is the nll's own rounding noise (~1e-12 relative) divided by h
         npt.assert_allclose(gr, want_grad, rtol=2e-6, atol=1e-7)
+
+
+def test_kpt_mle_objective_and_gradient(golden):
+    """tetralith/jobs/kpt_mle.py:39-42: obj_func(theta) = ekf_for_kpt(...)[-1][-1] and its jax.grad, here by five-point
+    differences over a candidate batch (fit_mle(method='ekf_for_kpt'))."""
+    import scipy.optimize
+    for name in ('kpt', 'kpt_h2'):
+        z = golden(name)
+        nh, fsamp = int(z['num_harmonics']), float(z['fs'])
+        calls = []
+
+        def spy(fun, x0, jac, method, options):
+            calls.append(fun(np.asarray(x0)))
+
+            class R:
+                x, success = np.asarray(x0), True
+            return R()
+
+        orig = scipy.optimize.minimize
+        scipy.optimize.minimize = spy
+        try:
+            mle.fit_mle(lambda p: cg.build_kpt_chirp_model(p, fsamp, nh), z['theta'], None, float(z['Xi']), float(z['dt']),
+                        z['ys'], method='ekf_for_kpt')
+        finally:
+            scipy.optimize.minimize = orig
+        v, gr = calls[0]
+        npt.assert_allclose(v, z['ekf_for_kpt_2'][-1], rtol=1e-10)
+        npt.assert_allclose(gr, z['grad_ekf_for_kpt'], rtol=2e-6, atol=1e-6)

@@ -398,3 +398,41 @@ def test_gaussian_expectation_device_vs_host(batch):
     assert np.isinf(got[-2, 0])
     big = gaussian_expectation(_cuda(np.array([50., 200.])), _cuda(np.array([1., 2.])), force_shape=True).cpu().numpy()
     _close(big[:, 0], [50., 200.], rtol=1e-14, atol=0)          # E[g(V)] = E[V] = m to rounding when g is linear there
+
+
+# ---------------------------------------------------------------------------------------- KPT model
+@pytest.mark.parametrize('name', ['kpt', 'kpt_h2'])
+def test_kpt_golden(golden, name):
+    """ekf_for_kpt + rts (filters_smoothers.py:267-314; the pipeline of tetralith/jobs/kpt_mle.py:52-62) through the CUDA
+    path against the outputs of the reference sources."""
+    z = golden(name)
+    nh = int(z['num_harmonics'])
+    F, Sigma, m0, P0, h = cg.build_kpt_chirp_model(z['params'], float(z['fs']), nh)
+    f = cg.ekf_for_kpt(F, Sigma, h, float(z['Xi']), m0, P0, float(z['dt']), z['ys'])
+    for j in range(3):
+        _close(f[j], z['ekf_for_kpt_%d' % j], rtol=NLL_RT if j == 2 else RT, atol=1e-9 if j == 2 else AT)
+    s = cg.rts(F, Sigma, z['ekf_for_kpt_0'], z['ekf_for_kpt_1'])
+    for j in range(2):
+        _close(s[j], z['rts_%d' % j])
+    with pytest.raises(NotImplementedError):
+        cg.ekf_for_kpt(F, Sigma, lambda x: x[1], 0.1, m0, P0, 1e-3, z['ys'])
+
+
+def test_kpt_batched_vs_oracle(batch):
+    """1 and 3 harmonics (d = 3, 5), per-chirp parameters, full length, + rts (d = 5 takes the thread-per-chirp sweep)."""
+    B, T, dt, ys = batch
+    rng = np.random.default_rng(11)
+    for nh, yy in ((1, ys[:8]), (3, toymodels.synthetic_batch(8, T, dt, Xi=0.1, num_harmonics=3, seed=4)[1])):
+        params = np.array([0.02, 1e-3, 1e-2, 8., 1.]) * np.exp(0.1 * rng.standard_normal((8, 5)))
+        F, Sigma, m0, P0, h = cg.build_kpt_chirp_model(params, 1. / dt, nh)
+        f = cg.ekf_for_kpt(F, Sigma, h, 0.1, m0, P0, dt, yy)
+        Fo = np.broadcast_to(F.numpy(), Sigma.shape).copy()
+        fo = orc.ekf_for_kpt(Fo, Sigma.numpy(), nh, 0.1, m0.numpy(), P0.numpy(), yy)
+        _check_filter(f, fo, ATOL_LONG)
+        assert np.all(np.isfinite(f[0]))
+    # shared parameters: rts on the filtering result
+    F, Sigma, m0, P0, h = cg.build_kpt_chirp_model(np.array([0.02, 1e-3, 1e-2, 8., 1.]), 1. / dt, 3)
+    f = cg.ekf_for_kpt(F, Sigma, h, 0.1, m0, P0, dt, yy)
+    s = cg.rts(F, Sigma, f[0], f[1])
+    so = orc.rts(F.numpy(), Sigma.numpy(), f[0], f[1])
+    _check_smoother(s, so, ATOL_LONG)

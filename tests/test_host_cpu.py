@@ -173,3 +173,18 @@ def test_toymodels_phase_derivative_is_frequency():
     _, ys, _ = cg.toymodels.synthetic_batch(3, 64, 1e-3, seed=2)
     _, ys2, _ = cg.toymodels.synthetic_batch(3, 64, 1e-3, seed=2)
     npt.assert_array_equal(ys, ys2)
+
+
+def test_kpt_model_builder_matches_reference_fixture(golden):
+    """build_kpt_chirp_model (models.py:522-580) and its measurement function on the host."""
+    import chirpgp_b200 as cg
+    for name in ('kpt', 'kpt_h2'):
+        z = golden(name)
+        nh = int(z['num_harmonics'])
+        F, Sigma, m0, P0, h = cg.build_kpt_chirp_model(z['params'], float(z['fs']), nh)
+        for a, b in ((F, z['F']), (Sigma, z['Sigma']), (m0, z['m0']), (P0, z['P0'])):
+            npt.assert_allclose(a.numpy(), b, rtol=1e-15, atol=0)
+        npt.assert_allclose(float(h(m0)), float(z['h_at_m0']), rtol=1e-15)
+        # batched parameters: one model per chirp
+        Fb, Sb, m0b, P0b, _ = cg.build_kpt_chirp_model(np.tile(z['params'], (3, 1)), float(z['fs']), nh)
+        assert Sb.shape == (3, nh + 2, nh + 2) and m0b.shape == (3, nh + 2) and P0b.shape == (3, nh + 2, nh + 2)
