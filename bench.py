@@ -130,7 +130,8 @@ def cpu_sample(n_chirps: int, nthreads: int = 0):
     spec = orc.ChirpSpec(PARAMS[0], PARAMS[1], PARAMS[3], PARAMS[4])
     m0, P0, H = orc.chirp_m0_P0_H(PARAMS[2], PARAMS[3], PARAMS[4], PARAMS[5])
     sg = SigmaPoints.gauss_hermite(D, 3)
-    threads = nthreads or orc.max_threads()
+    # all the host threads this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    threads = nthreads or len(os.sched_getaffinity(0))
     t0 = time.perf_counter()
     f = orc.sgp_filter(spec, sg, H, XI, m0, P0, DT, ys, nthreads=threads)
     orc.sgp_smoother(spec, sg, f[0], f[1], DT, nthreads=threads)
