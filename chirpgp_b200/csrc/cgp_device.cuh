@@ -67,6 +67,73 @@ template <int D> CGP_DEV void store_mat(double *__restrict__ dst, const double (
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) dst[r * D + c] = src[r][c];
     }
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.256).  One lane moves a whole 32-byte sector: a thread-per-chirp kernel whose
+// lanes write to 32 different chirps would otherwise fill every sector with two 16-byte partial writes.
+// Pointers must be 32-byte aligned.
+CGP_DEV void ldg256(const double *__restrict__ q, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(q));
+}
+CGP_DEV void stg256(double *__restrict__ q, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(q), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+template <bool WIDE, int N> CGP_DEV void gload_vec(const double *__restrict__ src, double (&dst)[N]) {
+    if constexpr (WIDE && N % 4 == 0) {
+        CGP_UNROLL for (int i = 0; i < N; i += 4) ldg256(src + i, dst[i], dst[i + 1], dst[i + 2], dst[i + 3]);
+    } else {
+        load_vec<N>(src, dst);
+    }
+}
+template <bool WIDE, int N> CGP_DEV void gstore_vec(double *__restrict__ dst, const double (&src)[N]) {
+    if constexpr (WIDE && N % 4 == 0) {
+        CGP_UNROLL for (int i = 0; i < N; i += 4) stg256(dst + i, src[i], src[i + 1], src[i + 2], src[i + 3]);
+    } else {
+        store_vec<N>(dst, src);
+    }
+}
+template <bool WIDE, int D> CGP_DEV void gload_mat(const double *__restrict__ src, double (&dst)[D][D]) {
+    if constexpr (WIDE && D % 4 == 0) {
+        CGP_UNROLL for (int r = 0; r < D; r++)
+            CGP_UNROLL for (int c = 0; c < D; c += 4) ldg256(src + r * D + c, dst[r][c], dst[r][c + 1], dst[r][c + 2], dst[r][c + 3]);
+    } else {
+        load_mat<D>(src, dst);
+    }
+}
+template <bool WIDE, int D> CGP_DEV void gstore_mat(double *__restrict__ dst, const double (&src)[D][D]) {
+    if constexpr (WIDE && D % 4 == 0) {
+        CGP_UNROLL for (int r = 0; r < D; r++)
+            CGP_UNROLL for (int c = 0; c < D; c += 4) stg256(dst + r * D + c, src[r][c], src[r][c + 1], src[r][c + 2], src[r][c + 3]);
+    } else {
+        store_mat<D>(dst, src);
+    }
+}
+
+// Cumulative nll of ONE chirp (thread-per-chirp kernels) written in whole 32-byte sectors: the values are collected four at a
+// time at the positions the row occupies in memory ((b T + t) mod 4); aligned groups go out as one 256-bit store, the
+// ragged ends of the row (and everything, if the buffer is not 32-byte aligned) as scalars.
+struct NellRowWriter {
+    double v0, v1, v2, v3;
+    double *row;
+    int64_t g0;
+    bool wide;
+    CGP_DEV void init(double *nell, int64_t b, int64_t T) {
+        row = nell + b * T; g0 = b * T;
+        wide = (reinterpret_cast<uintptr_t>(nell) & 31u) == 0;
+        v0 = v1 = v2 = v3 = 0.;
+    }
+    CGP_DEV void put(int64_t t, int64_t T, double acc) {
+        if (!wide) { row[t] = acc; return; }
+        const int q = (int)((g0 + t) & 3);
+        if (q == 0) v0 = acc; else if (q == 1) v1 = acc; else if (q == 2) v2 = acc; else v3 = acc;
+        if (q == 3 && t >= 3) { stg256(row + t - 3, v0, v1, v2, v3); return; }
+        if (q == 3 || t == T - 1) {                       // ragged start / end of the row: steps t - q .. t that exist
+            if (t - q >= 0) row[t - q] = v0;
+            if (q >= 1 && t - q + 1 >= 0) row[t - q + 1] = v1;
+            if (q >= 2 && t - q + 2 >= 0) row[t - q + 2] = v2;
+            if (q >= 3) row[t] = v3;
+        }
+    }
+};
+
 // packed-symmetric <-> full row-major memory
 template <int D> CGP_DEV void load_sym(const double *__restrict__ src, double (&dst)[NSym<D>::value]) {
     // reads the lower triangle only (what cholesky would see)

@@ -69,6 +69,7 @@ inline int group_size(const CgpProblem &p, bool share) {
 }
 
 inline bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+inline bool aligned32(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -7,6 +7,12 @@ int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     return dispatch_disc(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         const int block = 128;
+        if constexpr (Model::D % 4 == 0) {
+            if (io.mfs != nullptr && aligned32(io.mfs) && aligned32(io.Pfs)) {
+                ekf_thread_kernel<Model, true><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
+                return check_launch();
+            }
+        }
         ekf_thread_kernel<Model><<<(unsigned)ceil_div(p.B, block), block, 0, s>>>(p, io);
         return check_launch();
     });

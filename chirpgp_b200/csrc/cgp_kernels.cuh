@@ -36,7 +36,8 @@ template <int D> CGP_DEV constexpr int ws_record() { return 2 * D * D + D; }
 
 // ================================================================================================ thread-per-chirp filters
 // kf (filters_smoothers.py:145-184) and ekf (:222-264): Model = ModelLinearDisc<D> | ModelLCD<NH>
-template <class Model>
+// WIDE: outputs are 32-byte aligned and d % 4 == 0 -> every lane writes whole 32-byte sectors (STG.256)
+template <class Model, bool WIDE = false>
 __global__ void __launch_bounds__(128) ekf_thread_kernel(const CgpProblem p, const FilterIO io) {
     constexpr int D = Model::D;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,6 +52,8 @@ __global__ void __launch_bounds__(128) ekf_thread_kernel(const CgpProblem p, con
     const int64_t T = p.T;
     const bool store = io.mfs != nullptr;
     double acc = 0.;
+    NellRowWriter nellw;
+    if (io.nell && !io.nell_last_only) nellw.init(io.nell, b, T);
     double ynext = __ldg(y);
     for (int64_t t = 0; t < T; t++) {
         const double yt = ynext;
@@ -63,10 +66,10 @@ __global__ void __launch_bounds__(128) ekf_thread_kernel(const CgpProblem p, con
             if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
         acc = acc + linear_update<D>(mp, Pp, H, p.Xi, yt, m, P);
         if (store) {
-            store_vec<D>(io.mfs + (b * T + t) * D, m);
-            store_mat<D>(io.Pfs + (b * T + t) * (D * D), P);
+            gstore_vec<WIDE, D>(io.mfs + (b * T + t) * D, m);
+            gstore_mat<WIDE, D>(io.Pfs + (b * T + t) * (D * D), P);
         }
-        if (io.nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+        if (io.nell && !io.nell_last_only) nellw.put(t, T, acc);
     }
     if (io.nell && io.nell_last_only) io.nell[b] = acc;
 }
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(128) ekf_kpt_thread_kernel(const CgpProblem p,
     const int64_t T = p.T;
     const bool store = io.mfs != nullptr;
     double acc = 0.;
+    NellRowWriter nellw;
+    if (io.nell && !io.nell_last_only) nellw.init(io.nell, b, T);
     double ynext = __ldg(y);
     for (int64_t t = 0; t < T; t++) {
         const double yt = ynext;
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(128) ekf_kpt_thread_kernel(const CgpProblem p,
             store_vec<D>(io.mfs + (b * T + t) * D, m);
             store_mat<D>(io.Pfs + (b * T + t) * (D * D), P);
         }
-        if (io.nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+        if (io.nell && !io.nell_last_only) nellw.put(t, T, acc);
     }
     if (io.nell && io.nell_last_only) io.nell[b] = acc;
 }
@@ -179,6 +184,8 @@ __global__ void __launch_bounds__(128) cd_ekf_thread_kernel(const CgpProblem p, 
     const bool store = io.mfs != nullptr;
     const double dt = p.dt;
     double acc = 0.;
+    NellRowWriter nellw;
+    if (io.nell && !io.nell_last_only) nellw.init(io.nell, b, T);
     double ynext = __ldg(y);
     for (int64_t t = 0; t < T; t++) {
         const double yt = ynext;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(128) cd_ekf_thread_kernel(const CgpProblem p, 
             store_vec<D>(io.mfs + (b * T + t) * D, m);
             store_sym<D>(io.Pfs + (b * T + t) * (D * D), P);
         }
-        if (io.nell && !io.nell_last_only) io.nell[b * T + t] = acc;
+        if (io.nell && !io.nell_last_only) nellw.put(t, T, acc);
     }
     if (io.nell && io.nell_last_only) io.nell[b] = acc;
 }
@@ -523,6 +530,65 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const CgpProblem p, const
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
         if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
     gain_and_store<D>(DT, mp, Pp, io.ws + (b * p.T + t) * ws_record<D>());
+}
+
+// rts / eks in ONE pass, one thread per chirp, no workspace: for k = T-2 .. 0 the gain is formed from (mf_k, Pf_k)
+// (:342-345, :81-82) and applied at once (:83-84).  For batches large enough to fill the GPU with one thread per chirp (the
+// CRLB job runs 10^6 chirps, tetralith/jobs/crlb_ekf.py:59): DRAM traffic is the algorithmic 2 * 8 (d + d^2) bytes per step
+// instead of ~3.3x that through the [G | mp | Pp] workspace of the two-kernel path.  (mf, Pf) of the next step are
+// fetched while the current one is evaluated.
+template <class Model, bool WIDE = false>
+__global__ void __launch_bounds__(128) eks_onepass_thread_kernel(const CgpProblem p, const SmootherIO io) {
+    constexpr int D = Model::D;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int64_t T = p.T;
+    Model mdl;
+    mdl.load(p.consts + b * p.consts_stride, p.dt);
+    double ms[D], Ps[D][D];
+    gload_vec<WIDE, D>(io.mfs + (b * T + T - 1) * D, ms);
+    gload_mat<WIDE, D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
+    gstore_vec<WIDE, D>(io.mss + (b * T + T - 1) * D, ms);
+    gstore_mat<WIDE, D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+    if (T < 2) return;
+    double mfn[D], Pfn[D][D];
+    gload_vec<WIDE, D>(io.mfs + (b * T + T - 2) * D, mfn);
+    gload_mat<WIDE, D>(io.Pfs + (b * T + T - 2) * (D * D), Pfn);
+    for (int64_t t = T - 2; t >= 0; t--) {
+        double mf[D], Pf[D][D];
+        CGP_UNROLL for (int r = 0; r < D; r++) {
+            mf[r] = mfn[r];
+            CGP_UNROLL for (int c = 0; c < D; c++) Pf[r][c] = Pfn[r][c];
+        }
+        if (t > 0) {
+            gload_vec<WIDE, D>(io.mfs + (b * T + t - 1) * D, mfn);
+            gload_mat<WIDE, D>(io.Pfs + (b * T + t - 1) * (D * D), Pfn);
+        }
+        double mp[D], J[D][D], DT[D][D], Pp[D][D];
+        mdl.mean_jac(mf, mp, J);                          // :342-343
+        matmul<D>(J, Pf, DT);                             // DT = J Pf (:345)
+        matmul_nt<D>(DT, J, Pp);                          // :344
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
+            if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
+        double L[D][D], rinv[D], Gm[D][D];
+        chol_lower_rsqrt<D>(Pp, L, rinv);
+        CGP_UNROLL for (int c = 0; c < D; c++) {          // G = (Pp^{-1} DT)^T, as gain_and_store
+            double col[D];
+            CGP_UNROLL for (int i = 0; i < D; i++) col[i] = DT[i][c];
+            chol_solve_vec_rinv<D>(L, rinv, col);
+            CGP_UNROLL for (int i = 0; i < D; i++) Gm[c][i] = col[i];
+        }
+        double dm[D], dP[D][D], t1[D][D], t2[D][D], gm[D];
+        CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = ms[r] - mp[r];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) dP[r][c] = Ps[r][c] - Pp[r][c];
+        matvec<D>(Gm, dm, gm);
+        CGP_UNROLL for (int r = 0; r < D; r++) ms[r] = mf[r] + gm[r];
+        matmul<D>(Gm, dP, t1);
+        matmul_nt<D>(t1, Gm, t2);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ps[r][c] = Pf[r][c] + t2[r][c];
+        gstore_vec<WIDE, D>(io.mss + (b * T + t) * D, ms);
+        gstore_mat<WIDE, D>(io.Pss + (b * T + t) * (D * D), Ps);
+    }
 }
 
 // sgp_smoother gains (filters_smoothers.py:520-527): one thread per (chirp, step), all sigma points serially.

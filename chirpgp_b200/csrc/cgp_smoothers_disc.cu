@@ -30,10 +30,24 @@ template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &
     return check_launch();
 }
 
+// From this many chirps on one thread per chirp fills the GPU (148 SMs x 16 resident warps x 32) and the one-pass kernel's
+// 3.3x lower DRAM traffic wins over the time-parallel gain kernel + sweep (profiles/r1_ekf_eks.txt).
+static const int64_t kOnePassMinB = 32768;
+
 int launch_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
     return dispatch_disc(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         const int block = 128;
+        if constexpr (Model::D == 2 || Model::D == 4) {          // everything of a step fits the register file up to d = 4
+            if (p.B >= kOnePassMinB && aligned16(io.mfs) && aligned16(io.Pfs) && aligned16(io.mss) && aligned16(io.Pss)) {
+                const unsigned grid = (unsigned)ceil_div(p.B, block);
+                if (Model::D == 4 && aligned32(io.mfs) && aligned32(io.Pfs) && aligned32(io.mss) && aligned32(io.Pss))
+                    eks_onepass_thread_kernel<Model, true><<<grid, block, 0, s>>>(p, io);
+                else
+                    eks_onepass_thread_kernel<Model, false><<<grid, block, 0, s>>>(p, io);
+                return check_launch();
+            }
+        }
         const int64_t items = p.B * (p.T - 1);
         if (items > 0) {
             eks_gain_kernel<Model><<<(unsigned)ceil_div(items, block), block, 0, s>>>(p, io);

@@ -436,3 +436,30 @@ def test_kpt_batched_vs_oracle(batch):
     s = cg.rts(F, Sigma, f[0], f[1])
     so = orc.rts(F.numpy(), Sigma.numpy(), f[0], f[1])
     _check_smoother(s, so, ATOL_LONG)
+
+
+def test_large_batch_onepass_eks_and_wide_stores():
+    """B >= 32768 takes the one-pass thread-per-chirp smoother (no workspace, 256-bit loads / stores); smaller batches take the
+    gain kernel + sweep.  Same results to rounding, and both match the oracle.  Also rts (linear model, d = 2)."""
+    B, T, dt = 32768 + 5, 23, 0.01
+    rng = np.random.default_rng(3)
+    ys = rng.standard_normal((B, T))
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    f = cg.ekf(mc, H, 0.1, m0, P0, dt, ys)
+    s = cg.eks(mc, f[0], f[1], dt)                                   # one pass
+    half = B // 2
+    s_lo = cg.eks(mc, f[0][:half], f[1][:half], dt)                  # two kernels
+    s_hi = cg.eks(mc, f[0][half:], f[1][half:], dt)
+    for j in range(2):
+        _close(s[j][:half], s_lo[j], atol=ATOL_LONG)
+        _close(s[j][half:], s_hi[j], atol=ATOL_LONG)
+    pick = np.r_[0:16, B - 5:B]
+    fo = orc.ekf(spec, H, 0.1, m0, P0, dt, ys[pick])
+    _check_filter([x[pick] for x in f], fo, ATOL_LONG)
+    so = orc.eks(spec, fo[0], fo[1], dt)
+    _check_smoother([x[pick] for x in s], so, ATOL_LONG)
+    F = np.array([[0.9, 0.1], [0., 0.8]]); Sigma = np.diag([0.1, 0.2])
+    fk = cg.kf(F, Sigma, np.array([1., 0.]), 0.5, np.zeros(2), np.eye(2), ys)
+    sk = cg.rts(F, Sigma, fk[0], fk[1])
+    sko = orc.rts(F, Sigma, fk[0][pick], fk[1][pick])
+    _check_smoother([x[pick] for x in sk], sko, ATOL_LONG)
