@@ -107,6 +107,18 @@ template <bool WIDE, int D> CGP_DEV void gstore_mat(double *__restrict__ dst, co
     }
 }
 
+// Stores of one lane's record to GLOBAL memory that pick the 256-bit form whenever the destination allows it (checked at run
+// time: 32-byte aligned, element count a multiple of 4) -- for kernels where the lanes of a warp write different records.
+template <int N> CGP_DEV void gstore_vec_auto(double *__restrict__ dst, const double (&src)[N]) {
+    if (N % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) gstore_vec<true, N>(dst, src);
+    else store_vec<N>(dst, src);
+}
+template <int D> CGP_DEV void gstore_mat_auto(double *__restrict__ dst, const double (&src)[D][D]) {
+    if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) gstore_mat<true, D>(dst, src);
+    else store_mat<D>(dst, src);
+}
+template <int D> CGP_DEV void gstore_sym_auto(double *__restrict__ dst, const double (&src)[D * (D + 1) / 2]);
+
 // Cumulative nll of ONE chirp (thread-per-chirp kernels) written in whole 32-byte sectors: the values are collected four at a
 // time at the positions the row occupies in memory ((b T + t) mod 4); aligned groups go out as one 256-bit store, the
 // ragged ends of the row (and everything, if the buffer is not 32-byte aligned) as scalars.
@@ -146,6 +158,16 @@ template <int D> CGP_DEV void store_sym(double *__restrict__ dst, const double (
                 *reinterpret_cast<double2 *>(dst + r * D + c) = make_double2(src[sidx(r, c)], src[sidx(r, c + 1)]);
     } else {
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) dst[r * D + c] = src[sidx(r, c)];
+    }
+}
+
+template <int D> CGP_DEV void gstore_sym_auto(double *__restrict__ dst, const double (&src)[D * (D + 1) / 2]) {
+    if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+        CGP_UNROLL for (int r = 0; r < D; r++)
+            CGP_UNROLL for (int c = 0; c < D; c += 4)
+                stg256(dst + r * D + c, src[sidx(r, c)], src[sidx(r, c + 1)], src[sidx(r, c + 2)], src[sidx(r, c + 3)]);
+    } else {
+        store_sym<D>(dst, src);
     }
 }
 

@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(128) ekf_kpt_thread_kernel(const CgpProblem p,
         H[D - 1] = H[0];
         acc = acc + nonlinear_update<D>(mp, Pp, H, pred, p.Xi, yt, m, P);
         if (store) {
-            store_vec<D>(io.mfs + (b * T + t) * D, m);
-            store_mat<D>(io.Pfs + (b * T + t) * (D * D), P);
+            gstore_vec_auto<D>(io.mfs + (b * T + t) * D, m);
+            gstore_mat_auto<D>(io.Pfs + (b * T + t) * (D * D), P);
         }
         if (io.nell && !io.nell_last_only) nellw.put(t, T, acc);
     }
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(128) cd_ekf_thread_kernel(const CgpProblem p, 
         CGP_UNROLL for (int i = 0; i < D; i++) m[i] = mf[i];
         CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = Pf[i];
         if (store) {
-            store_vec<D>(io.mfs + (b * T + t) * D, m);
-            store_sym<D>(io.Pfs + (b * T + t) * (D * D), P);
+            gstore_vec_auto<D>(io.mfs + (b * T + t) * D, m);
+            gstore_sym_auto<D>(io.Pfs + (b * T + t) * (D * D), P);
         }
         if (io.nell && !io.nell_last_only) nellw.put(t, T, acc);
     }
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, CD>::kBlock) sgp_filter_ker
         double S, resid;
         linear_update_fast<D, false>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
         if (store) {
-            store_vec<D>(io.mfs + (b * T + t) * D, m);
-            store_sym<D>(io.Pfs + (b * T + t) * (D * D), Pc);
+            gstore_vec_auto<D>(io.mfs + (b * T + t) * D, m);
+            gstore_sym_auto<D>(io.Pfs + (b * T + t) * (D * D), Pc);
         }
         if constexpr (G == 1) {
             acc = acc + nll_increment(S, resid);
@@ -500,10 +500,10 @@ CGP_DEV void gain_and_store(const double (&DT)[D][D], const double (&mp)[D], con
         chol_solve_vec_rinv<D>(L, rinv, col);
         CGP_UNROLL for (int i = 0; i < D; i++) Gm[c][i] = col[i];
     }
-    store_mat<D>(rec, Gm);
+    gstore_mat_auto<D>(rec, Gm);
     if constexpr (D % 2 == 0) {
-        store_vec<D>(rec + D * D, mp);
-        store_mat<D>(rec + D * D + D, Pp);
+        gstore_vec_auto<D>(rec + D * D, mp);
+        gstore_mat_auto<D>(rec + D * D + D, Pp);
     } else {
         CGP_UNROLL for (int i = 0; i < D; i++) rec[D * D + i] = mp[i];
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) rec[D * D + D + r * D + c] = Pp[r][c];
@@ -624,8 +624,8 @@ __global__ void __launch_bounds__(64) smoother_sweep_kernel(const CgpProblem p, 
     double ms[D], Ps[D][D];
     load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
     load_mat<D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
-    store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
-    store_mat<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+    gstore_vec_auto<D>(io.mss + (b * T + T - 1) * D, ms);
+    gstore_mat_auto<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
     if (T < 2) return;
     double Gn[D][D], mpn[D], Ppn[D][D], mfn[D], Pfn[D][D];
     auto fetch = [&](int64_t t) {
@@ -655,8 +655,8 @@ __global__ void __launch_bounds__(64) smoother_sweep_kernel(const CgpProblem p, 
         matmul<D>(Gm, dP, t1);
         matmul_nt<D>(t1, Gm, t2);
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ps[r][c] = Pf[r][c] + t2[r][c];
-        store_vec<D>(io.mss + (b * T + t) * D, ms);
-        store_mat<D>(io.Pss + (b * T + t) * (D * D), Ps);
+        gstore_vec_auto<D>(io.mss + (b * T + t) * D, ms);
+        gstore_mat_auto<D>(io.Pss + (b * T + t) * (D * D), Ps);
     }
 }
 
@@ -678,8 +678,8 @@ __global__ void __launch_bounds__(64) cd_eks_thread_kernel(const CgpProblem p, c
     double ms[D], Ps[NS];
     load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
     load_sym<D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
-    store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
-    store_sym<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+    gstore_vec_auto<D>(io.mss + (b * T + T - 1) * D, ms);
+    gstore_sym_auto<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
     const double ndt = -p.dt;
     for (int64_t t = T - 2; t >= 0; t--) {
         double mf[D], Pf[D][D], Lf[D][D], X[D][D];
@@ -706,8 +706,8 @@ __global__ void __launch_bounds__(64) cd_eks_thread_kernel(const CgpProblem p, c
             CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++)
                 dP[sidx(r, c)] = (Y[r][c] + Y[c][r]) - Qc[sidx(r, c)];
         }, ms, Ps, ndt);
-        store_vec<D>(io.mss + (b * T + t) * D, ms);
-        store_sym<D>(io.Pss + (b * T + t) * (D * D), Ps);
+        gstore_vec_auto<D>(io.mss + (b * T + t) * D, ms);
+        gstore_sym_auto<D>(io.Pss + (b * T + t) * (D * D), Ps);
     }
 }
 
@@ -735,8 +735,8 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, true>::kBlock) cd_sgp_smoot
     load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
     load_sym<D>(io.Pfs + (b * T + T - 1) * (D * D), Ps);
     if (store) {
-        store_vec<D>(io.mss + (b * T + T - 1) * D, ms);
-        store_sym<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
+        gstore_vec_auto<D>(io.mss + (b * T + T - 1) * D, ms);
+        gstore_sym_auto<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
     }
     const int n = p.n_sigma;
     const double ndt = -p.dt;
@@ -763,8 +763,8 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, true>::kBlock) cd_sgp_smoot
                 dP[sidx(r, c)] = ((_P[sidx(r, c)] + W[r][c]) + W[c][r]) - 2 * Qc[sidx(r, c)];
         }, ms, Ps, ndt);
         if (store) {
-            store_vec<D>(io.mss + (b * T + t) * D, ms);
-            store_sym<D>(io.Pss + (b * T + t) * (D * D), Ps);
+            gstore_vec_auto<D>(io.mss + (b * T + t) * D, ms);
+            gstore_sym_auto<D>(io.Pss + (b * T + t) * (D * D), Ps);
         }
     }
 }

@@ -290,7 +290,9 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
     nell = torch.empty((B,) if last_only else (B, T), dtype=_F64, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rec = None
-    if gains_for is not None and store and kind[0] == 'torch' and kind[1] == dev and T > 1:
+    # only where the filter kernel itself produces the gains: elsewhere the same gain kernel would merely run earlier
+    if (gains_for is not None and store and kind[0] == 'torch' and kind[1] == dev and T > 1
+            and L.cgp_sgp_filter_gains_fused(C.byref(p)) == 1):
         nbytes = L.cgp_workspace_bytes(b'sgp_filter_gains', C.byref(p))
         try:
             ws = torch.empty((max(nbytes, 8) // 8,), dtype=_F64, device=dev)
@@ -422,8 +424,8 @@ def eks(cond_m_cov, mfs, Pfs, dt) -> Tuple:
 def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, *, smoother_gains=None) -> Tuple:
     """Sigma-point (Gauss--Hermite / cubature) filter (filters_smoothers.py:446-490).
 
-    ``smoother_gains`` (extension; default: on for CUDA-tensor ``ys``, see ``FUSE_SMOOTHER_GAINS``): the filter kernel
-    also evaluates what ``sgp_smoother``'s reverse scan computes from the filtering result alone (:520-527 -- the
+    ``smoother_gains`` (extension; default: on for CUDA-tensor ``ys`` where a fused kernel exists -- chirp LCD model with
+    Gauss--Hermite order 3 --, see ``FUSE_SMOOTHER_GAINS``): the filter kernel also evaluates what ``sgp_smoother``'s reverse scan computes from the filtering result alone (:520-527 -- the
     sigma-point prediction from (mf_k, Pf_k) is the one the filter makes for step k + 1) and leaves it in a device
     workspace attached to the returned ``mfs``; ``sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt)`` on those very tensors
     then only runs the sequential sweep (:83-84).  Any other input to the smoother takes the stand-alone path."""

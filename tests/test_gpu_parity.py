@@ -355,19 +355,42 @@ def test_fused_gains_are_dropped_when_inputs_change(batch):
 
 def test_filter_gains_abi_unfused_models(golden):
     """cgp_sgp_filter_gains_f64 for a configuration without a fused kernel (harmonic d = 8, cubature): filter, then the
-    time-parallel gain kernel; the Python API gives the same smoother result either way."""
+    time-parallel gain kernel, then cgp_smoother_sweep_f64 -- same result as cgp_sgp_smoother_f64.  The Python API does not
+    precompute gains there (nothing would be saved)."""
+    import ctypes as C
+    from chirpgp_b200 import _native as N
+    from chirpgp_b200 import filters_smoothers as fs
     z = golden('harmonic')
     drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(z['params'], num_harmonics=3)
     dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
     sg = cg.SigmaPoints.cubature(8)
     f = cg.sgp_filter(mc, sg, H.cuda(), Xi, m0.cuda(), P0.cuda(), dt, _cuda(ys))
-    assert getattr(f[0], '_cgp_smoother_gains', None) is not None
-    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    assert getattr(f[0], '_cgp_smoother_gains', None) is None
+    s_ref = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    L = N.lib()
+    dev = torch.device('cuda', 0)
+    T, d = ys.shape[0], 8
+    consts = fs._consts_on_device(mc, dt, dev, dt)
+    sig = fs._sigma_tables(sg, dev)
+    m0d, P0d, Hd, ysd = m0.cuda(), P0.cuda(), H.cuda(), _cuda(ys)
+    p = fs._problem(1, T, N.CGP_MODEL_LCD, d, 3, consts, 0, m0d, 0, P0d, 0, Hd, None, 0, sig, Xi, dt, 1, fs._h_unit_index(H))
+    assert L.cgp_sgp_filter_gains_fused(C.byref(p)) == 0
+    nbytes = L.cgp_workspace_bytes(b'sgp_filter_gains', C.byref(p))
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+    mfs, Pfs, nell = torch.empty((T, d), dtype=torch.float64, device=dev), torch.empty((T, d, d), dtype=torch.float64, device=dev), \
+        torch.empty(T, dtype=torch.float64, device=dev)
+    rc = L.cgp_sgp_filter_gains_f64(C.byref(p), fs._ptr(ysd), fs._ptr(mfs), fs._ptr(Pfs), fs._ptr(nell), 0, fs._ptr(ws),
+                                    C.c_size_t(nbytes), None)
+    assert rc == 0
+    mss, Pss = torch.empty_like(mfs), torch.empty_like(Pfs)
+    rc = L.cgp_smoother_sweep_f64(C.byref(p), fs._ptr(mfs), fs._ptr(Pfs), fs._ptr(mss), fs._ptr(Pss), fs._ptr(ws),
+                                  C.c_size_t(nbytes), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(mfs, f[0]) and torch.equal(Pfs, f[1])
+    assert torch.equal(mss, s_ref[0]) and torch.equal(Pss, s_ref[1])
     for j in range(3):
         _close(f[j].cpu().numpy(), z['sgp_filter_cub_%d' % j], rtol=NLL_RT if j == 2 else RT, atol=1e-9 if j == 2 else AT_D8)
-    s_ref = cg.sgp_smoother(mc, sg, z['sgp_filter_cub_0'], z['sgp_filter_cub_1'], dt)
-    for j in range(2):
-        _close(s[j].cpu().numpy(), s_ref[j], atol=AT_D8)
 
 
 # ---------------------------------------------------------------------------------------- post-processing on the device
