@@ -377,6 +377,8 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': B_PER_GPU * T * 8,
                     'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D), 'steps': n_e2e,
                     'ms_per_step_wall_clock': ms_e2e_wall, 'ms_single_step_latency': ms_e2e_single,
+                    'd2h_gb_per_s': B_PER_GPU * T * 8 * (D + D * D) / (ms_e2e * 1e-3) / 1e9,
+                    'bound': 'PCIe device->host copy of the 503 MB result (kernels hidden behind the copy of the previous step)',
                     'what': 'pinned host ys -> cg.sgp_filter -> cg.sgp_smoother -> pinned host (mss, Pss); steps issued on '
                             'two alternating streams so the D2H copy of one step overlaps the filter of the next'},
             'gpu_launches': args.steps * 2,
