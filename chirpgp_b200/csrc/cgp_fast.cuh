@@ -367,13 +367,18 @@ __global__ void __launch_bounds__(32) gh_warp_filter_kernel(const CgpProblem p, 
 // cd_sgp_smoother (filters_smoothers.py:585-632) for ModelSDE<NH> with a Gauss-Hermite table: one warp per chirp, RK4
 // backwards in time.  rhs (:615-621): Gm = Pf^{-1} gamma (hoisted out of the 4 stages), (_m, _P) = cd_sgp_common(m, P),
 // dm = _m + Gm^T (m - mf),  dP = _P + Gm^T P + P Gm - 2 gamma.   Results go through a 32-step ring like the filter.
+// Everything that depends on the FILTERING result only -- the loads of (mf_k, Pf_k), chol(Pf_k) and the four solves of
+// Gm_k -- is taken off the sequential chain: once per 32-step block lane j does it for step j of the block (SIMD over
+// time) and leaves [mf | Gm] in shared memory, where the time loop picks it up as a broadcast read.
 template <int NH, int P>
 __global__ void __launch_bounds__(32) cd_ghs_warp_kernel(const CgpProblem p, const SmootherIO io) {
     using Rhs = GhRhsSDE<NH, P>;
     constexpr int D = Rhs::D, NS = NSym<D>::value, NA = Rhs::NA, DD = D * D, REC = D + DD;
+    constexpr int PROW = (((D + DD) / 2) % 2 == 1) ? D + DD : D + DD + 2;      // odd number of 16-byte units per row
     __shared__ double red[NA][33];
     __shared__ __align__(16) double res[(NA + 1) & ~1];
     __shared__ __align__(16) double ring[32][REC];
+    __shared__ __align__(16) double pre[32][PROW];                             // per step of the block: mf | Gm
     const int lane = threadIdx.x;
     const int64_t b = blockIdx.x;
     const int64_t T = p.T;
@@ -391,15 +396,32 @@ __global__ void __launch_bounds__(32) cd_ghs_warp_kernel(const CgpProblem p, con
     const double ndt = -p.dt;
     // walk backwards; ring slot s holds step t with (t & 31) == s; flush when a 32-aligned block is complete
     for (int64_t t = T - 2; t >= 0; t--) {
-        double mf[D], Pf[D][D], Lf[D][D], rinv[D], Gm[D][D];
-        load_vec<D>(io.mfs + (b * T + t) * D, mf);
-        load_mat<D>(io.Pfs + (b * T + t) * DD, Pf);
-        chol_lower_rsqrt<D>(Pf, Lf, rinv);
-        CGP_UNROLL for (int c = 0; c < D; c++) {       // Gm = Pf^{-1} gamma, column by column
-            double col[D];
-            CGP_UNROLL for (int i = 0; i < D; i++) col[i] = Qf[i][c];
-            chol_solve_vec_rinv<D>(Lf, rinv, col);
-            CGP_UNROLL for (int i = 0; i < D; i++) Gm[i][c] = col[i];
+        if (t == T - 2 || (t & 31) == 31) {            // first step of a 32-aligned block: lane j prepares step (t & ~31) + j
+            const int64_t tj = (t & ~(int64_t)31) + lane;
+            if (tj <= t) {
+                double mfj[D], Pf[D][D], Lf[D][D], rinv[D];
+                load_vec<D>(io.mfs + (b * T + tj) * D, mfj);
+                load_mat<D>(io.Pfs + (b * T + tj) * DD, Pf);
+                chol_lower_rsqrt<D>(Pf, Lf, rinv);
+                store_vec<D>(&pre[lane][0], mfj);
+                CGP_UNROLL for (int c = 0; c < D; c++) {       // Gm = Pf^{-1} gamma, column by column; stored as Gm^T rows
+                    double col[D];
+                    CGP_UNROLL for (int i = 0; i < D; i++) col[i] = Qf[i][c];
+                    chol_solve_vec_rinv<D>(Lf, rinv, col);
+                    store_vec<D>(&pre[lane][D + c * D], col);
+                }
+            }
+            __syncwarp();
+        }
+        double mf[D], Gm[D][D];
+        {
+            const double *row = &pre[t & 31][0];
+            load_vec<D>(row, mf);
+            CGP_UNROLL for (int c = 0; c < D; c++) {
+                double col[D];
+                load_vec<D>(row + D + c * D, col);
+                CGP_UNROLL for (int i = 0; i < D; i++) Gm[i][c] = col[i];
+            }
         }
         rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
             double _m[D], _P[NS], W[D][D];
@@ -700,15 +722,20 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
 }
 
 // cd_eks: rhs (filters_smoothers.py:427-432) gamma = b b^T, M = J_a(m) + (Pf^{-1} gamma)^T, dm = a(m) + gamma Pf^{-1} (m - mf),
-// dP = M P + P M^T - gamma.  chol(Pf) and Pf^{-1} gamma are formed once per step (replicated in the lanes).
+// dP = M P + P M^T - gamma.  X = Pf^{-1} gamma depends on the filtering result only: once per 16-step block lane j of the
+// half-warp loads (mf, Pf) of step j, factorises Pf and solves for X (SIMD over time), and the time loop reads [mf | X] back
+// from shared memory.  With gamma symmetric, gamma Pf^{-1} = X^T, so dm = a + X^T (m - mf): a 4 x 4 product on the chain instead
+// of the reference's two triangular solves per stage (same value up to rounding).
 template <int NH>
 __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, const SmootherIO io) {
     static_assert(NH == 1, "16 lanes per chirp need d == 4");
     using Model = ModelSDE<1>;
-    constexpr int D = 4, DD = 16;
+    constexpr int D = 4, DD = 16, PROW = 22;               // [mf (4) | X (16)] + pad: 11 x 16 bytes per row
+    __shared__ __align__(16) double pre[2][16][PROW];
     const int lane = threadIdx.x;
     const HalfWarp hw(lane);
-    const int64_t gid = (int64_t)blockIdx.x * 2 + (lane >> 4);
+    const int half = lane >> 4;
+    const int64_t gid = (int64_t)blockIdx.x * 2 + half;
     const bool active = gid < p.B;
     const int64_t b = active ? gid : p.B - 1;
     const int64_t T = p.T;
@@ -730,28 +757,35 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
     }
     const double ndt = -p.dt;
     for (int64_t t = T - 2; t >= 0; t--) {
-        double mf[D], Pf[D][D], Lf[D][D], rinv[D], xrow[D];
-        load_vec<D>(io.mfs + (b * T + t) * D, mf);
-        load_mat<D>(io.Pfs + (b * T + t) * DD, Pf);
-        chol_lower_rsqrt<D>(Pf, Lf, rinv);
-        {   // column i of X = Pf^{-1} gamma^T  ->  row i of X^T, the constant part of M's row i
-            double col[D];
-            CGP_UNROLL for (int q = 0; q < D; q++)
-                col[q] = hw.i == 0 ? Qf[q][0] : (hw.i == 1 ? Qf[q][1] : (hw.i == 2 ? Qf[q][2] : Qf[q][3]));
-            chol_solve_vec_rinv<D>(Lf, rinv, col);
-            CGP_UNROLL for (int q = 0; q < D; q++) xrow[q] = col[q];
+        if (t == T - 2 || (t & 15) == 15) {            // first step of a 16-aligned block: lane j prepares step (t & ~15) + j
+            const int64_t tj = (t & ~(int64_t)15) + hw.l;
+            if (tj <= t) {
+                double mfj[D], Pf[D][D], Lf[D][D], rinv[D];
+                load_vec<D>(io.mfs + (b * T + tj) * D, mfj);
+                load_mat<D>(io.Pfs + (b * T + tj) * DD, Pf);
+                chol_lower_rsqrt<D>(Pf, Lf, rinv);
+                store_vec<D>(&pre[half][hw.l][0], mfj);
+                CGP_UNROLL for (int c = 0; c < D; c++) {       // column c of X = Pf^{-1} gamma
+                    double col[D];
+                    CGP_UNROLL for (int q = 0; q < D; q++) col[q] = Qf[q][c];
+                    chol_solve_vec_rinv<D>(Lf, rinv, col);
+                    store_vec<D>(&pre[half][hw.l][D + c * D], col);
+                }
+            }
+            __syncwarp();
         }
+        double mf[D], xcol[D];                         // column i of X: row i of X^T = gamma Pf^{-1}, and the constant part of M's row i
+        load_vec<D>(&pre[half][t & 15][0], mf);
+        load_vec<D>(&pre[half][t & 15][D + hw.i * D], xcol);
         rk4_step_lane([&](const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
             double jr[D], a[D], z[D];
             chirp_drift_and_jrow(mdl, hw, mm, a, jr);
-            CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xrow[q];
+            CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
             CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
-            chol_solve_vec_rinv<D>(Lf, rinv, z);
-            CGP_UNROLL for (int r = 0; r < D; r++) {
-                double s = Qf[r][0] * z[0];
-                CGP_UNROLL for (int k = 1; k < D; k++) s = fma(Qf[r][k], z[k], s);
-                dm[r] = a[r] + s;
-            }
+            // dm_r = a_r + sum_k X_kr z_k: lane (i, .) forms component i with its column of X, the four are gathered
+            double di = xcol[0] * z[0];
+            CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
+            CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
             const double Y = row_times_P(hw, jr, PP);
             const double Yt = hw.get(Y, 4 * hw.j + hw.i);
             dP = (Y + Yt) - Qe;
