@@ -1058,13 +1058,12 @@ __global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, c
             Ds[r * D + c][tid] = fma(lj[r], evp[c], Ds[r * D + c][tid]);
     }
     // mp, Pp of the record; chol(Pp) into the registers the accumulators leave behind
-    CGP_UNROLL for (int r = 0; r < D; r++) rec[D * D + r] = am[r];
+    gstore_vec_auto<D>(rec + D * D, am);                  // whole 32-byte sectors where the record allows (cgp_device.cuh)
     double Lq[NS], rinv[D];
     {
         double Pps[NS];
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++) Pps[sidx(r, c)] = aP[sidx(r, c)] - am[r] * am[c];
-        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c += 2)
-            *reinterpret_cast<double2 *>(rec + D * D + D + r * D + c) = make_double2(Pps[sidx(r, c)], Pps[sidx(r, c + 1)]);
+        gstore_sym_auto<D>(rec + D * D + D, Pps);
         CGP_UNROLL for (int j = 0; j < D; j++) {             // chol_lower_sym_rsqrt, keeping 1 / L_jj
             double sacc = Pps[sidx(j, j)];
             CGP_UNROLL for (int k = 0; k < j; k++) sacc = fma(-Lq[sidx(j, k)], Lq[sidx(j, k)], sacc);
@@ -1092,7 +1091,7 @@ __global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, c
             CGP_UNROLL for (int k = i + 1; k < D; k++) sacc = fma(-Lq[sidx(k, i)], z[k], sacc);
             z[i] = sacc * rinv[i];
         }
-        CGP_UNROLL for (int c = 0; c < D; c += 2) *reinterpret_cast<double2 *>(rec + r * D + c) = make_double2(z[c], z[c + 1]);
+        gstore_vec_auto<D>(rec + r * D, z);
     }
 }
 
