@@ -394,6 +394,13 @@ def run_ours(args):
                               'flops_per_step': flops_per_step('sgp_filter'),
                               'peak_source': 'DFMA-only kernel measured in this run',
                               'whole_step_tflops': step_flops / (ms_step * 1e-3) / 1e12},
+            # neither of the two throughput rooflines binds at 1000 chirps per GPU: the kernel time is T x (cycles one
+            # producer warp needs per step); floor = the pure dependency latency of one step
+            'roofline_chain': {'bound': 'dependency-chain latency of one filter step', 'kernel': 'gh_duo_filter_kernel',
+                               'achieved_cycles_per_step': ms_filter * 1e-3 * (clocks.get('sm_mhz') or 1965.) * 1e6 / T,
+                               'floor_cycles_per_step': 840, 'scheduled_cycles_per_step': 1394,
+                               'frac': 840. / (ms_filter * 1e-3 * (clocks.get('sm_mhz') or 1965.) * 1e6 / T),
+                               'source': 'profiles/sass_dyn.py (static schedule), profiles/microbench/fp64_latency.cu'},
             'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
