@@ -158,6 +158,20 @@ int cgp_gaussian_expectation_softplus_f64(int64_t n, const double *ms, int64_t m
                                           int64_t sd_stride, int sd_is_variance, const double *w_host,
                                           const double *xi_host, int order, double *out, void *stream);
 
+/* ---- Monte-Carlo input side (tetralith/jobs/crlb_ekf.py:41-56, test/test_crlb.py:41-55, tools.py:81-170): B trajectories of
+ * a discretised model (CGP_MODEL_LINEAR_DISC or CGP_MODEL_LCD) and their measurements,
+ *   x_0 = m0 + chol(P0) eps,  x_k = mean(x_{k-1}) + chol(Sigma) eps_k,  y_k = H x_k + sqrt(Xi) eps'_k,   k = 1 .. T,
+ * with normals from the counter-based Philox4x32-10 generator (key = seed, counter = (draw, k, first_trajectory + b)) and
+ * Box-Muller in float64: trajectory i depends on (seed, i) only, whatever the batch split.  Outputs (device pointers, each may
+ * be NULL): x0 [B, d], xs [B, T, d], ys [B, T].  No bit parity with jax.random (threefry); oracle/sim_oracle.py restates the
+ * generator in NumPy. */
+int cgp_simulate_f64(const CgpProblem *p, uint64_t seed, uint64_t first_trajectory, double *x0, double *xs, double *ys,
+                     void *stream);
+/* test hooks: one Philox4x32-10 block (out_dev: 4 uint32 on the device); 2 n normals of a fixed counter pattern */
+int cgp_test_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out_dev,
+                    void *stream);
+int cgp_test_normals(uint64_t seed, int64_t n, double *out_dev, void *stream);
+
 /* ---- measurement utility: DFMA-only kernel (8 independent chains / thread) for the FP64 roofline denominator.
  * `out` holds blocks * 256 doubles.  Returns the flops issued (caller times the stream), < 0 on error. */
 double cgp_bench_dfma(double *out, int blocks, int iters, void *stream);
