@@ -486,3 +486,35 @@ def test_large_batch_onepass_eks_and_wide_stores():
     sk = cg.rts(F, Sigma, fk[0], fk[1])
     sko = orc.rts(F, Sigma, fk[0][pick], fk[1][pick])
     _check_smoother([x[pick] for x in sk], sko, ATOL_LONG)
+
+
+def test_full_size_config2_properties():
+    """BASELINE configs[1] at full size (1000 chirps x 3141 steps, GH order 3) through the path bench.py times, checked with
+    size-independent properties: fused (filter + gains, sweep) == stand-alone (filter, gain kernel + sweep) to rounding;
+    the last smoothed step is the last filtering step (filters_smoothers.py:140-142); covariances exactly symmetric;
+    smoothing never increases the marginal variances; a 16-chirp sample against the oracle."""
+    B, T, dt = 1000, 3141, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, T, dt, Xi=0.1, seed=2)
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    ys_d = _cuda(ys)
+    f = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, ys_d)
+    assert getattr(f[0], '_cgp_smoother_gains', None) is not None
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    f2 = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, ys_d, smoother_gains=False)
+    s2 = cg.sgp_smoother(mc, sg, f2[0], f2[1], dt)
+    for a, b in zip(f + s, f2 + s2):
+        assert torch.isfinite(a).all()
+        _close(a.cpu().numpy(), b.cpu().numpy(), atol=ATOL_LONG)
+    assert torch.equal(s[0][:, -1], f[0][:, -1]) and torch.equal(s[1][:, -1], f[1][:, -1])
+    assert torch.equal(f[1], f[1].transpose(-1, -2))                       # packed-symmetric arithmetic: exact
+    sym = (s[1] - s[1].transpose(-1, -2)).abs().max().item()
+    assert sym < 1e-12, sym
+    dvar = (torch.diagonal(s[1], dim1=-2, dim2=-1) - torch.diagonal(f[1], dim1=-2, dim2=-1)).max().item()
+    assert dvar < 1e-9, dvar
+    assert (f[2][:, 1:] - f[2][:, :-1]).min().item() > -20.              # cumulative nll: increments are -log N(y; ., S) >= -log-peak
+    pick = np.arange(0, B, 64)
+    fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys[pick])
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_filter([x[pick].cpu().numpy() for x in f], fo, ATOL_LONG)
+    _check_smoother([x[pick].cpu().numpy() for x in s], so, ATOL_LONG)
