@@ -6,7 +6,8 @@ from .filters_smoothers import (kf, rts, ekf, eks, cd_ekf, cd_eks, sgp_filter, s
                                 cd_sgp_smoother, ekf_for_kpt)
 from .models import (g, g_inv, model_chirp, model_harmonic_chirp, model_lascala, disc_chirp_lcd,  # noqa: F401
                      disc_harmonic_chirp_lcd, disc_model_lascala_lcd, disc_m32, build_chirp_model,
-                     build_harmonic_chirp_model, build_lascala_model, build_kpt_chirp_model, LinearDisc, LinearSDE)
+                     build_harmonic_chirp_model, build_lascala_model, build_kpt_chirp_model, posterior_cramer_rao,
+                     LinearDisc, LinearSDE)
 from .quadratures import SigmaPoints, gaussian_expectation  # noqa: F401
 from .toymodels import (gen_chirp, gen_harmonic_chirp, constant_mag, damped_exp_mag, random_ou_mag,  # noqa: F401
                         affine_freq, polynomial_freq, meow_freq)

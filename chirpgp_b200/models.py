@@ -25,7 +25,8 @@ import torch
 
 __all__ = ['g', 'g_inv', 'model_chirp', 'model_harmonic_chirp', 'model_lascala', 'disc_chirp_lcd',
            'disc_harmonic_chirp_lcd', 'disc_model_lascala_lcd', 'disc_m32', 'build_chirp_model',
-           'build_harmonic_chirp_model', 'build_lascala_model', 'build_kpt_chirp_model', 'LinearDisc', 'LinearSDE',
+           'build_harmonic_chirp_model', 'build_lascala_model', 'build_kpt_chirp_model', 'posterior_cramer_rao', 'LinearDisc',
+           'LinearSDE',
            'LCDModel', 'SDEDrift', 'Dispersion', 'KPTMeasurement',
            'MODEL_LINEAR_DISC', 'MODEL_LCD', 'MODEL_LINEAR_SDE', 'MODEL_SDE', 'MODEL_KPT', 'NC_LCD', 'NC_SDE']
 
@@ -371,3 +372,30 @@ def build_kpt_chirp_model(params, fs: float, num_harmonics: int = 1):
     diag = torch.stack([(2 * math.pi * q1 / fs) ** 2] + [q2] * num_harmonics + [torch.zeros_like(q2)], dim=-1)
     Sigma = torch.diag_embed(diag)
     return F, Sigma, m0, P0, KPTMeasurement(num_harmonics)
+
+
+def posterior_cramer_rao(xss, yss, j0, logpdf_transition, logpdf_likelihood):
+    """Posterior Cramer--Rao lower bound by Monte Carlo (models.py:583-644; Tichavsky et al. 1998), for 1-d measurements.
+
+    xss (T + 1, N, d) state trajectories (initial samples first), yss (T, N) measurements, j0 (d, d) = -E[Hess log p(x0)],
+    ``logpdf_transition(xt, xs)`` and ``logpdf_likelihood(yt, xt)`` scalar-valued callables written with torch operations.
+    Returns J (T, d, d), the inverses of the bound matrices.
+
+    Analysis tool next to the hot path, not a kernel: the reference takes the Hessians with jax.hessian / jacfwd / jacrev under
+    vmap (:631-634); this is the same recursion (:636-646) with ``torch.func`` doing the differentiation on whatever device
+    the samples live on (``chirpgp_b200.tools.simulate`` leaves them on the GPU)."""
+    from torch.func import hessian, jacfwd, jacrev, vmap
+    xss, yss, j = _t(xss), _t(yss), _t(j0)
+    htt_tr = vmap(hessian(logpdf_transition, argnums=0))
+    hts_tr = vmap(jacfwd(jacrev(logpdf_transition, argnums=1), argnums=0))
+    hss_tr = vmap(hessian(logpdf_transition, argnums=1))
+    htt_li = vmap(hessian(logpdf_likelihood, argnums=1))
+    js = []
+    for k in range(yss.shape[0]):
+        yt, xt, xs = yss[k], xss[k + 1], xss[k]
+        d11 = -hss_tr(xt, xs).mean(0)
+        d12 = -hts_tr(xt, xs).mean(0)
+        d22 = -(htt_tr(xt, xs) + htt_li(yt, xt)).mean(0)
+        j = d22 - d12.transpose(-1, -2) @ torch.linalg.solve(j + d11, d12)
+        js.append(j)
+    return torch.stack(js)

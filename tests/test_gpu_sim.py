@@ -65,7 +65,7 @@ def test_simulated_trajectories_match_the_restatement():
 def test_crlb_lgssm_monte_carlo():
     """test/test_crlb.py:19-73 on the CUDA path: 10^6 simulated trajectories of the Matern-3/2 LGSSM, batched kf;
     covariances bit-identical across the batch (:64-66) and the Monte-Carlo error covariance ~ Pf (atol 1e-1, :71-73).
-    (The PCRLB recursion itself, models.py:583-644, is not part of this build.)"""
+    and inv(PCRLB) == Pf (atol 1e-12, :75-87) with posterior_cramer_rao (models.py:583-644)."""
     ell, sigma, dt, T = 1., 1., 0.1, 10
     A = np.array([[0., 1.], [-3 / ell ** 2, -2 * math.sqrt(3) / ell]])
     Bv = np.array([[0.], [2 * sigma * (math.sqrt(3) / ell) ** 1.5]])
@@ -86,3 +86,20 @@ def test_crlb_lgssm_monte_carlo():
     npt.assert_allclose(Emc.cpu().numpy(), Pfs[0].cpu().numpy(), rtol=2e-2, atol=2e-3)     # what 10^6 samples actually give
     # x0 ~ N(m0, P0)
     npt.assert_allclose(np.cov(x0.cpu().numpy().T), P0, atol=2e-2)
+    # :75-87: the PCRLB of the linear Gaussian model is the Kalman covariance
+    Ft, St, Ht = torch.as_tensor(F).cuda(), torch.as_tensor(Sigma).cuda(), torch.as_tensor(H).cuda()
+    Sinv = torch.linalg.inv(St)
+    logdet = torch.logdet(St)
+
+    def logpdf_transition(xt, xs):
+        r = xt - Ft @ xs
+        return -0.5 * (r @ Sinv @ r) - 0.5 * logdet - math.log(2 * math.pi)
+
+    def logpdf_likelihood(yt, xt):
+        return -0.5 * (yt - Ht @ xt) ** 2 / Xi - 0.5 * math.log(2 * math.pi * Xi)
+
+    n = 2000                                                   # the Hessians are constant for this model: no MC noise
+    xss = torch.cat([x0[:n, None], xs[:n]], dim=1).transpose(0, 1).contiguous()
+    js = cg.posterior_cramer_rao(xss, ys[:n].T.contiguous(), torch.linalg.inv(torch.as_tensor(P0).cuda()),
+                                 logpdf_transition, logpdf_likelihood)
+    npt.assert_allclose(torch.linalg.inv(js).cpu().numpy(), Pfs[0].cpu().numpy(), atol=1e-12)
