@@ -37,7 +37,7 @@ METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
 UNIT = 'steps/s'
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one gh_duo_filter_kernel launch (ncu --set full, profiles/r1_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 1_402_062_456    # 26.1 MB read + 1375.9 MB written: 552.8 MB algorithmic + 904.6 MB smoother workspace
+NCU_TRAFFIC_BYTES = 1_401_431_000    # 26.7 MB read + 1374.8 MB written: 552.8 MB algorithmic + 904.6 MB smoother workspace
 
 # algorithmic bytes / flops per chirp time-step (DESIGN.md "Roofline accounting")
 BYTES_FILTER = 8 + 8 * (D + D * D + 1)          # ys in, mf + Pf + nell out                      = 176
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -229,7 +229,6 @@ def run_ours(args):
         marks.append((e0, e1, e2))
         del f, s
     barrier()
-    clocks = sampler.stop()
     t_filter = [a.elapsed_time(b) for a, b, _ in marks]
     t_step = [a.elapsed_time(c) for a, _, c in marks]
     ms_step = statistics.mean(t_step)
@@ -298,6 +297,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     ms_e2e = e0.elapsed_time(e1) / n_e2e
     ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_e2e
+    clocks = sampler.stop()              # sampled through the three timed regions (serial, two-stream, end-to-end)
     # single-step latency (one stream, no overlap) for reference; first pass warms the default stream's allocator pool
     for _ in range(2):
         flush.fill_(1.)
