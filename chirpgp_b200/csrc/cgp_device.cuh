@@ -196,6 +196,33 @@ template <int D> CGP_DEV void matvec(const double (&A)[D][D], const double (&x)[
     }
 }
 
+// Products with the Jacobian J of a model mean that skip its structural zeros (Model::jnz) at compile time.  The terms
+// are taken in the same order as the dense loops, so for finite operands the results are bit-identical (a skipped term
+// is an exact zero); d = 4 chirp model: 10 of 16 entries are non-zero.
+#define CGP_JSUM(nzexpr, aexpr, bexpr)                                                            \
+    double sacc = 0.; bool first = true;                                                          \
+    CGP_UNROLL for (int k = 0; k < D; k++)                                                        \
+        if (nzexpr) { sacc = first ? (aexpr) * (bexpr) : fma((aexpr), (bexpr), sacc); first = false; }
+template <class Model, int D> CGP_DEV void jmul(const double (&J)[D][D], const double (&Bm)[D][D], double (&Cm)[D][D]) {          // J B
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) { CGP_JSUM(Model::jnz(i, k), J[i][k], Bm[k][j]) Cm[i][j] = sacc; }
+}
+template <class Model, int D> CGP_DEV void jmul_nt(const double (&J)[D][D], const double (&Bm)[D][D], double (&Cm)[D][D]) {       // J B^T
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) { CGP_JSUM(Model::jnz(i, k), J[i][k], Bm[j][k]) Cm[i][j] = sacc; }
+}
+template <class Model, int D> CGP_DEV void mul_jt(const double (&A)[D][D], const double (&J)[D][D], double (&Cm)[D][D]) {         // A J^T
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) { CGP_JSUM(Model::jnz(j, k), A[i][k], J[j][k]) Cm[i][j] = sacc; }
+}
+template <class Model, int D> CGP_DEV void mul_j(const double (&A)[D][D], const double (&J)[D][D], double (&Cm)[D][D]) {          // A J
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) { CGP_JSUM(Model::jnz(k, j), A[i][k], J[k][j]) Cm[i][j] = sacc; }
+}
+template <class Model, int D> CGP_DEV void jtmul(const double (&J)[D][D], const double (&Bm)[D][D], double (&Cm)[D][D]) {         // J^T B
+    CGP_UNROLL for (int i = 0; i < D; i++) CGP_UNROLL for (int j = 0; j < D; j++) { CGP_JSUM(Model::jnz(k, i), J[k][i], Bm[k][j]) Cm[i][j] = sacc; }
+}
+template <class Model, int D> CGP_DEV void jtvec(const double (&J)[D][D], const double (&x)[D], double (&y)[D]) {                 // J^T x
+    CGP_UNROLL for (int i = 0; i < D; i++) { CGP_JSUM(Model::jnz(k, i), J[k][i], x[k]) y[i] = sacc; }
+}
+#undef CGP_JSUM
+
 // lower Cholesky of a full matrix, reading its lower triangle only.  L full (upper part left untouched = 0
 // must be provided by the caller if needed; only the lower triangle is ever read afterwards).
 template <int D> CGP_DEV void chol_lower(const double (&P)[D][D], double (&L)[D][D]) {
@@ -432,6 +459,7 @@ template <int D_> struct ModelLinearDisc {
         }
     }
     static CGP_DEV constexpr bool has_sig(int, int) { return true; }
+    static CGP_DEV constexpr bool jnz(int, int) { return true; }        // Jacobian of the mean: dense
     CGP_DEV double sig(int r, int c) const { return Sg[r][c]; }
     CGP_DEV Trig prep(const double (&)[D]) const { return Trig{}; }
     CGP_DEV void mean_with(const Trig &, const double (&u)[D], double (&m)[D]) const { matvec<D>(F, u, m); }
@@ -458,6 +486,10 @@ template <int NH_> struct ModelLCD {
     }
     static CGP_DEV constexpr bool has_sig(int r, int c) {
         return (r == c) || (r == V && c == V + 1) || (r == V + 1 && c == V);
+    }
+    // structural non-zeros of the Jacobian of the mean (mean_jac): the 2 x 2 rotation blocks, their column V, the Matern block
+    static CGP_DEV constexpr bool jnz(int r, int c) {
+        return r < V ? ((r / 2 == c / 2) || c == V) : (c >= V);
     }
     CGP_DEV double sig(int r, int c) const {
         if (r == c) return r < V ? q : (r == V ? s00 : s11);

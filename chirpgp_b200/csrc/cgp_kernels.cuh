@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(128) ekf_thread_kernel(const CgpProblem p, con
         if (t + 1 < T) ynext = __ldg(y + t + 1);
         double mp[D], J[D][D], JP[D][D], Pp[D][D];
         mdl.mean_jac(m, mp, J);                       // :255-256
-        matmul<D>(J, P, JP);
-        matmul_nt<D>(JP, J, Pp);                      // :257
+        jmul<Model, D>(J, P, JP);
+        mul_jt<Model, D>(JP, J, Pp);                  // :257
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
             if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
         acc = acc + linear_update<D>(mp, Pp, H, p.Xi, yt, m, P);
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const CgpProblem p, const
     load_mat<D>(io.Pfs + (b * p.T + t) * (D * D), Pf);
     double mp[D], J[D][D], DT[D][D], Pp[D][D];
     mdl.mean_jac(mf, mp, J);                          // :342-343
-    matmul<D>(J, Pf, DT);                             // DT = J Pf (:345)
-    matmul_nt<D>(DT, J, Pp);                          // :344
+    jmul<Model, D>(J, Pf, DT);                        // DT = J Pf (:345)
+    mul_jt<Model, D>(DT, J, Pp);                      // :344
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
         if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
     gain_and_store<D>(DT, mp, Pp, io.ws + (b * p.T + t) * ws_record<D>());
@@ -566,8 +566,8 @@ __global__ void __launch_bounds__(128) eks_onepass_thread_kernel(const CgpProble
         }
         double mp[D], J[D][D], DT[D][D], Pp[D][D];
         mdl.mean_jac(mf, mp, J);                          // :342-343
-        matmul<D>(J, Pf, DT);                             // DT = J Pf (:345)
-        matmul_nt<D>(DT, J, Pp);                          // :344
+        jmul<Model, D>(J, Pf, DT);                        // DT = J Pf (:345)
+        mul_jt<Model, D>(DT, J, Pp);                      // :344
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
             if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
         double L[D][D], rinv[D], Gm[D][D];

@@ -47,8 +47,8 @@ CGP_DEV double ekf_step(const Model &mdl, const double (&H)[Model::D], double Xi
     constexpr int D = Model::D;
     double mp[D], J[D][D], JP[D][D], Pp[D][D];
     mdl.mean_jac(m, mp, J);
-    matmul<D>(J, P, JP);
-    matmul_nt<D>(JP, J, Pp);
+    jmul<Model, D>(J, P, JP);
+    mul_jt<Model, D>(JP, J, Pp);
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
         if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
     return linear_update<D>(mp, Pp, H, Xi, y, m, P);
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(128) ekf_nll_bwd_kernel(const CgpProblem p, co
             // ---- recompute the forward quantities of this step
             double mp[D], J[D][D], JP[D][D], Pp[D][D];
             mdl.mean_jac(m, mp, J);
-            matmul<D>(J, P, JP);
-            matmul_nt<D>(JP, J, Pp);
+            jmul<Model, D>(J, P, JP);
+            mul_jt<Model, D>(JP, J, Pp);
             CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
                 if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
             double cv[D], S = 0., pred = 0.;
@@ -163,23 +163,15 @@ __global__ void __launch_bounds__(128) ekf_nll_bwd_kernel(const CgpProblem p, co
             CGP_UNROLL for (int r = 0; r < V; r++) qb += Ppb[r][r];
             sb00 += Ppb[V][V]; sb01 += Ppb[V][V + 1] + Ppb[V + 1][V]; sb11 += Ppb[V + 1][V + 1];
             double JPt[D][D], Jb[D][D], T1[D][D];
-            matmul_nt<D>(J, P, JPt);                                   // J P^T
+            jmul_nt<Model, D>(J, P, JPt);                              // J P^T
             CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) {
                 double s = 0.;
                 CGP_UNROLL for (int k = 0; k < D; k++) s = fma(Ppb[r][k], JPt[k][c], fma(Ppb[k][r], JP[k][c], s));
                 Jb[r][c] = s;                                          // Ppb J P^T + Ppb^T J P
             }
-            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) {   // T1 = J^T Ppb
-                double s = 0.;
-                CGP_UNROLL for (int k = 0; k < D; k++) s = fma(J[k][r], Ppb[k][c], s);
-                T1[r][c] = s;
-            }
-            matmul<D>(T1, J, Pb);                                      // Pb <- J^T Ppb J
-            CGP_UNROLL for (int r = 0; r < D; r++) {                   // mb <- J^T mpb (+ second-order terms below)
-                double s = 0.;
-                CGP_UNROLL for (int k = 0; k < D; k++) s = fma(J[k][r], mpb[k], s);
-                mb[r] = s;
-            }
+            jtmul<Model, D>(J, Ppb, T1);                               // T1 = J^T Ppb
+            mul_j<Model, D>(T1, J, Pb);                                // Pb <- J^T Ppb J
+            jtvec<Model, D>(J, mpb, mb);                               // mb <- J^T mpb (+ second-order terms below)
             // model-specific part: second derivatives of the mean and cotangents of the constants
             double gv, sg;
             softplus_and_sigmoid(m[V], gv, sg);
