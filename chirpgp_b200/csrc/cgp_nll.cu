@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) ekf_nll_fwd_kernel(const CgpProblem p, co
 }
 
 template <int NH>
-__global__ void __launch_bounds__(128) ekf_nll_bwd_kernel(const CgpProblem p, const double *__restrict__ ys,
+__global__ void __launch_bounds__(128, NH == 1 ? 3 : 1) ekf_nll_bwd_kernel(const CgpProblem p, const double *__restrict__ ys,
                                                           const double *__restrict__ nll_bar, const double *__restrict__ ckpt,
                                                           double *__restrict__ scratch, int64_t ckpt_every,
                                                           double *__restrict__ consts_bar, double *__restrict__ m0_bar,
