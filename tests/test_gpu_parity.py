@@ -550,3 +550,30 @@ def test_fused_kernel_is_deterministic_under_load():
                 assert torch.equal(a, b)
     # chirps 0..999 and 1000..1999 see the same measurements: identical results whatever CTA / SM they ran on
     assert torch.equal(ref[0][:1000], ref[0][1000:2000]) and torch.equal(ref[4][:1000], ref[4][1000:2000])
+
+
+def test_general_measurement_row_and_nan_inputs_on_the_fused_path(batch):
+    """H that is not a unit vector takes the general-H instantiations of the tuned kernels (plain and fused); a NaN
+    measurement poisons that chirp only and nothing hangs (the producer / consumer hand-over is data independent)."""
+    B, T, dt, ys = batch
+    ys = ys[:6, :200].copy()
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    Hg = np.array([0.3, 1.0, 0., 0.1])
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    fo = orc.sgp_filter(spec, sg, Hg, 0.1, m0, P0, dt, ys)
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    f = cg.sgp_filter(mc, sg, Hg, 0.1, m0, P0, dt, ys)                           # NumPy in: plain kernel
+    _check_filter(f, fo, ATOL_LONG)
+    fd = cg.sgp_filter(mc, sg, _cuda(Hg), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))      # fused kernel
+    assert getattr(fd[0], '_cgp_smoother_gains', None) is not None
+    sd = cg.sgp_smoother(mc, sg, fd[0], fd[1], dt)
+    _check_filter([x.cpu().numpy() for x in fd], fo, ATOL_LONG)
+    _check_smoother([x.cpu().numpy() for x in sd], so, ATOL_LONG)
+    ys[2, 50] = np.nan
+    fn = cg.sgp_filter(mc, sg, _cuda(Hg), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
+    sn = cg.sgp_smoother(mc, sg, fn[0], fn[1], dt)
+    torch.cuda.synchronize()
+    assert torch.isnan(fn[0][2, 50:]).all() and torch.isfinite(fn[0][2, :50]).all()
+    assert torch.isnan(sn[0][2]).all()                                           # the backward sweep starts from NaN
+    keep = [0, 1, 3, 4, 5]
+    assert torch.equal(fn[0][keep], fd[0][keep]) and torch.equal(sn[1][keep], sd[1][keep])
