@@ -56,7 +56,8 @@ CGP_DEV double ekf_step(const Model &mdl, const double (&H)[Model::D], double Xi
 
 template <int NH>
 __global__ void __launch_bounds__(128) ekf_nll_fwd_kernel(const CgpProblem p, const double *__restrict__ ys, double *__restrict__ nll,
-                                                          double *__restrict__ ckpt, int64_t ckpt_every) {
+                                                          double *__restrict__ ckpt, int64_t ckpt_every,
+                                                          double *__restrict__ nell_path /* [B, T] cumulative, or NULL */) {
     using Model = ModelLCD<NH>;
     constexpr int D = Model::D, REC = NllLayout<D>::REC;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,6 +71,8 @@ __global__ void __launch_bounds__(128) ekf_nll_fwd_kernel(const CgpProblem p, co
     const double *__restrict__ y = ys + (b / p.ys_repeat) * p.T;
     double acc = 0.;
     int64_t seg = 0, left = 0;
+    NellRowWriter pathw;
+    if (nell_path) pathw.init(nell_path, b, p.T);
     for (int64_t t = 0; t < p.T; t++) {
         if (left == 0) {
             if (ckpt) save_state<D>(ckpt + seg * REC * p.B, p.B, b, m, P);
@@ -78,13 +81,16 @@ __global__ void __launch_bounds__(128) ekf_nll_fwd_kernel(const CgpProblem p, co
         }
         left--;
         acc = acc + ekf_step<Model>(mdl, H, p.Xi, __ldg(y + t), m, P);
+        if (nell_path) pathw.put(t, p.T, acc);
     }
-    nll[b] = acc;
+    if (nll) nll[b] = acc;
 }
 
 template <int NH>
 __global__ void __launch_bounds__(128, NH == 1 ? 3 : 1) ekf_nll_bwd_kernel(const CgpProblem p, const double *__restrict__ ys,
-                                                          const double *__restrict__ nll_bar, const double *__restrict__ ckpt,
+                                                          const double *__restrict__ nll_bar,
+                                                          const double *__restrict__ step_w /* [B, T] weight of every increment, or NULL */,
+                                                          const double *__restrict__ ckpt,
                                                           double *__restrict__ scratch, int64_t ckpt_every,
                                                           double *__restrict__ consts_bar, double *__restrict__ m0_bar,
                                                           double *__restrict__ P0_bar, double *__restrict__ Xi_bar) {
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(128, NH == 1 ? 3 : 1) ekf_nll_bwd_kernel(const
     double H[D];
     CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
     const double *__restrict__ y = ys + (b / p.ys_repeat) * T;
-    const double lw = nll_bar ? nll_bar[b] : 1.;
+    const double lw_all = nll_bar ? nll_bar[b] : (step_w ? 0. : 1.);
     const double Xi = p.Xi;
     double mb[D], Pb[D][D];
     CGP_UNROLL for (int i = 0; i < D; i++) mb[i] = 0.;
@@ -120,6 +126,7 @@ __global__ void __launch_bounds__(128, NH == 1 ? 3 : 1) ekf_nll_bwd_kernel(const
             double m[D], P[D][D];
             load_state<D>(scratch + (int64_t)j * REC * B, B, b, m, P);
             const double yt = __ldg(y + t0 + j);
+            const double lw = step_w ? lw_all + __ldg(step_w + b * T + t0 + j) : lw_all;     // dL / d(increment of this step)
             // ---- recompute the forward quantities of this step
             double mp[D], J[D][D], JP[D][D], Pp[D][D];
             mdl.mean_jac(m, mp, J);
@@ -229,9 +236,9 @@ size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every) {
     return (ckpt_doubles(*p, ckpt_every) + scratch_doubles(*p, ckpt_every)) * sizeof(double);
 }
 
-int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void *workspace, size_t ws_bytes,
-                        int64_t ckpt_every, void *stream) {
-    if (!p || !ys || !nll || p->B < 1 || p->T < 1 || !p->consts || !p->m0 || !p->P0 || !p->H || p->ys_repeat < 1)
+static int nll_fwd(const CgpProblem *p, const double *ys, double *nll, double *nell_path, void *workspace, size_t ws_bytes,
+                   int64_t ckpt_every, void *stream) {
+    if (!p || !ys || (!nll && !nell_path) || p->B < 1 || p->T < 1 || !p->consts || !p->m0 || !p->P0 || !p->H || p->ys_repeat < 1)
         return CGP_ERR_BAD_ARG;
     if (p->model != CGP_MODEL_LCD || p->d != 2 * p->num_harmonics + 2) return CGP_ERR_UNSUPPORTED;
     double *ckpt = nullptr;
@@ -246,16 +253,26 @@ int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void
     const unsigned grid = (unsigned)ceil_div(p->B, block);
     cudaStream_t s = (cudaStream_t)stream;
     switch (p->num_harmonics) {
-        case 1: ekf_nll_fwd_kernel<1><<<grid, block, 0, s>>>(*p, ys, nll, ckpt, ckpt_every); break;
-        case 2: ekf_nll_fwd_kernel<2><<<grid, block, 0, s>>>(*p, ys, nll, ckpt, ckpt_every); break;
-        case 3: ekf_nll_fwd_kernel<3><<<grid, block, 0, s>>>(*p, ys, nll, ckpt, ckpt_every); break;
+        case 1: ekf_nll_fwd_kernel<1><<<grid, block, 0, s>>>(*p, ys, nll, ckpt, ckpt_every, nell_path); break;
+        case 2: ekf_nll_fwd_kernel<2><<<grid, block, 0, s>>>(*p, ys, nll, ckpt, ckpt_every, nell_path); break;
+        case 3: ekf_nll_fwd_kernel<3><<<grid, block, 0, s>>>(*p, ys, nll, ckpt, ckpt_every, nell_path); break;
         default: return CGP_ERR_UNSUPPORTED;
     }
     return check_launch();
 }
 
-int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace, size_t ws_bytes,
-                        int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar, void *stream) {
+int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void *workspace, size_t ws_bytes,
+                        int64_t ckpt_every, void *stream) {
+    return nll_fwd(p, ys, nll, nullptr, workspace, ws_bytes, ckpt_every, stream);
+}
+int cgp_ekf_nll_path_fwd_f64(const CgpProblem *p, const double *ys, double *nell, void *workspace, size_t ws_bytes,
+                             int64_t ckpt_every, void *stream) {
+    return nll_fwd(p, ys, nullptr, nell, workspace, ws_bytes, ckpt_every, stream);
+}
+
+static int nll_bwd(const CgpProblem *p, const double *ys, const double *nll_bar, const double *step_w, void *workspace,
+                   size_t ws_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar,
+                   void *stream) {
     if (!p || !ys || !workspace || !consts_bar || !m0_bar || !P0_bar || p->B < 1 || p->T < 1 || ckpt_every < 1 ||
         !p->consts || !p->H || p->ys_repeat < 1)
         return CGP_ERR_BAD_ARG;
@@ -267,12 +284,22 @@ int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll
     const unsigned grid = (unsigned)ceil_div(p->B, block);
     cudaStream_t s = (cudaStream_t)stream;
     switch (p->num_harmonics) {
-        case 1: ekf_nll_bwd_kernel<1><<<grid, block, 0, s>>>(*p, ys, nll_bar, ckpt, scratch, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar); break;
-        case 2: ekf_nll_bwd_kernel<2><<<grid, block, 0, s>>>(*p, ys, nll_bar, ckpt, scratch, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar); break;
-        case 3: ekf_nll_bwd_kernel<3><<<grid, block, 0, s>>>(*p, ys, nll_bar, ckpt, scratch, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar); break;
+        case 1: ekf_nll_bwd_kernel<1><<<grid, block, 0, s>>>(*p, ys, nll_bar, step_w, ckpt, scratch, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar); break;
+        case 2: ekf_nll_bwd_kernel<2><<<grid, block, 0, s>>>(*p, ys, nll_bar, step_w, ckpt, scratch, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar); break;
+        case 3: ekf_nll_bwd_kernel<3><<<grid, block, 0, s>>>(*p, ys, nll_bar, step_w, ckpt, scratch, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar); break;
         default: return CGP_ERR_UNSUPPORTED;
     }
     return check_launch();
+}
+int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace, size_t ws_bytes,
+                        int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar, void *stream) {
+    return nll_bwd(p, ys, nll_bar, nullptr, workspace, ws_bytes, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar, stream);
+}
+int cgp_ekf_nll_path_bwd_f64(const CgpProblem *p, const double *ys, const double *step_weights, void *workspace,
+                             size_t ws_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,
+                             double *Xi_bar, void *stream) {
+    if (!step_weights) return CGP_ERR_BAD_ARG;
+    return nll_bwd(p, ys, nullptr, step_weights, workspace, ws_bytes, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar, stream);
 }
 
 }  // extern "C"

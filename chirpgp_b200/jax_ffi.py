@@ -91,7 +91,9 @@ def smoother_call(fn, model, consts, mfs, Pfs, dt, Qc=None, sig=None, num_harmon
 
 def make_ekf_nll(num_harmonics: int, Xi: float, dt: float, T: int, h_unit_index: int = 1):
     """Returns nll(consts (B,NC), m0 (B,d), P0 (B,d,d), H (d,), ys (B,T)) -> (B,) with a custom VJP that launches the
-    adjoint kernel.  Cotangents for (consts, m0, P0); zeros for H, ys (constants in every caller of the reference)."""
+    adjoint kernel.  (For a cotangent on the whole n_ell (T,) output bind cgp_ekf_nll_path_{fwd,bwd}_f64 the same way: the
+    backward rule passes the reversed cumulative sum of the cotangent as step weights; chirpgp_b200.mle._EkfNllPath is the
+    tested torch version.)  Cotangents for (consts, m0, P0); zeros for H, ys (constants in every caller of the reference)."""
     _register()
     d = 2 * num_harmonics + 2
     every = max(1, int(round(T ** 0.5)))

@@ -21,7 +21,7 @@ from . import _native as N
 from .filters_smoothers import _device, _problem, _ptr, _h_unit_index
 from .models import LCDModel, NC_LCD
 
-__all__ = ['ekf_nll', 'filter_nll', 'fit_mle']
+__all__ = ['ekf_nll', 'ekf_nll_path', 'filter_nll', 'fit_mle']
 
 _F64 = torch.float64
 
@@ -73,6 +73,54 @@ class _EkfNll(torch.autograd.Function):
         return cb, mb, Pb, xb.sum(), None, None, None, None, None, None, None
 
 
+class _EkfNllPath(torch.autograd.Function):
+    """As _EkfNll, but the output is the whole cumulative n_ell [B, T] (filters_smoothers.py:180-184) and the backward pass
+    takes an arbitrary cotangent on it: the weight of step k's increment is sum_{j >= k} ct_j."""
+
+    @staticmethod
+    def forward(ctx, consts, m0, P0, Xi, ys, H, dt, nh, ys_repeat, h_unit, ckpt_every):
+        L = N.lib()
+        dev = consts.device
+        B, d = m0.shape
+        T = ys.shape[-1]
+        p = _problem(B, T, N.CGP_MODEL_LCD, d, nh, consts, NC_LCD, m0, d, P0, d * d, H, None, 0, None, float(Xi), dt,
+                     ys_repeat, h_unit)
+        need_grad = any(ctx.needs_input_grad[:4])
+        every = int(ckpt_every or L.cgp_ekf_nll_default_ckpt(T))
+        ws, nbytes = None, 0
+        if need_grad:
+            nbytes = L.cgp_ekf_nll_workspace_bytes(C.byref(p), every)
+            ws = torch.empty((nbytes // 8,), dtype=_F64, device=dev)
+        nell = torch.empty((B, T), dtype=_F64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = L.cgp_ekf_nll_path_fwd_f64(C.byref(p), _ptr(ys), _ptr(nell), _ptr(ws), C.c_size_t(nbytes), every, stream)
+        N.check(rc, 'ekf_nll_path')
+        ctx.save_for_backward(consts, m0, P0, Xi, ys, H)
+        ctx.ws, ctx.meta = ws, (dt, nh, ys_repeat, h_unit, every, nbytes)
+        return nell
+
+    @staticmethod
+    def backward(ctx, nell_bar):
+        consts, m0, P0, Xi, ys, H = ctx.saved_tensors
+        dt, nh, ys_repeat, h_unit, every, nbytes = ctx.meta
+        L = N.lib()
+        dev = consts.device
+        B, d = m0.shape
+        T = ys.shape[-1]
+        p = _problem(B, T, N.CGP_MODEL_LCD, d, nh, consts, NC_LCD, m0, d, P0, d * d, H, None, 0, None, float(Xi), dt,
+                     ys_repeat, h_unit)
+        cb = torch.empty((B, NC_LCD), dtype=_F64, device=dev)
+        mb = torch.empty((B, d), dtype=_F64, device=dev)
+        Pb = torch.empty((B, d, d), dtype=_F64, device=dev)
+        xb = torch.empty((B,), dtype=_F64, device=dev)
+        w = torch.flip(torch.cumsum(torch.flip(nell_bar, dims=(-1,)), dim=-1), dims=(-1,)).contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = L.cgp_ekf_nll_path_bwd_f64(C.byref(p), _ptr(ys), _ptr(w), _ptr(ctx.ws), C.c_size_t(nbytes), every, _ptr(cb),
+                                        _ptr(mb), _ptr(Pb), _ptr(xb), stream)
+        N.check(rc, 'ekf_nll_path backward')
+        return cb, mb, Pb, xb.sum(), None, None, None, None, None, None, None
+
+
 def _as_dev(x, dev):
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=_F64)
@@ -80,11 +128,13 @@ def _as_dev(x, dev):
 
 
 def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = False,
-            ckpt_every: Optional[int] = None) -> torch.Tensor:
+            ckpt_every: Optional[int] = None, path: bool = False) -> torch.Tensor:
     """Final cumulative negative log-likelihood of the EKF == ``ekf(cond_m_cov, H, Xi, m0, P0, dt, ys)[-1][-1]``
     (filters_smoothers.py:222-264), differentiable w.r.t. the model hyper-parameters, ``m0``, ``P0`` and ``Xi``.
 
-    Returns a CUDA tensor of shape () for one problem, (B,) for a batch, (B, G) with ``candidates=True``."""
+    Returns a CUDA tensor of shape () for one problem, (B,) for a batch, (B, G) with ``candidates=True``.
+    ``path=True`` returns the whole third output of ``ekf`` instead -- the cumulative n_ell at every step, shape (..., T) --
+    and accepts any cotangent on it (``ekf_nll_path``)."""
     if not isinstance(cond_m_cov, LCDModel):
         raise NotImplementedError('ekf_nll: the adjoint kernel is compiled for the chirp-family LCD models only')
     dev = _device()
@@ -117,8 +167,19 @@ def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = Fals
     P0_b = expand(P0_t, (d, d)).contiguous()
     h_unit = _h_unit_index(H)
     H_t = _as_dev(H, dev).reshape(-1).contiguous()
+    if path:
+        nell = _EkfNllPath.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every)
+        return nell.reshape(out_shape + (ys2.shape[-1],))
     nll = _EkfNll.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every)
     return nll.reshape(out_shape)
+
+
+def ekf_nll_path(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = False,
+                 ckpt_every: Optional[int] = None) -> torch.Tensor:
+    """The cumulative negative log-likelihood at every step == ``ekf(...)[-1]`` (filters_smoothers.py:180-184, :263-264), shape
+    (..., T), differentiable with ANY cotangent (what ``jax.vjp`` of the reference's third output accepts): the adjoint
+    kernel weights the increment of step k by the sum of the cotangents of steps >= k."""
+    return ekf_nll(cond_m_cov, H, Xi, m0, P0, dt, ys, candidates=candidates, ckpt_every=ckpt_every, path=True)
 
 
 def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None) -> torch.Tensor:

@@ -172,6 +172,16 @@ int cgp_test_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t
                     void *stream);
 int cgp_test_normals(uint64_t seed, int64_t n, double *out_dev, void *stream);
 
+/* The same pair for a cotangent on the WHOLE n_ell output (jax.vjp of ekf(...)[-1] with an arbitrary (T,) cotangent ct):
+ *   path_fwd: nell [B, T] = cumulative negative log-likelihood at every step (:180-184), checkpoints as above;
+ *   path_bwd: step_weights [B, T], the weight of every step's increment = sum_{j >= k} ct_j (a reversed cumulative sum the
+ *             caller forms), otherwise as cgp_ekf_nll_bwd_f64. */
+int cgp_ekf_nll_path_fwd_f64(const CgpProblem *p, const double *ys, double *nell, void *workspace, size_t workspace_bytes,
+                             int64_t ckpt_every, void *stream);
+int cgp_ekf_nll_path_bwd_f64(const CgpProblem *p, const double *ys, const double *step_weights, void *workspace,
+                             size_t workspace_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,
+                             double *Xi_bar, void *stream);
+
 /* ---- measurement utility: DFMA-only kernel (8 independent chains / thread) for the FP64 roofline denominator.
  * `out` holds blocks * 256 doubles.  Returns the flops issued (caller times the stream), < 0 on error. */
 double cgp_bench_dfma(double *out, int blocks, int iters, void *stream);

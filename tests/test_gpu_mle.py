@@ -168,3 +168,50 @@ def test_kpt_mle_objective_and_gradient(golden):
         v, gr = calls[0]
         npt.assert_allclose(v, z['ekf_for_kpt_2'][-1], rtol=1e-10)
         npt.assert_allclose(gr, z['grad_ekf_for_kpt'], rtol=2e-6, atol=1e-6)
+
+
+def test_nll_path_and_arbitrary_cotangent():
+    """ekf(...)[-1] as a differentiable (T,) output: values == the filter kernel's n_ell; the gradient of a
+    randomly weighted sum of ALL steps matches the torch autodiff twin, and the all-weight-on-the-last-step case reproduces
+    ekf_nll's gradient."""
+    from oracle import ekf_torch
+    from chirpgp_b200.models import g_inv
+    rng = np.random.default_rng(12)
+    T, dt, Xi = 40, 1e-3, 0.1
+    _, ys, _ = toymodels.synthetic_batch(2, 3141, dt, Xi=Xi, seed=2)
+    ys = ys[:, 1200:1200 + T]
+    theta0 = g_inv(np.array([0.1, 0.1, 0.1, 1., 1., 7.]))
+    ct = rng.standard_normal((2, T))
+
+    def run(use_path, cot):
+        theta = torch.tensor(theta0, dtype=torch.float64, requires_grad=True)
+        _, _, mc, m0, P0, H = cg.build_chirp_model(gfun(theta))
+        if use_path:
+            nell = mle.ekf_nll_path(mc, H, Xi, m0, P0, dt, ys)
+            assert tuple(nell.shape) == (2, T)
+            loss = (nell * torch.as_tensor(cot, device=nell.device)).sum()
+        else:
+            nell = None
+            loss = mle.ekf_nll(mc, H, Xi, m0, P0, dt, ys).sum()
+        grad, = torch.autograd.grad(loss, theta)
+        return (None if nell is None else nell.detach().cpu().numpy()), grad.cpu().numpy()
+
+    nell, grad = run(True, ct)
+    _, _, mc, m0, P0, H = cg.build_chirp_model(gfun(torch.tensor(theta0)))
+    f = cg.ekf(mc, H, Xi, m0, P0, dt, ys)
+    npt.assert_allclose(nell, f[2], rtol=1e-12)
+    # autodiff twin: n_ell_k is the final nll of the first k + 1 samples
+    theta = torch.tensor(theta0, dtype=torch.float64, requires_grad=True)
+    _, _, mc_t, m0_t, P0_t, H_t = cg.build_chirp_model(gfun(theta))
+    consts = mc_t.consts(dt)
+    total = torch.zeros((), dtype=torch.float64)
+    for b in range(2):
+        for k in range(T):
+            total = total + float(ct[b, k]) * ekf_torch.ekf_nll(consts, H_t, Xi, m0_t, P0_t, dt, torch.as_tensor(ys[b, :k + 1]), 1)
+    want, = torch.autograd.grad(total, theta)
+    npt.assert_allclose(grad, want.numpy(), rtol=1e-7, atol=1e-8)
+    # weight on the last step only == gradient of the final nll
+    last = np.zeros((2, T)); last[:, -1] = 1.
+    _, g_last = run(True, last)
+    _, g_final = run(False, None)
+    npt.assert_allclose(g_last, g_final, rtol=1e-12, atol=1e-13)
