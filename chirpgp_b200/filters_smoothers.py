@@ -60,8 +60,21 @@ def _kind(x):
     return ('numpy', None)
 
 
+_PINNED_MIN_BYTES = 1 << 20
+
+
 def _back(t: torch.Tensor, kind):
     if kind[0] == 'numpy':
+        # NumPy callers get arrays backed by pinned host memory (torch's caching host allocator recycles the blocks): the
+        # device->host copy of the (T, d, d) outputs runs at the PCIe rate instead of the pageable-memory rate
+        if t.is_cuda and t.numel() * t.element_size() >= _PINNED_MIN_BYTES:
+            try:
+                host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host.copy_(t, non_blocking=True)
+                torch.cuda.current_stream(t.device).synchronize()
+                return host.numpy()
+            except RuntimeError:
+                pass                     # no pinned memory left: pageable copy below
         return t.cpu().numpy()
     return t.to(kind[1])
 
