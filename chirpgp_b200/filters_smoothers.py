@@ -30,7 +30,7 @@ from .models import (LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, KPTM
                      MODEL_LCD, MODEL_LINEAR_SDE, MODEL_SDE, MODEL_KPT)
 
 __all__ = ['kf', 'rts', 'ekf', 'ekf_for_kpt', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
-           'cd_sgp_smoother']
+           'cd_sgp_smoother', 'sgp_filter_smoother']
 
 _F64 = torch.float64
 
@@ -454,6 +454,18 @@ def sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt) -> Tuple:
     dt = float(dt)
     model = _disc_model(cond_m_cov, int(mfs.shape[-1]), dt)
     return _run_smoother('sgp_smoother', model, _consts_on_device(model, dt, _device(), dt), mfs, Pfs, dt, sgps=sgps)
+
+
+def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys) -> Tuple:
+    """``sgp_filter`` followed by ``sgp_smoother`` in one call (extension; what every demo / job does back to back,
+    demos/ghfs_mle.py:69-85): returns ``(mfs, Pfs, n_ell, mss, Pss)`` of the kind of ``ys``.  For host (NumPy) callers this is
+    the efficient form of the pair: the measurements are uploaded once, the filtering result never travels back up, and the
+    filter kernel hands the smoother its gains; the five results come down into pinned host memory."""
+    dev = _device()
+    kind = _kind(ys)
+    f = sgp_filter(cond_m_cov, sgps, _dev(H, dev), Xi, _dev(m0, dev), _dev(P0, dev), dt, _dev(ys, dev))
+    s = sgp_smoother(cond_m_cov, sgps, f[0], f[1], dt)
+    return tuple(_back(t, kind) for t in f + s)
 
 
 def _qc(bm):

@@ -577,3 +577,21 @@ def test_general_measurement_row_and_nan_inputs_on_the_fused_path(batch):
     assert torch.isnan(sn[0][2]).all()                                           # the backward sweep starts from NaN
     keep = [0, 1, 3, 4, 5]
     assert torch.equal(fn[0][keep], fd[0][keep]) and torch.equal(sn[1][keep], sd[1][keep])
+
+
+def test_sgp_filter_smoother_one_call(batch):
+    """The one-call pair for host callers == the two reference-style calls (NumPy in, NumPy out)."""
+    B, T, dt, ys = batch
+    ys = ys[:5, :300]
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    out = cg.sgp_filter_smoother(mc, sg, H, 0.1, m0, P0, dt, ys)
+    assert all(isinstance(x, np.ndarray) for x in out) and len(out) == 5
+    f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    for a, b in zip(out, f + s):
+        _close(a, b, atol=ATOL_LONG)
+    fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_filter(out[:3], fo, ATOL_LONG)
+    _check_smoother(out[3:], so, ATOL_LONG)
