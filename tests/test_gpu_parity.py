@@ -595,3 +595,25 @@ def test_sgp_filter_smoother_one_call(batch):
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
     _check_filter(out[:3], fo, ATOL_LONG)
     _check_smoother(out[3:], so, ATOL_LONG)
+
+
+def test_long_sequence_fused_path():
+    """T = 20 000 (config 5 runs 10^5): the fused filter is bit-identical to the stand-alone filter kernel (same producer
+    arithmetic), the smoothers agree to rounding, both match the oracle at the long-run tolerance."""
+    B, T, dt, Xi = 6, 20000, 1.5e-4, 0.1
+    rng = np.random.default_rng(0)
+    ts = np.linspace(dt, dt * T, T)
+    ys = np.sin(2 * np.pi * (500 * np.exp(-5 / np.sin(ts)) + 8 * ts))[None] + np.sqrt(Xi) * rng.standard_normal((B, T))
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    args = (_cuda(H), Xi, _cuda(m0), _cuda(P0), dt, _cuda(ys))
+    f = cg.sgp_filter(mc, sg, *args)
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    f2 = cg.sgp_filter(mc, sg, *args, smoother_gains=False)
+    s2 = cg.sgp_smoother(mc, sg, f2[0], f2[1], dt)
+    assert torch.equal(f[0], f2[0]) and torch.equal(f[1], f2[1]) and torch.equal(f[2], f2[2])
+    _check_smoother([x.cpu().numpy() for x in s], [x.cpu().numpy() for x in s2], 2e-8)
+    fo = orc.sgp_filter(spec, sg, H, Xi, m0, P0, dt, ys[:2])
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_filter([x[:2].cpu().numpy() for x in f], fo, 2e-8)
+    _check_smoother([x[:2].cpu().numpy() for x in s], so, 2e-8)
