@@ -12,7 +12,6 @@ every rank owns B = 1000 chirps), no data-path collective.  Rank 0 prints ONE JS
 """
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess

@@ -26,8 +26,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .models import (LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, KPTMeasurement, MODEL_LINEAR_DISC,
-                     MODEL_LCD, MODEL_LINEAR_SDE, MODEL_SDE, MODEL_KPT)
+from .models import LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, KPTMeasurement, MODEL_KPT
 
 __all__ = ['kf', 'rts', 'ekf', 'ekf_for_kpt', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
            'cd_sgp_smoother', 'sgp_filter_smoother']

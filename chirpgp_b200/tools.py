@@ -30,7 +30,7 @@ def simulate(cond_m_cov, H, Xi, m0, P0, dt, T: int, num_trajectories: int, seed:
     callable) and their measurements.  Returns CUDA tensors ``(x0 (B, d), xs (B, T, d) or None, ys (B, T))``."""
     dev = fs._device()
     dt = float(dt)
-    model = fs._disc_model(cond_m_cov, int(np.shape(m0)[-1]) if not isinstance(m0, torch.Tensor) else int(m0.shape[-1]), dt)
+    model = fs._disc_model(cond_m_cov, int(np.shape(m0)[-1]), dt)
     if not isinstance(model, (LCDModel, LinearDisc)):
         raise NotImplementedError('simulate: discretised models only')
     model_id, d, nh = fs._model_fields(model)
