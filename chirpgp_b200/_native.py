@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 
 CGP_MODEL_LINEAR_DISC, CGP_MODEL_LCD, CGP_MODEL_LINEAR_SDE, CGP_MODEL_SDE, CGP_MODEL_KPT = 0, 1, 2, 3, 4
 CGP_SIGMA_GENERIC, CGP_SIGMA_GAUSS_HERMITE, CGP_SIGMA_CUBATURE = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _ERRORS = {-1: 'CGP_ERR_BAD_ARG', -2: 'CGP_ERR_UNSUPPORTED (no kernel compiled for this model / state dimension)',
            -3: 'CGP_ERR_WORKSPACE'}
@@ -38,8 +38,8 @@ class CgpProblem(C.Structure):
 FILTER_FUNCS = ('kf', 'ekf', 'ekf_for_kpt', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
 SMOOTHER_FUNCS = ('rts', 'eks', 'sgp_smoother', 'cd_eks', 'cd_sgp_smoother')
 EXPORTED = (['cgp_abi_version', 'cgp_workspace_bytes'] + ['cgp_%s_f64' % f for f in FILTER_FUNCS + SMOOTHER_FUNCS]
-            + ['cgp_ekf_nll_default_ckpt', 'cgp_ekf_nll_workspace_bytes', 'cgp_ekf_nll_fwd_f64', 'cgp_ekf_nll_bwd_f64',
-               'cgp_ekf_nll_path_fwd_f64', 'cgp_ekf_nll_path_bwd_f64',
+            + ['cgp_ekf_nll_default_ckpt', 'cgp_ekf_nll_workspace_bytes', 'cgp_ekf_nll_fwd_f64', 'cgp_ekf_nll_bwd_f64', 'cgp_ekf_nll_bwd_sym_f64',
+               'cgp_ekf_nll_path_fwd_f64', 'cgp_ekf_nll_path_bwd_f64', 'cgp_filter_nll_tangent_f64',
                'cgp_sgp_filter_gains_fused', 'cgp_sgp_filter_gains_f64', 'cgp_smoother_sweep_f64',
                'cgp_gaussian_expectation_softplus_f64', 'cgp_simulate_f64', 'cgp_test_philox', 'cgp_test_normals',
                'cgp_bench_dfma', 'cgp_test_math'])
@@ -97,6 +97,8 @@ def lib():
         L.cgp_ekf_nll_bwd_f64.restype = C.c_int
         L.cgp_ekf_nll_bwd_f64.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cgp_ekf_nll_bwd_sym_f64.restype = C.c_int
+        L.cgp_ekf_nll_bwd_sym_f64.argtypes = L.cgp_ekf_nll_bwd_f64.argtypes
         L.cgp_gaussian_expectation_softplus_f64.restype = C.c_int
         L.cgp_gaussian_expectation_softplus_f64.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                                             C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -111,6 +113,10 @@ def lib():
         L.cgp_ekf_nll_path_fwd_f64.argtypes = L.cgp_ekf_nll_fwd_f64.argtypes
         L.cgp_ekf_nll_path_bwd_f64.restype = C.c_int
         L.cgp_ekf_nll_path_bwd_f64.argtypes = L.cgp_ekf_nll_bwd_f64.argtypes
+        L.cgp_filter_nll_tangent_f64.restype = C.c_int
+        L.cgp_filter_nll_tangent_f64.argtypes = [C.c_char_p, C.POINTER(CgpProblem), C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cgp_bench_dfma.restype = C.c_double
         L.cgp_bench_dfma.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.cgp_test_math.restype = C.c_int

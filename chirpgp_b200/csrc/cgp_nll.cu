@@ -219,6 +219,13 @@ static size_t scratch_doubles(const CgpProblem &p, int64_t every) {
     return (size_t)every * (size_t)(p.d + p.d * p.d) * (size_t)p.B;
 }
 
+// second-generation kernels (cgp_nll2.cu): persistent, ticket-scheduled, packed-symmetric covariance
+size_t nll2_workspace_bytes(const CgpProblem &p, int64_t every);
+bool nll2_supported(const CgpProblem &p);
+int nll2_fwd(const CgpProblem &p, const double *ys, double *nll, void *workspace, int64_t every, cudaStream_t s);
+int nll2_bwd(const CgpProblem &p, const double *ys, const double *nll_bar, void *workspace, int64_t every, bool raw_p0_bar,
+             double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar, cudaStream_t s);
+
 }  // namespace cgp
 
 using namespace cgp;
@@ -226,14 +233,19 @@ using namespace cgp;
 extern "C" {
 
 int64_t cgp_ekf_nll_default_ckpt(int64_t T) {
+    // segments of 32 steps keep the adjoint's per-warp scratch slot (32 x 17 x 256 bytes for d = 4) resident in L2; short
+    // series get ~sqrt(T)
     int64_t c = 1;
     while (c * c < T) c++;
-    return c < 1 ? 1 : c;
+    return c > 32 ? 32 : (c < 1 ? 1 : c);
 }
 
 size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every) {
     if (!p || ckpt_every < 1) return 0;
-    return (ckpt_doubles(*p, ckpt_every) + scratch_doubles(*p, ckpt_every)) * sizeof(double);
+    // the larger of the two layouts: thread-per-problem kernels (n_ell path variants) / persistent kernels (scalar nll)
+    const size_t v1 = (ckpt_doubles(*p, ckpt_every) + scratch_doubles(*p, ckpt_every)) * sizeof(double);
+    const size_t v2 = nll2_supported(*p) ? nll2_workspace_bytes(*p, ckpt_every) : 0;
+    return v1 > v2 ? v1 : v2;
 }
 
 static int nll_fwd(const CgpProblem *p, const double *ys, double *nll, double *nell_path, void *workspace, size_t ws_bytes,
@@ -263,7 +275,14 @@ static int nll_fwd(const CgpProblem *p, const double *ys, double *nll, double *n
 
 int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void *workspace, size_t ws_bytes,
                         int64_t ckpt_every, void *stream) {
-    return nll_fwd(p, ys, nll, nullptr, workspace, ws_bytes, ckpt_every, stream);
+    if (!p || !ys || !nll || p->B < 1 || p->T < 1 || !p->consts || !p->m0 || !p->P0 || !p->H || p->ys_repeat < 1)
+        return CGP_ERR_BAD_ARG;
+    if (!nll2_supported(*p)) return CGP_ERR_UNSUPPORTED;
+    if (workspace) {
+        if (ckpt_every < 1) return CGP_ERR_BAD_ARG;
+        if (ws_bytes < cgp_ekf_nll_workspace_bytes(p, ckpt_every)) return CGP_ERR_WORKSPACE;
+    }
+    return nll2_fwd(*p, ys, nll, workspace, ckpt_every, (cudaStream_t)stream);
 }
 int cgp_ekf_nll_path_fwd_f64(const CgpProblem *p, const double *ys, double *nell, void *workspace, size_t ws_bytes,
                              int64_t ckpt_every, void *stream) {
@@ -291,9 +310,22 @@ static int nll_bwd(const CgpProblem *p, const double *ys, const double *nll_bar,
     }
     return check_launch();
 }
+static int nll_bwd2(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace, size_t ws_bytes,
+                    int64_t ckpt_every, bool raw, double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar, void *stream) {
+    if (!p || !ys || !workspace || !consts_bar || !m0_bar || !P0_bar || p->B < 1 || p->T < 1 || ckpt_every < 1 ||
+        !p->consts || !p->m0 || !p->P0 || !p->H || p->ys_repeat < 1)
+        return CGP_ERR_BAD_ARG;
+    if (!nll2_supported(*p)) return CGP_ERR_UNSUPPORTED;
+    if (ws_bytes < cgp_ekf_nll_workspace_bytes(p, ckpt_every)) return CGP_ERR_WORKSPACE;
+    return nll2_bwd(*p, ys, nll_bar, workspace, ckpt_every, raw, consts_bar, m0_bar, P0_bar, Xi_bar, (cudaStream_t)stream);
+}
 int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace, size_t ws_bytes,
                         int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar, void *stream) {
-    return nll_bwd(p, ys, nll_bar, nullptr, workspace, ws_bytes, ckpt_every, consts_bar, m0_bar, P0_bar, Xi_bar, stream);
+    return nll_bwd2(p, ys, nll_bar, workspace, ws_bytes, ckpt_every, true, consts_bar, m0_bar, P0_bar, Xi_bar, stream);
+}
+int cgp_ekf_nll_bwd_sym_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace, size_t ws_bytes,
+                            int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar, double *Xi_bar, void *stream) {
+    return nll_bwd2(p, ys, nll_bar, workspace, ws_bytes, ckpt_every, false, consts_bar, m0_bar, P0_bar, Xi_bar, stream);
 }
 int cgp_ekf_nll_path_bwd_f64(const CgpProblem *p, const double *ys, const double *step_weights, void *workspace,
                              size_t ws_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,

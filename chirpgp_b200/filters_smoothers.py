@@ -20,6 +20,7 @@ Differences that follow from running compiled kernels instead of traced Python c
 """
 import ctypes as C
 import os
+import weakref
 from typing import Tuple
 
 import numpy as np
@@ -50,7 +51,12 @@ def _dev(x, dev) -> torch.Tensor:
         t = x.detach()
     else:
         t = torch.as_tensor(np.asarray(x, dtype=np.float64))
-    return t.to(device=dev, dtype=_F64, non_blocking=True).contiguous()
+    t = t.to(device=dev, dtype=_F64, non_blocking=True).contiguous()
+    if t.data_ptr() % 32:
+        # the kernels use 16- and 32-byte vector accesses (every ABI pointer is 32-byte aligned); a view with
+        # a storage offset (x[1:5]) would raise a misaligned-address fault, which is sticky for the whole CUDA context
+        t = t.clone()
+    return t
 
 
 def _kind(x):
@@ -87,13 +93,15 @@ _h_cache = {}
 
 
 def _h_unit_index(H) -> int:
-    """j if H is exactly the unit vector e_j, else -1 (a kernel specialisation hint).  Device tensors are inspected
-    once per (storage, version) so that steady-state calls do not synchronise the stream."""
+    """j if H is exactly the unit vector e_j, else -1 (a kernel specialisation hint: the H_E1 kernels never read H).
+    Device tensors are inspected once per tensor OBJECT and version so that steady-state calls do not synchronise the
+    stream.  The cache entry holds a weak reference to the tensor and is honoured only while that very object is alive and
+    unmodified -- an address can be recycled by the caching allocator for a different H, an object identity cannot."""
     if isinstance(H, torch.Tensor) and H.is_cuda:
-        key = (H.data_ptr(), H._version, tuple(H.shape))
+        key = id(H)
         hit = _h_cache.get(key)
-        if hit is not None:
-            return hit
+        if hit is not None and hit[0]() is H and hit[1] == H._version:
+            return hit[2]
         host = H.detach().cpu().numpy().reshape(-1)
     else:
         key = None
@@ -103,7 +111,7 @@ def _h_unit_index(H) -> int:
     if key is not None:
         if len(_h_cache) > 64:
             _h_cache.clear()
-        _h_cache[key] = out
+        _h_cache[key] = (weakref.ref(H), H._version, out)
     return out
 
 
@@ -248,13 +256,18 @@ def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, X
 
 class _SmootherGains:
     """Smoother workspace ([G | mp | Pp] per (chirp, step)) that a filter call produced together with (mfs, Pfs).  Rides
-    on the returned ``mfs`` tensor; the smoother uses it only if it is called with exactly those tensors, unmodified, and
-    the same model constants / sigma points / dt -- otherwise it recomputes the gains."""
-    __slots__ = ('ws', 'nbytes', 'mfs_ptr', 'Pfs_ptr', 'mfs_version', 'Pfs_ref', 'Pfs_version', 'consts', 'consts_version',
+    on the returned ``mfs`` tensor; the smoother uses it only if it is called with exactly those tensor OBJECTS (identity,
+    through weak references -- not addresses, which the allocator recycles), unmodified according to torch's version
+    counters, and the same model constants / sigma points / dt -- otherwise it recomputes the gains.
+
+    Limits: a write into ``mfs`` / ``Pfs`` that bypasses torch's version counter (a raw-pointer kernel, DLPack / cupy view)
+    is invisible here -- callers who do that must pass ``smoother_gains=False`` to ``sgp_filter`` or drop the attribute
+    (``del mfs._cgp_smoother_gains``).  The record keeps (2 d^2 + d) doubles per step alive as long as ``mfs`` lives."""
+    __slots__ = ('ws', 'nbytes', 'mfs_ref', 'Pfs_ref', 'mfs_version', 'Pfs_version', 'consts', 'consts_version',
                  'sig', 'dt', 'shape', 'smoother')
 
     def matches(self, smoother, mfs, Pfs, consts, sig, dt):
-        return (self.smoother == smoother and mfs.data_ptr() == self.mfs_ptr and Pfs.data_ptr() == self.Pfs_ptr
+        return (self.smoother == smoother and self.mfs_ref() is mfs and self.Pfs_ref() is Pfs
                 and mfs._version == self.mfs_version and Pfs._version == self.Pfs_version
                 and tuple(mfs.shape) == self.shape
                 and consts.data_ptr() == self.consts.data_ptr() and consts._version == self.consts_version
@@ -328,7 +341,7 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
         return _back(nell, kind)
     mfs, Pfs = _back(mfs, kind), _back(Pfs, kind)
     if rec is not None:
-        rec.mfs_ptr, rec.Pfs_ptr, rec.shape = mfs.data_ptr(), Pfs.data_ptr(), tuple(mfs.shape)
+        rec.mfs_ref, rec.Pfs_ref, rec.shape = weakref.ref(mfs), weakref.ref(Pfs), tuple(mfs.shape)
         rec.mfs_version, rec.Pfs_version = mfs._version, Pfs._version
         mfs._cgp_smoother_gains = rec
     return mfs, Pfs, _back(nell, kind)

@@ -21,7 +21,7 @@ from . import _native as N
 from .filters_smoothers import _device, _problem, _ptr, _h_unit_index
 from .models import LCDModel, NC_LCD
 
-__all__ = ['ekf_nll', 'ekf_nll_path', 'filter_nll', 'fit_mle']
+__all__ = ['ekf_nll', 'ekf_nll_path', 'filter_nll', 'filter_nll_grad', 'fit_mle', 'fit_mle_batched']
 
 _F64 = torch.float64
 
@@ -30,7 +30,7 @@ class _EkfNll(torch.autograd.Function):
     """consts [B, NC_LCD], m0 [B, d], P0 [B, d, d], Xi (0-d tensor) -> nll [B]  (all CUDA float64, contiguous)."""
 
     @staticmethod
-    def forward(ctx, consts, m0, P0, Xi, ys, H, dt, nh, ys_repeat, h_unit, ckpt_every):
+    def forward(ctx, consts, m0, P0, Xi, ys, H, dt, nh, ys_repeat, h_unit, ckpt_every, raw_p0):
         L = N.lib()
         dev = consts.device
         B, d = m0.shape
@@ -38,7 +38,7 @@ class _EkfNll(torch.autograd.Function):
         p = _problem(B, T, N.CGP_MODEL_LCD, d, nh, consts, NC_LCD, m0, d, P0, d * d, H, None, 0, None, float(Xi), dt,
                      ys_repeat, h_unit)
         need_grad = any(ctx.needs_input_grad[:4])
-        every = int(ckpt_every or L.cgp_ekf_nll_default_ckpt(T))
+        every = int(ckpt_every or _default_ckpt(L, p, T, dev))
         ws, nbytes = None, 0
         if need_grad:
             nbytes = L.cgp_ekf_nll_workspace_bytes(C.byref(p), every)
@@ -48,13 +48,13 @@ class _EkfNll(torch.autograd.Function):
         rc = L.cgp_ekf_nll_fwd_f64(C.byref(p), _ptr(ys), _ptr(nll), _ptr(ws), C.c_size_t(nbytes), every, stream)
         N.check(rc, 'ekf_nll')
         ctx.save_for_backward(consts, m0, P0, Xi, ys, H)
-        ctx.ws, ctx.meta = ws, (dt, nh, ys_repeat, h_unit, every, nbytes)
+        ctx.ws, ctx.meta = ws, (dt, nh, ys_repeat, h_unit, every, nbytes, bool(raw_p0))
         return nll
 
     @staticmethod
     def backward(ctx, nll_bar):
         consts, m0, P0, Xi, ys, H = ctx.saved_tensors
-        dt, nh, ys_repeat, h_unit, every, nbytes = ctx.meta
+        dt, nh, ys_repeat, h_unit, every, nbytes, raw_p0 = ctx.meta
         L = N.lib()
         dev = consts.device
         B, d = m0.shape
@@ -67,10 +67,11 @@ class _EkfNll(torch.autograd.Function):
         xb = torch.empty((B,), dtype=_F64, device=dev)
         nb = nll_bar.contiguous()
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        rc = L.cgp_ekf_nll_bwd_f64(C.byref(p), _ptr(ys), _ptr(nb), _ptr(ctx.ws), C.c_size_t(nbytes), every, _ptr(cb),
-                                   _ptr(mb), _ptr(Pb), _ptr(xb), stream)
+        fn = L.cgp_ekf_nll_bwd_f64 if raw_p0 else L.cgp_ekf_nll_bwd_sym_f64
+        rc = fn(C.byref(p), _ptr(ys), _ptr(nb), _ptr(ctx.ws), C.c_size_t(nbytes), every, _ptr(cb), _ptr(mb), _ptr(Pb),
+                _ptr(xb), stream)
         N.check(rc, 'ekf_nll backward')
-        return cb, mb, Pb, xb.sum(), None, None, None, None, None, None, None
+        return cb, mb, Pb, xb.sum(), None, None, None, None, None, None, None, None
 
 
 class _EkfNllPath(torch.autograd.Function):
@@ -121,6 +122,16 @@ class _EkfNllPath(torch.autograd.Function):
         return cb, mb, Pb, xb.sum(), None, None, None, None, None, None, None
 
 
+def _default_ckpt(L, p, T, dev) -> int:
+    """Segment length of the checkpointed adjoint: the library default (32 steps: the per-warp scratch slot stays in L2),
+    lengthened until the checkpoints (one (m, P, nll) record per problem and segment) fit into half of the free memory."""
+    every = int(L.cgp_ekf_nll_default_ckpt(T))
+    free, _ = torch.cuda.mem_get_info(dev)
+    while every < T and L.cgp_ekf_nll_workspace_bytes(C.byref(p), every) > 0.5 * free:
+        every *= 2
+    return every
+
+
 def _as_dev(x, dev):
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=_F64)
@@ -128,13 +139,18 @@ def _as_dev(x, dev):
 
 
 def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = False,
-            ckpt_every: Optional[int] = None, path: bool = False) -> torch.Tensor:
+            ckpt_every: Optional[int] = None, path: bool = False, raw_p0_cotangent: bool = False) -> torch.Tensor:
     """Final cumulative negative log-likelihood of the EKF == ``ekf(cond_m_cov, H, Xi, m0, P0, dt, ys)[-1][-1]``
     (filters_smoothers.py:222-264), differentiable w.r.t. the model hyper-parameters, ``m0``, ``P0`` and ``Xi``.
 
     Returns a CUDA tensor of shape () for one problem, (B,) for a batch, (B, G) with ``candidates=True``.
     ``path=True`` returns the whole third output of ``ekf`` instead -- the cumulative n_ell at every step, shape (..., T) --
-    and accepts any cotangent on it (``ekf_nll_path``)."""
+    and accepts any cotangent on it (``ekf_nll_path``).
+
+    The cotangent of ``P0`` is symmetrised, (X + X^T) / 2 of what ``jax.grad`` of the reference returns for a general
+    matrix argument: the same gradient for every parametrisation in which P0 is a symmetric matrix (all callers of the
+    reference build it as a diagonal, models.py:56-58).  ``raw_p0_cotangent=True`` makes the adjoint kernel also carry the
+    antisymmetric part and return JAX's unsymmetrised matrix."""
     if not isinstance(cond_m_cov, LCDModel):
         raise NotImplementedError('ekf_nll: the adjoint kernel is compiled for the chirp-family LCD models only')
     dev = _device()
@@ -170,7 +186,7 @@ def ekf_nll(cond_m_cov: LCDModel, H, Xi, m0, P0, dt, ys, candidates: bool = Fals
     if path:
         nell = _EkfNllPath.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every)
         return nell.reshape(out_shape + (ys2.shape[-1],))
-    nll = _EkfNll.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every)
+    nll = _EkfNll.apply(consts_b, m0_b, P0_b, Xi_t, ys2, H_t, dt, nh, ys_repeat, h_unit, ckpt_every, raw_p0_cotangent)
     return nll.reshape(out_shape)
 
 
@@ -191,8 +207,9 @@ def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None)
     from . import filters_smoothers as fs
     dt = float(dt)
     if method in ('kf', 'ekf', 'sgp_filter'):
-        model = fs._disc_model(model_args[0], int(m0.shape[-1]), dt) if method != 'kf' else model_args[0]
-        consts = fs._consts_on_device(model, dt, fs._device(), *((dt,) if method != 'kf' else ()))
+        # kf takes (F, Sigma) like the reference (filters_smoothers.py:145-148); the other two a cond_m_cov callable
+        model = fs._disc_model(model_args[0], int(m0.shape[-1]), dt) if method != 'kf' else fs.LinearDisc(*model_args[:2])
+        consts = fs._consts_on_device(model, dt if method != 'kf' else None, fs._device(), *((dt,) if method != 'kf' else ()))
         return fs._run_filter(method, model, consts, H, Xi, m0, P0, dt, ys, sgps=sgps, store=False, last_only=True)
     if method == 'ekf_for_kpt':
         F, Sigma, h = model_args
@@ -209,6 +226,123 @@ def filter_nll(method: str, model_args: tuple, H, Xi, m0, P0, dt, ys, sgps=None)
     raise ValueError('unknown filter %r' % method)
 
 
+_TANGENT_METHODS = ('ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter')
+
+
+def filter_nll_grad(method: str, build_model: Callable, theta, H, Xi, dt, ys, sgps=None, transform: Optional[Callable] = None):
+    """Final cumulative nll of ``method`` in {'ekf', 'sgp_filter', 'cd_ekf', 'cd_sgp_filter'} AND its exact gradient w.r.t. the
+    unconstrained parameters ``theta`` -- what ``jax.value_and_grad(obj_func)(theta)`` gives in demos/ghfs_mle.py:54-61,
+    demos/cd_ekfs_mle.py and demos/cd_ghfs_mle.py -- by the forward-mode tangent kernels (csrc/cgp_tangent.cu): one group of
+    lanes per (chirp, parameter direction) carries the filter state and its derivative along that direction.
+
+    ``build_model(transform(theta))`` -> (drift, dispersion, m_and_cov, m0, P0, _) as ``chirpgp_b200.models.build_*``;
+    ``theta`` is (P,) (shared by all chirps in ``ys``) or (B, P) (one parameter vector per chirp: the lock-step MLE of
+    ``fit_mle_batched``).  The tangents of the kernel inputs (d consts / d theta etc.) come from ``torch.func.jacfwd`` of the
+    builder on the host.  Returns ``(nll (B,), grad (B, P))`` as CUDA tensors (B = number of chirps)."""
+    from . import filters_smoothers as fs
+    from .models import g as _g, NC_SDE
+    if method not in _TANGENT_METHODS:
+        raise ValueError('no tangent kernel for %r' % method)
+    transform = transform or _g
+    dev = _device()
+    dt = float(dt)
+    L = N.lib()
+    cd = method in ('cd_ekf', 'cd_sgp_filter')
+    theta_t = (theta.detach() if isinstance(theta, torch.Tensor) else torch.as_tensor(np.asarray(theta, dtype=np.float64))).to(_F64).cpu()
+    ys_t = _as_dev(ys, dev)
+    ys2 = ys_t.reshape(-1, ys_t.shape[-1]).contiguous()
+    B, T = int(ys2.shape[0]), int(ys2.shape[1])
+    meta = {}
+
+    def pack(th):
+        drift, dispersion, m_and_cov, m0, P0, _ = build_model(transform(th))
+        model = drift if cd else m_and_cov
+        meta['d'], meta['nh'] = int(model.d), int(model.num_harmonics)
+        parts = [(model.consts() if cd else model.consts(dt)).reshape(-1), m0.reshape(-1), P0.reshape(-1)]
+        if cd:
+            bm = dispersion.matrix()
+            parts.append((bm @ bm.transpose(-1, -2)).reshape(-1))
+        return torch.cat(parts)
+
+    per_chirp = theta_t.dim() == 2
+    if per_chirp and theta_t.shape[0] != B:
+        raise ValueError('theta has %d rows for %d chirps' % (theta_t.shape[0], B))
+    if per_chirp:
+        vals = torch.func.vmap(pack)(theta_t)                                   # (B, NV)
+        jac = torch.func.vmap(torch.func.jacfwd(pack))(theta_t)                 # (B, NV, P)
+    else:
+        vals = pack(theta_t)[None]
+        jac = torch.func.jacfwd(pack)(theta_t)[None]
+    d, nh = meta['d'], meta['nh']
+    nc = NC_SDE if cd else NC_LCD
+    P_ = int(theta_t.shape[-1])
+    sizes = [nc, d, d * d] + ([d * d] if cd else [])
+    vparts = torch.split(vals.to(dev), sizes, dim=1)
+    dparts = torch.split(jac.to(dev).transpose(1, 2).contiguous(), sizes, dim=2)     # (B|1, P, size)
+    consts, m0, P0 = [v.contiguous() for v in vparts[:3]]
+    consts_d, m0_d, P0_d = [t.contiguous() for t in dparts[:3]]
+    Qc = vparts[3].contiguous() if cd else None
+    Qc_d = dparts[3].contiguous() if cd else None
+    st = (lambda n: n) if per_chirp else (lambda n: 0)
+    sig = fs._sigma_tables(sgps, dev) if method in ('sgp_filter', 'cd_sgp_filter') else None
+    if method in ('sgp_filter', 'cd_sgp_filter') and sig is None:
+        raise ValueError('%s needs sgps' % method)
+    H_t = _as_dev(H, dev).reshape(-1).contiguous()
+    p = _problem(B, T, N.CGP_MODEL_SDE if cd else N.CGP_MODEL_LCD, d, nh, consts, st(nc), m0, st(d), P0, st(d * d), H_t,
+                 Qc, st(d * d) if cd else 0, sig, float(Xi), dt, 1, -1)
+    nll = torch.empty((B,), dtype=_F64, device=dev)
+    nll_dot = torch.empty((B, P_), dtype=_F64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = L.cgp_filter_nll_tangent_f64(method.encode(), C.byref(p), _ptr(ys2), P_, _ptr(consts_d), st(P_ * nc), _ptr(m0_d),
+                                      st(P_ * d), _ptr(P0_d), st(P_ * d * d), _ptr(Qc_d), st(P_ * d * d) if cd else 0, None,
+                                      _ptr(nll), _ptr(nll_dot), stream)
+    N.check(rc, 'filter_nll_grad(%s)' % method)
+    return nll, nll_dot
+
+
+def _objective(build_model, H, Xi, dt, ys_t, method, sgps, transform, fd_step):
+    """-> f(theta (n, P) numpy) = (values (n,), grads (n, P)) numpy: row i is the nll of chirp i under theta[i] and its
+    gradient.  'ekf': adjoint kernel; 'sgp_filter' / 'cd_ekf' / 'cd_sgp_filter': tangent kernels; 'ekf_for_kpt': five-point
+    central differences over a candidate batch."""
+    dev = _device()
+
+    def f_adjoint(theta_np, rows):
+        theta = torch.tensor(theta_np, dtype=_F64, device=dev, requires_grad=True)
+        _, _, m_and_cov, m0, P0, _ = build_model(transform(theta))
+        val = ekf_nll(m_and_cov, H, Xi, m0, P0, dt, ys_t[rows])
+        grad, = torch.autograd.grad(val.sum(), theta)
+        return val.detach(), grad
+
+    def f_tangent(theta_np, rows):
+        return filter_nll_grad(method, build_model, torch.as_tensor(theta_np), H, Xi, dt, ys_t[rows], sgps=sgps,
+                               transform=transform)
+
+    def f_fd(theta_np, rows):
+        # five-point central differences: (-f(+2h) + 8 f(+h) - 8 f(-h) + f(-2h)) / 12h, all 4P + 1 candidates of a chirp in ONE
+        # batch against its signal (nll-only kernel)
+        vals, grads = [], []
+        for th, r in zip(theta_np, rows):
+            n = th.shape[0]
+            h = (fd_step if fd_step is not None else 1e-4) * np.maximum(1., np.abs(th))
+            cand = np.tile(th, (4 * n + 1, 1))
+            for i in range(n):
+                for j, mult in enumerate((1., -1., 2., -2.)):
+                    cand[1 + 4 * i + j, i] += mult * h[i]
+            F_, Sigma_, m0, P0, h_ = build_model(transform(torch.as_tensor(cand)))
+            total = filter_nll(method, (F_, Sigma_, h_), H, Xi, m0, P0, dt, ys_t[r])
+            grads.append((8. * (total[1::4] - total[2::4]) - (total[3::4] - total[4::4])) / torch.as_tensor(12 * h, device=dev))
+            vals.append(total[0])
+        return torch.stack(vals), torch.stack(grads)
+
+    if method == 'ekf':
+        return f_adjoint
+    if method in _TANGENT_METHODS:
+        return f_tangent
+    if method == 'ekf_for_kpt':
+        return f_fd
+    raise ValueError('unknown filter %r' % method)
+
+
 def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optional[Callable] = None, maxiter: int = 200,
             reduce_group=None, method: str = 'ekf', sgps=None, fd_step: Optional[float] = None):
     """L-BFGS-B maximum-likelihood fit driving the nll kernels -- the role of
@@ -218,13 +352,13 @@ def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optiona
     build_model(params) -> (drift, dispersion, m_and_cov, m0, P0, H') as chirpgp_b200.models.build_* (for
     method='ekf_for_kpt': (F, Sigma, m0, P0, h) as build_kpt_chirp_model with fs bound, and ``H`` is ignored); ``transform`` maps
     the unconstrained theta to params (default: the reference's softplus ``g``).  The objective is the SUM of the nll over
-    all chirps in ``ys`` (this rank's shard when torch.distributed is initialised: the scalar objective and its 6-vector
-    gradient are then summed over ranks with one all-reduce -- the only collective on this path).
+    all chirps in ``ys`` under ONE parameter vector (this rank's shard when torch.distributed is initialised: the scalar
+    objective and its gradient are then summed over ranks with one all-reduce -- the only collective on this path).  For one
+    independent fit per chirp see ``fit_mle_batched``.
 
-    method='ekf' uses the hand-written adjoint kernel.  The other filters ('sgp_filter' with ``sgps``, 'cd_ekf',
-    'cd_sgp_filter') have no adjoint kernel: their gradient is taken by fourth-order central differences, with all
-    4P + 1 perturbed parameter sets evaluated as ONE candidate batch against the shared signals (nll-only kernels;
-    agreement with jax.grad ~1e-8 relative, tests/test_gpu_mle.py).
+    Gradients are exact for every filter of the reference's MLE demos: method='ekf' uses the hand-written reverse-mode adjoint
+    kernel (csrc/cgp_nll2.cu), 'sgp_filter' (with ``sgps``), 'cd_ekf' and 'cd_sgp_filter' the forward-mode tangent kernels
+    (csrc/cgp_tangent.cu).  Only 'ekf_for_kpt' (KPT model) is differentiated by five-point central differences.
 
     Returns (theta_opt (numpy), scipy OptimizeResult); ``result.success`` follows the reference's convention
     (tetralith/jobs/ekfs_mle.py:49, :75-78: a failed fit is reported, not raised)."""
@@ -235,46 +369,131 @@ def fit_mle(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optiona
     dev = _device()
     ys_t = _as_dev(ys, dev)
     ys2 = ys_t.reshape(-1, ys_t.shape[-1])
+    B = int(ys2.shape[0])
+    rows = torch.arange(B, device=dev)
 
-    def fun_adjoint(theta_np):
-        theta = torch.tensor(theta_np, dtype=_F64, device=dev, requires_grad=True)
-        _, _, m_and_cov, m0, P0, _ = build_model(transform(theta))
-        val = ekf_nll(m_and_cov, H, Xi, m0, P0, dt, ys_t).sum()
-        grad, = torch.autograd.grad(val, theta)
-        v, gr = allreduce_objective(val.detach(), grad, group=reduce_group)
+    if method == 'ekf_for_kpt':
+        per_row = _objective(build_model, H, Xi, dt, ys2, method, sgps, transform, fd_step)
+
+        def shared(theta_np):
+            v, gr = per_row(np.tile(theta_np, (B, 1)), rows)
+            return v.sum(), gr.sum(0)
+    elif method == 'ekf':
+        def shared(theta_np):
+            theta = torch.tensor(theta_np, dtype=_F64, device=dev, requires_grad=True)
+            _, _, m_and_cov, m0, P0, _ = build_model(transform(theta))
+            val = ekf_nll(m_and_cov, H, Xi, m0, P0, dt, ys2).sum()
+            grad, = torch.autograd.grad(val, theta)
+            return val.detach(), grad
+    elif method in _TANGENT_METHODS:
+        def shared(theta_np):
+            v, gr = filter_nll_grad(method, build_model, torch.as_tensor(theta_np), H, Xi, dt, ys2, sgps=sgps, transform=transform)
+            return v.sum(), gr.sum(0)
+    else:
+        raise ValueError('unknown filter %r' % method)
+
+    def fun(theta_np):
+        v, gr = shared(theta_np)
+        v, gr = allreduce_objective(v, gr, group=reduce_group)
         return float(v.cpu()), gr.cpu().numpy().copy()
 
-    def fun_fd(theta_np):
-        # five-point central differences: (-f(+2h) + 8 f(+h) - 8 f(-h) + f(-2h)) / 12h, all 4P + 1 candidates in ONE batch.
-        # On this hardware the candidates cost nothing extra (a single chirp leaves the GPU empty and the candidates run
-        # side by side), and truncation (h^4) and round-off (eps |f| / h) both sit near 1e-8 relative or below.
-        n = theta_np.shape[0]
-        # step: the sigma-point objectives carry ~1e-12 relative summation noise (tests/test_noise_floor.py) and want the larger
-        # step; the EKF-type objectives are smooth to ~1e-15 and take the smaller one (truncation ~ h^4)
-        step = fd_step if fd_step is not None else (2e-3 if method in ('sgp_filter', 'cd_sgp_filter') else 1e-4)
-        h = step * np.maximum(1., np.abs(theta_np))
-        cand = np.tile(theta_np, (4 * n + 1, 1))
-        for i in range(n):
-            for j, mult in enumerate((1., -1., 2., -2.)):
-                cand[1 + 4 * i + j, i] += mult * h[i]
-        built = build_model(transform(torch.as_tensor(cand)))
-        if method == 'ekf_for_kpt':                       # build_kpt_chirp_model: (F, Sigma, m0, P0, h)
-            F_, Sigma_, m0, P0, h_ = built
-            margs = (F_, Sigma_, h_)
-        else:
-            drift, dispersion, m_and_cov, m0, P0, _ = built
-            if method in ('ekf', 'sgp_filter'):
-                margs = (m_and_cov,)
-            else:
-                margs = (drift, dispersion if method == 'cd_ekf' else dispersion.matrix())
-        total = torch.zeros(4 * n + 1, dtype=_F64, device=dev)
-        for row in ys2:                                   # every chirp against the 4P + 1 candidates
-            total = total + filter_nll(method, margs, H, Xi, m0, P0, dt, row, sgps=sgps)
-        grad = (8. * (total[1::4] - total[2::4]) - (total[3::4] - total[4::4])) / torch.as_tensor(12 * h, device=dev)
-        v, gr = allreduce_objective(total[0], grad, group=reduce_group)
-        return float(v.cpu()), gr.cpu().numpy().copy()
-
-    fun = fun_adjoint if method == 'ekf' else fun_fd
     res = scipy.optimize.minimize(fun, np.asarray(init_theta, dtype=np.float64), jac=True, method='L-BFGS-B',
                                   options={'maxiter': maxiter})
     return res.x, res
+
+
+def fit_mle_batched(build_model: Callable, init_theta, H, Xi, dt, ys, transform: Optional[Callable] = None, maxiter: int = 200,
+                    method: str = 'ekf', sgps=None, fd_step: Optional[float] = None, nan_on_failure: bool = True):
+    """One INDEPENDENT L-BFGS-B fit per chirp, all fits advanced in lock-step: what tetralith/jobs/ghfs_mle.py:26-86 (and the
+    other ``*_mle.py`` jobs) run as 100 Monte-Carlo runs x 3 magnitudes of sequential ``ScipyMinimize(...).run(init_theta)``
+    calls.  Every iteration evaluates the objectives and gradients that all still-running optimisers ask for in ONE batched
+    kernel launch (per-chirp parameter vectors: theta (n, P) against ys (n, T)).
+
+    Each fit is driven by SciPy's own L-BFGS-B (one optimiser per chirp on its own Python thread; the threads meet at the
+    objective, where a coordinator gathers the requested points, launches the batch and hands the results back), so every
+    chirp follows exactly the iterates a stand-alone ``fit_mle`` on that chirp would.
+
+    init_theta: (P,) shared start or (B, P).  Returns (thetas (B, P) numpy, results list of scipy OptimizeResult); with
+    ``nan_on_failure`` the rows of failed fits are NaN -- the reference's convention
+    (tetralith/jobs/ekfs_mle.py:49, :75-78: ``if not opt_state.success: params = nan``)."""
+    import threading
+    import scipy.optimize
+    from .models import g as _g
+    transform = transform or _g
+    dev = _device()
+    ys_t = _as_dev(ys, dev)
+    ys2 = ys_t.reshape(-1, ys_t.shape[-1]).contiguous()
+    B = int(ys2.shape[0])
+    init = np.asarray(init_theta, dtype=np.float64)
+    init = np.tile(init, (B, 1)) if init.ndim == 1 else init
+    if init.shape[0] != B:
+        raise ValueError('init_theta has %d rows for %d chirps' % (init.shape[0], B))
+    batch_fun = _objective(build_model, H, Xi, dt, ys2, method, sgps, transform, fd_step)
+
+    cond = threading.Condition()
+    pending, answers, state = {}, {}, {'active': B, 'error': None}
+
+    def worker_fun(i):
+        def fun(theta_np):
+            with cond:
+                pending[i] = np.array(theta_np, dtype=np.float64)
+                cond.notify_all()
+                while i not in answers and state['error'] is None:
+                    cond.wait()
+                if state['error'] is not None:
+                    raise RuntimeError('batched objective failed') from state['error']
+                return answers.pop(i)
+        return fun
+
+    results = [None] * B
+
+    def worker(i):
+        try:
+            results[i] = scipy.optimize.minimize(worker_fun(i), init[i], jac=True, method='L-BFGS-B', options={'maxiter': maxiter})
+        except Exception as exc:  # noqa: BLE001
+            results[i] = exc
+        finally:
+            with cond:
+                state['active'] -= 1
+                cond.notify_all()
+
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(B)]
+    for t in threads:
+        t.start()
+    n_launches = 0
+    while True:
+        with cond:
+            while state['active'] > 0 and len(pending) < state['active']:
+                cond.wait()
+            if state['active'] == 0:
+                break
+            idx = sorted(pending)
+            thetas = np.stack([pending.pop(i) for i in idx])
+        try:
+            with torch.cuda.device(dev):
+                v, gr = batch_fun(thetas, torch.as_tensor(idx, device=dev))
+            v, gr = v.cpu().numpy(), gr.cpu().numpy()
+            n_launches += 1
+            with cond:
+                for j, i in enumerate(idx):
+                    answers[i] = (float(v[j]), gr[j].copy())
+                cond.notify_all()
+        except Exception as exc:  # noqa: BLE001
+            with cond:
+                state['error'] = exc
+                cond.notify_all()
+            break
+    for t in threads:
+        t.join()
+    if state['error'] is not None:
+        raise state['error']
+    for r in results:
+        if isinstance(r, Exception):
+            raise r
+    thetas = np.stack([r.x for r in results])
+    if nan_on_failure:
+        for i, r in enumerate(results):
+            if not r.success:
+                thetas[i] = np.nan
+    fit_mle_batched.last_launches = n_launches
+    return thetas, results

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CGP_ABI_VERSION 2
+#define CGP_ABI_VERSION 3
 
 /* model ids (chirpgp_b200/models.py uses the same numbers) */
 enum {
@@ -134,19 +134,44 @@ int cgp_smoother_sweep_f64(const CgpProblem *p, const double *mfs, const double 
 
 /* ---- MLE path: EKF negative log-likelihood without per-step outputs, and its reverse-mode adjoint
  * (jax.grad of `ekf(...)[-1][-1]`, demos/ekfs_mle.py:42-49, tetralith/jobs/ekfs_mle.py:41-48).  LCD models only.
+ * Persistent, ticket-scheduled kernels (csrc/cgp_nll2.cu): 32 problems form a chain, time is cut into segments of
+ * `ckpt_every` steps, and warps pick (chain, segment) units from a global counter -- any number of problems keeps every SM
+ * sub-partition equally busy.  The covariance is carried as its packed lower triangle (exactly symmetric arithmetic).
  *   fwd: nll [B] = final cumulative negative log-likelihood.  With a workspace, (m, P) checkpoints are stored every
- *        `ckpt_every` steps for the adjoint; workspace == NULL gives a pure objective evaluation.
+ *        `ckpt_every` steps for the adjoint; workspace == NULL gives a pure objective evaluation (one unit per chain).
  *   bwd: given nll_bar [B] (NULL = ones) and the workspace filled by fwd (same problem, same ckpt_every), returns the
  *        cotangents of the kernel inputs: consts_bar [B, CGP_NC_LCD], m0_bar [B, d], P0_bar [B, d, d] (general matrix,
  *        JAX's unsymmetrised convention), Xi_bar [B] (may be NULL).  Shared inputs (stride 0) get per-problem
- *        cotangents that the caller sums.  */
-int64_t cgp_ekf_nll_default_ckpt(int64_t T);                       /* ~ sqrt(T) */
+ *        cotangents that the caller sums.
+ *   bwd_sym: the same with P0_bar symmetrised, (X + X^T)/2 of the above -- identical for every use in which P0 is a
+ *        symmetric-matrix-valued function of the parameters (all callers of the reference), and ~10 % cheaper: the
+ *        antisymmetric part of the covariance cotangent feeds nothing but itself and is not tracked.
+ * The workspace is read and written by both calls (checkpoints, scheduling words, per-warp scratch); one workspace serves one
+ * fwd / bwd pair at a time.  Its size depends on the current CUDA device (number of SMs). */
+int64_t cgp_ekf_nll_default_ckpt(int64_t T);                       /* min(32, ~sqrt(T)) */
 size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every);
 int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void *workspace, size_t workspace_bytes,
                         int64_t ckpt_every, void *stream);
 int cgp_ekf_nll_bwd_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace,
                         size_t workspace_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,
                         double *Xi_bar, void *stream);
+int cgp_ekf_nll_bwd_sym_f64(const CgpProblem *p, const double *ys, const double *nll_bar, void *workspace,
+                            size_t workspace_bytes, int64_t ckpt_every, double *consts_bar, double *m0_bar, double *P0_bar,
+                            double *Xi_bar, void *stream);
+
+/* ---- forward-mode derivative of the nll of ANY filter on the path (csrc/cgp_tangent.cu): what jax.grad of
+ * `sgp_filter(...)[-1][-1]`, `cd_ekf(...)[-1][-1]`, `cd_sgp_filter(...)[-1][-1]` (and `ekf`) computes in demos/ghfs_mle.py:54-61,
+ * demos/cd_ekfs_mle.py, demos/cd_ghfs_mle.py.  `filter` is one of "ekf", "sgp_filter" (model CGP_MODEL_LCD), "cd_ekf",
+ * "cd_sgp_filter" (model CGP_MODEL_SDE, p->Qc set); sigma tables in p for the sigma-point filters.  For each of the n_dir
+ * parameter directions k the caller passes the tangents of the kernel inputs (any pointer may be NULL = zero tangent):
+ *   consts_dot [B|1, n_dir, NC], m0_dot [B|1, n_dir, d], P0_dot [B|1, n_dir, d, d] (symmetrised on load),
+ *   Qc_dot [B|1, n_dir, d, d], Xi_dot [n_dir];  the *_stride arguments are per-problem strides in doubles (0 = shared).
+ * Outputs: nll [B] (may be NULL) and nll_dot [B, n_dir] = d nll / d direction_k.  One group of lanes per (problem, direction);
+ * no workspace. */
+int cgp_filter_nll_tangent_f64(const char *filter, const CgpProblem *p, const double *ys, int n_dir,
+                               const double *consts_dot, int64_t consts_dot_stride, const double *m0_dot, int64_t m0_dot_stride,
+                               const double *P0_dot, int64_t P0_dot_stride, const double *Qc_dot, int64_t Qc_dot_stride,
+                               const double *Xi_dot, double *nll, double *nll_dot, void *stream);
 
 /* ---- post-processing right after the smoothers: chirpgp.quadratures.gaussian_expectation (quadratures.py:234-274) for its
  * default integrand g (softplus, models.py:50) and d = 1 -- the frequency estimate E[g(V_k)], V_k ~ N(ms_k, chol_k^2), every

@@ -142,6 +142,12 @@ def nonlinear_case(name, builder, params, T, dt, ys, sigmas, with_grad, num_harm
                 return fs.sgp_filter(mc, sg, H_, Xi, m0_, P0_, dt, ys_t)[-1][-1]
 
             out['grad_sgp_filter_' + tag] = npy(jax.grad(obj_sgp)(theta))
+
+            def obj_cd_sgp(th, sg=sg):                      # demos/cd_ghfs_mle.py:46-58
+                dr, di, _, m0_, P0_, H_ = builder(md.g(th))
+                return fs.cd_sgp_filter(dr, di(jnp.eye(d)), sg, H_, Xi, m0_, P0_, dt, ys_t)[-1][-1]
+
+            out['grad_cd_sgp_filter_' + tag] = npy(jax.grad(obj_cd_sgp)(theta))
     save(name, **out)
 
 

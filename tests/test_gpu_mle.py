@@ -77,15 +77,45 @@ def test_cotangents_of_every_kernel_input_vs_autodiff_twin():
         def consts(self, dt):
             return self._c
 
-    c2 = consts.detach().clone().requires_grad_(True)
-    m2, P2 = m0.clone().requires_grad_(True), P0.clone().requires_grad_(True)
-    X2 = torch.tensor(0.1, dtype=torch.float64, requires_grad=True)
-    got = mle.ekf_nll(_M(c2), H, X2, m2, P2, dt, ys, ckpt_every=7)
-    gg = torch.autograd.grad(got, [c2, m2, P2, X2])
-    npt.assert_allclose(got.item(), want.item(), rtol=1e-11)
-    for a, b, nm in zip(gg, gw, ['consts', 'm0', 'P0', 'Xi']):
-        npt.assert_allclose(a.cpu().numpy()[..., :9] if nm == 'consts' else a.cpu().numpy(),
-                            b.numpy()[..., :9] if nm == 'consts' else b.numpy(), rtol=1e-7, atol=1e-9, err_msg=nm)
+    for raw in (True, False):
+        c2 = consts.detach().clone().requires_grad_(True)
+        m2, P2 = m0.clone().requires_grad_(True), P0.clone().requires_grad_(True)
+        X2 = torch.tensor(0.1, dtype=torch.float64, requires_grad=True)
+        got = mle.ekf_nll(_M(c2), H, X2, m2, P2, dt, ys, ckpt_every=7, raw_p0_cotangent=raw)
+        gg = torch.autograd.grad(got, [c2, m2, P2, X2])
+        npt.assert_allclose(got.item(), want.item(), rtol=1e-11)
+        for a, b, nm in zip(gg, gw, ['consts', 'm0', 'P0', 'Xi']):
+            a, b = a.cpu().numpy(), b.numpy()
+            if nm == 'consts':
+                a, b = a[..., :9], b[..., :9]
+            if nm == 'P0' and not raw:                     # default: the symmetrised covariance cotangent
+                b = 0.5 * (b + b.T)
+            npt.assert_allclose(a, b, rtol=1e-7, atol=1e-9, err_msg='%s raw=%s' % (nm, raw))
+    assert np.abs(gw[2].numpy() - gw[2].numpy().T).max() > 1e-3    # the case does exercise the antisymmetric part
+
+
+def test_general_measurement_row_and_ragged_chains():
+    """H that is not a unit vector (generic kernel instance), a number of problems that is not a multiple of the 32-problem
+    chain, several segments per chain, against the filter kernel and central differences."""
+    B, T, dt = 37, 300, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, 3141, dt, Xi=0.1, seed=11)
+    ys = ys[:, 700:700 + T]
+    Hrow = np.array([0.3, 1., 0., 0.2])
+    theta0 = np.log(np.exp(np.array([0.2, 0.15, 0.1, 1.1, 0.9, 6.5])) - 1.)
+    val, grad = _theta_grad(cg.build_chirp_model, theta0, Hrow, 0.1, dt, ys, ckpt_every=16)
+    _, _, mc, m0, P0, _ = cg.build_chirp_model(gfun(torch.tensor(theta0)))
+    f = cg.ekf(mc, Hrow, 0.1, m0, P0, dt, ys)
+    npt.assert_allclose(val, f[2][:, -1], rtol=1e-11)
+    fd = np.zeros(6)
+    for i in range(6):
+        h = 1e-5 * max(1., abs(theta0[i]))
+        v = []
+        for sgn in (1., -1.):
+            th = theta0.copy(); th[i] += sgn * h
+            _, _, mc1, m01, P01, _ = cg.build_chirp_model(gfun(torch.tensor(th)))
+            v.append(float(mle.ekf_nll(mc1, Hrow, 0.1, m01, P01, dt, ys).sum()))
+        fd[i] = (v[0] - v[1]) / (2 * h)
+    npt.assert_allclose(grad, fd, rtol=1e-5, atol=1e-6)
 
 
 def test_candidate_grid_and_fit():
@@ -108,38 +138,75 @@ def test_candidate_grid_and_fit():
                                        *cg.build_chirp_model(gfun(torch.tensor(theta0)))[3:5], dt, ys[:1]).sum())
 
 
-def test_fd_gradient_mle_for_sigma_point_and_cd_filters(golden):
+def _builder(name):
+    return cg.build_chirp_model if name == 'chirp' else (lambda p: cg.build_harmonic_chirp_model(p, num_harmonics=3))
+
+
+@pytest.mark.parametrize('name,method,tag', [
+    ('chirp', 'ekf', None), ('chirp', 'cd_ekf', None), ('chirp', 'sgp_filter', 'gh3'), ('chirp', 'sgp_filter', 'cub'),
+    ('chirp', 'cd_sgp_filter', 'gh3'), ('chirp', 'cd_sgp_filter', 'cub'),
+    ('harmonic', 'ekf', None), ('harmonic', 'cd_ekf', None), ('harmonic', 'sgp_filter', 'cub'), ('harmonic', 'cd_sgp_filter', 'cub'),
+])
+def test_tangent_kernels_match_reference_jax_grad(golden, name, method, tag):
     """The MLE demos of the sigma-point / continuous-discrete filters (demos/ghfs_mle.py:54-61, cd_ekfs_mle.py,
-    cd_ghfs_mle.py) take jax.grad of their nll; here those objectives are differentiated by five-point central differences
-    over a candidate batch.  Check objective and gradient against the reference's jax.grad fixtures."""
-    z = golden('chirp')
-    H, Xi, dt, ys = z['H'], float(z['Xi']), float(z['dt']), z['ys']
+    cd_ghfs_mle.py) take jax.grad of their nll.  Forward-mode tangent kernels vs the gradients the reference's own sources
+    produce (fixtures): value rtol 1e-10, gradient rtol 1e-7."""
+    z = golden(name)
+    key = method if tag is None else '%s_%s' % (method, tag)
+    if 'grad_' + key not in z:
+        pytest.skip('fixture has no grad_%s' % key)
+    d = int(z['m0'].shape[0])
+    sgps = None
+    if tag is not None:
+        sgps = cg.SigmaPoints.gauss_hermite(d, 3) if tag == 'gh3' else cg.SigmaPoints.cubature(d)
+    val, grad = mle.filter_nll_grad(method, _builder(name), z['theta'], z['H'], float(z['Xi']), float(z['dt']), z['ys'], sgps=sgps)
+    npt.assert_allclose(val.cpu().numpy()[0], z[key + '_2'][-1], rtol=1e-10)
+    npt.assert_allclose(grad.cpu().numpy()[0], z['grad_' + key], rtol=1e-7, atol=1e-9)
+
+
+def test_tangent_kernel_per_chirp_parameters_and_fit_mle():
+    """theta (B, P): one parameter vector per chirp in one launch == B separate launches; fit_mle on the exact gradients."""
+    B, T, dt = 5, 200, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, 3141, dt, Xi=0.1, seed=21)
+    ys = ys[:, 900:900 + T]
+    rng = np.random.default_rng(5)
+    theta0 = np.log(np.exp(np.array([0.1, 0.1, 0.1, 1., 1., 7.])) - 1.)
+    thetas = theta0 + 0.05 * rng.standard_normal((B, 6))
+    H = np.array([0., 1., 0., 0.])
     sg = cg.SigmaPoints.gauss_hermite(4, 3)
-    cases = [('sgp_filter', sg, z['grad_sgp_filter_gh3'], z['sgp_filter_gh3_2'][-1]),
-             ('cd_ekf', None, z['grad_cd_ekf'], z['cd_ekf_2'][-1])]
-    for method, sgps, want_grad, want_val in cases:
-        calls = []
+    for method, sgps in (('sgp_filter', sg), ('cd_ekf', None)):
+        v, gr = mle.filter_nll_grad(method, cg.build_chirp_model, thetas, H, 0.1, dt, ys, sgps=sgps)
+        for i in (0, B - 1):
+            v1, g1 = mle.filter_nll_grad(method, cg.build_chirp_model, thetas[i], H, 0.1, dt, ys[i], sgps=sgps)
+            npt.assert_allclose(v[i].item(), v1[0].item(), rtol=1e-14)
+            npt.assert_allclose(gr[i].cpu().numpy(), g1[0].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    theta, res = mle.fit_mle(cg.build_chirp_model, theta0, H, 0.1, dt, ys[:2], method='sgp_filter', sgps=sg, maxiter=8)
+    v0, _ = mle.filter_nll_grad('sgp_filter', cg.build_chirp_model, theta0, H, 0.1, dt, ys[:2], sgps=sg)
+    assert res.fun < float(v0.sum())
 
-        def spy(fun, x0, jac, method, options):
-            v, gr = fun(np.asarray(x0))
-            calls.append((v, gr))
 
-            class R:
-                x, success = np.asarray(x0), True
-                fun_ = v
-            return R()
-
-        import scipy.optimize
-        orig = scipy.optimize.minimize
-        scipy.optimize.minimize = spy
-        try:
-            mle.fit_mle(cg.build_chirp_model, z['theta'], H, Xi, dt, ys, method=method, sgps=sgps)
-        finally:
-            scipy.optimize.minimize = orig
-        v, gr = calls[0]
-        npt.assert_allclose(v, want_val, rtol=1e-10)
-        # measured: 2.8e-7 (sgp_filter) -- the floor is the nll's own rounding noise (~1e-12 relative) divided by h
-        npt.assert_allclose(gr, want_grad, rtol=2e-6, atol=1e-7)
+def test_fit_mle_batched_follows_the_sequential_fits():
+    """tetralith/jobs/ekfs_mle.py:26-86 runs one L-BFGS-B fit per Monte-Carlo chirp; fit_mle_batched advances all of them in
+    lock-step with one batched nll / gradient launch per iteration.  Each chirp must reach the optimum its own sequential
+    fit_mle reaches (same SciPy optimiser, same objective values: the iterates coincide)."""
+    B, T, dt = 24, 300, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, 3141, dt, Xi=0.1, seed=31)
+    ys = ys[:, 1200:1200 + T]
+    theta0 = np.log(np.exp(np.array([0.1, 0.1, 0.1, 1., 1., 7.])) - 1.)
+    H = np.array([0., 1., 0., 0.])
+    thetas, results = mle.fit_mle_batched(cg.build_chirp_model, theta0, H, 0.1, dt, ys, maxiter=12, nan_on_failure=False)
+    assert thetas.shape == (B, 6)
+    launches = mle.fit_mle_batched.last_launches
+    assert launches <= max(r.nfev for r in results)          # lock-step: one launch serves every running fit
+    for i in (0, 7, 23):
+        th_i, res_i = mle.fit_mle(cg.build_chirp_model, theta0, H, 0.1, dt, ys[i:i + 1], maxiter=12)
+        npt.assert_allclose(thetas[i], th_i, rtol=1e-9, atol=1e-12)
+        npt.assert_allclose(results[i].fun, res_i.fun, rtol=1e-12)
+        assert results[i].nit == res_i.nit
+    # NaN convention of the reference for failed fits
+    th_nan, res_nan = mle.fit_mle_batched(cg.build_chirp_model, theta0, H, 0.1, dt, ys[:3], maxiter=1)
+    for row, r in zip(th_nan, res_nan):
+        assert np.all(np.isnan(row)) == (not r.success)
 
 
 def test_kpt_mle_objective_and_gradient(golden):
