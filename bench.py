@@ -33,10 +33,30 @@ PARAMS = [0.1, 0.1, 0.1, 1., 1., 7.]
 D = 4
 N_SIGMA = 81
 METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
+WORKLOAD = ('configs[1]: 1000 toymodel chirps per GPU x T=3141, dt=1e-3, chirp model d=4, sgp_filter + sgp_smoother with '
+            'gauss_hermite(d=4, order=3) (81 points)')
 UNIT = 'steps/s'
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one gh_duo_filter_kernel launch (ncu --set full, profiles/r1_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 1_401_431_000    # 26.7 MB read + 1374.8 MB written: 552.8 MB algorithmic + 904.6 MB smoother workspace
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel: read from the committed ncu capture of
+# this very command (`ncu --set full`, raw page as CSV; see profiles/README.md), never a literal
+NCU_RAW_CSV = os.path.join(ROOT, 'profiles', 'r2_ncu_headline_raw.csv')
+
+
+def ncu_traffic_bytes(kernel_substr: str):
+    """(bytes per launch, source) of the first kernel whose name contains `kernel_substr` in the committed ncu raw CSV."""
+    import csv
+    try:
+        rows = list(csv.reader(open(NCU_RAW_CSV)))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+        scale = {'byte': 1., 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return (float(r[ir]) * scale.get(units[ir], 1.) + float(r[iw]) * scale.get(units[iw], 1.),
+                        os.path.relpath(NCU_RAW_CSV, ROOT))
+    except Exception:  # noqa: BLE001
+        pass
+    return None, None
 
 # algorithmic bytes / flops per chirp time-step (SURVEY 8d; DESIGN.md "Roofline accounting")
 BYTES_FILTER = 8 + 8 * (D + D * D + 1)          # ys in, mf + Pf + nell out                      = 176
@@ -47,17 +67,34 @@ FLOPS_SMOOTHER = 13668                          # sgp_smoother
 
 
 def flops_per_step(variant: str, d: int = 4, n: int = 81) -> int:
-    """Counting convention v1 of SURVEY 8(d) for the chirp model (dense d x d algebra, FMA = 2 flops,
-    every exp/log/sin/cos/sqrt/div = 1 flop)."""
+    """Counting convention v1 of SURVEY 8(d) (dense d x d algebra, no symmetry / sparsity credit, FMA = 2 flops, every
+    exp / log / sin / cos / sqrt / div = 1 flop); model cost constants of the chirp family as tabulated there."""
     U = 7 * d * d + 7 * d + 9
     CH = d ** 3 / 3 + d * d
-    c_pt = 21
+    harmonic = d > 4
+    c = 80 if harmonic else 35           # LCD mean + Jacobian
+    c_pt = 53 if harmonic else 21        # LCD mean per sigma point
+    c_a, c_a_pt = 25, 12                 # drift + Jacobian, drift per sigma point
     SP = CH + n * (2 * d * d + d) + n * c_pt + 2 * n * d + 3 * n * d * d + 4 * d * d
-    if variant == 'sgp_filter':
-        return int(round(SP + U))
-    if variant == 'sgp_smoother':
-        return int(round(SP + 3 * n * d * d + 2 * d * d + CH + 2 * d ** 3 + (2 * d * d + 2 * d) + 4 * d ** 3 + 2 * d * d))
-    raise ValueError(variant)
+    ST = CH + n * (2 * d * d + d) + n * c_a_pt + 2 * n * d + n * d + 3 * n * d * d + 2 * d * d
+    table = {
+        'ekf': c + 4 * d ** 3 + d * d + U,
+        'eks': c + 4 * d ** 3 + d * d + 2 * d ** 3 + CH + 2 * d ** 3 + (2 * d * d + 2 * d) + 4 * d ** 3 + 2 * d * d,
+        'sgp_filter': SP + U,
+        'sgp_smoother': SP + 3 * n * d * d + 2 * d * d + CH + 2 * d ** 3 + (2 * d * d + 2 * d) + 4 * d ** 3 + 2 * d * d,
+        'cd_ekf': 4 * (c_a + 4 * d ** 3 + 2 * d * d + 2 * (d + d * d)) + 6 * (d + d * d) + U,
+        'cd_eks': CH + 2 * d ** 3 + 4 * (c_a + d * d + 4 * d * d + 4 * d ** 3 + 2 * d * d + 2 * (d + d * d)) + 6 * (d + d * d),
+        'cd_sgp_filter': 4 * ST + 6 * (d + d * d) + U,
+        'cd_sgp_smoother': 4 * ST + 6 * (d + d * d) + 4 * (4 * d ** 3 + 4 * d * d) + CH + 2 * d ** 3,
+    }
+    if variant not in table:
+        raise ValueError(variant)
+    return int(round(table[variant]))
+
+
+def bytes_per_smoothed_step(d: int) -> int:
+    """Algorithmic HBM bytes of one filter + smoother step: ys in, (mf, Pf, nell) out; (mf, Pf) in, (ms, Ps) out."""
+    return 8 + 8 * (d + d * d + 1) + 2 * 8 * (d + d * d)
 
 
 def synthetic_inputs(rank: int):
@@ -161,13 +198,206 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * statistics.mean(secs), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: 1000 toymodel chirps x T=3141, GHF+GHS (gauss_hermite d=4 order 3)',
-                   'sample': sample},
+        'config': {'workload': WORKLOAD, 'sample': sample},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'JAX not installable here: CPU arm = oracle/ C restatement of the reference algorithm (proxy)',
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ the other BASELINE configs
+def _cpu_rate(fn, n_small, target_s, unit_steps):
+    """Times fn(n) (oracle on n chirps) on a bounded sample sized for ~target_s of CPU work; returns (steps/s, n, seconds)."""
+    fn(max(2, n_small // 4))                                     # spin up the OpenMP team
+    t0 = time.perf_counter(); fn(n_small); dt = time.perf_counter() - t0
+    n = int(max(n_small, min(50 * n_small, n_small * target_s / max(dt, 1e-6))))
+    t0 = time.perf_counter(); fn(n); dt = time.perf_counter() - t0
+    return n * unit_steps / dt, n, dt
+
+
+def run_other_configs(dev, fp64_peak, hbm_peak, with_cpu, flush):
+    """BASELINE.json configs[0], [2], [3] on this GPU: filter + smoother time (CUDA events, L2
+    flushed, mean of 3 after warm-up), the two roofline fractions of SURVEY 8d, and the oracle's CPU rate beside each."""
+    import torch
+    import chirpgp_b200 as cg
+    from chirpgp_b200 import toymodels
+    out = []
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    threads = len(os.sched_getaffinity(0))
+
+    def timed(filt, smooth, reps=3):
+        for _ in range(2):
+            f = filt(); sm = smooth(f); del f, sm
+        tf, ts = [], []
+        for _ in range(reps):
+            flush.fill_(1.)
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record(); f = filt(); e1.record(); sm = smooth(f); e2.record()
+            torch.cuda.synchronize(dev)
+            tf.append(e0.elapsed_time(e1)); ts.append(e1.elapsed_time(e2))
+            del f, sm
+        return statistics.mean(tf), statistics.mean(ts)
+
+    def entry(config, what, B, d, n, variants, tf, ts, cpu):
+        steps = B * T
+        fl = sum(flops_per_step(v, d, n) for v in variants)
+        sec = (tf + ts) * 1e-3
+        e = {'config': config, 'workload': what, 'filter_ms': tf, 'smoother_ms': ts, 'value': steps / sec, 'unit': UNIT,
+             'flops_per_step': fl, 'bytes_per_step': bytes_per_smoothed_step(d),
+             'fp64_tflops': steps * fl / sec / 1e12, 'fp64_frac': steps * fl / sec / 1e12 / fp64_peak if fp64_peak else None,
+             'hbm_gbs': steps * bytes_per_smoothed_step(d) / sec / 1e9,
+             'hbm_frac': steps * bytes_per_smoothed_step(d) / sec / 1e9 / hbm_peak, 'cpu_baseline': cpu}
+        if B == 1:
+            e['us_per_step'] = sec * 1e6 / T
+            e['note'] = 'single chirp: latency-bound, report us/step (SURVEY 8d)'
+        return e
+
+    from oracle import oracle as orc
+    params = np.array(PARAMS)
+    spec = orc.ChirpSpec(PARAMS[0], PARAMS[1], PARAMS[3], PARAMS[4])
+    m0o, P0o, Ho = orc.chirp_m0_P0_H(PARAMS[2], PARAMS[3], PARAMS[4], PARAMS[5])
+    drift, disp, mc, m0, P0, H = cg.build_chirp_model(params)
+    m0, P0, H = m0.to(dev), P0.to(dev), H.to(dev)
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    _, ys_all, _ = toymodels.synthetic_batch(B_PER_GPU, T, DT, Xi=XI, seed=2)
+
+    def cpu_of(fn, n_small, target=3.):
+        if not with_cpu:
+            return None
+        rate, n, sec = _cpu_rate(fn, n_small, target, T)
+        return {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                'sample': '%d chirps x %d steps, oracle/ C restatement with OpenMP (%.1f s)' % (n, T, sec)}
+
+    def tile(n):
+        return ys_all if n <= ys_all.shape[0] else np.tile(ys_all, (-(-n // ys_all.shape[0]), 1))
+
+    # ---- config 1: single chirp, EKF + EKS
+    _, y1, _ = toymodels.synthetic_batch(1, T, DT, Xi=XI, seed=1)
+    y1d = torch.as_tensor(y1[0]).to(dev)
+    tf, ts = timed(lambda: cg.ekf(mc, H, XI, m0, P0, DT, y1d), lambda f: cg.eks(mc, f[0], f[1], DT))
+
+    def cpu1(n):
+        f = orc.ekf(spec, Ho, XI, m0o, P0o, DT, tile(n)[:n], nthreads=threads)
+        orc.eks(spec, f[0], f[1], DT, nthreads=threads)
+    out.append(entry(1, 'configs[0]: single toymodel chirp x T=%d, ekf + eks, d=4' % T, 1, 4, 0, ('ekf', 'eks'), tf, ts,
+                     cpu_of(cpu1, 256)))
+    # ---- config 3: continuous-discrete, 1000 chirps
+    ysd = torch.as_tensor(ys_all).to(dev)
+    tf, ts = timed(lambda: cg.cd_ekf(drift, disp, H, XI, m0, P0, DT, ysd), lambda f: cg.cd_eks(drift, disp, f[0], f[1], DT))
+    Bm = spec.dispersion_matrix()
+
+    def cpu3a(n):
+        f = orc.cd_ekf(spec, Bm, Ho, XI, m0o, P0o, DT, tile(n)[:n], nthreads=threads)
+        orc.cd_eks(spec, Bm, f[0], f[1], DT, nthreads=threads)
+    out.append(entry(3, 'configs[2]: %d chirps x T=%d, cd_ekf + cd_eks (one RK4 step per sample)' % (B_PER_GPU, T), B_PER_GPU, 4,
+                     0, ('cd_ekf', 'cd_eks'), tf, ts, cpu_of(cpu3a, 128)))
+    bm = disp(None)
+    tf, ts = timed(lambda: cg.cd_sgp_filter(drift, bm, sg, H, XI, m0, P0, DT, ysd),
+                   lambda f: cg.cd_sgp_smoother(drift, bm, sg, f[0], f[1], DT))
+
+    def cpu3b(n):
+        f = orc.cd_sgp_filter(spec, Bm, sg, Ho, XI, m0o, P0o, DT, tile(n)[:n], nthreads=threads)
+        orc.cd_sgp_smoother(spec, Bm, sg, f[0], f[1], DT, nthreads=threads)
+    out.append(entry(3, 'configs[2]: %d chirps x T=%d, cd_sgp_filter + cd_sgp_smoother, gauss_hermite(4, 3)' % (B_PER_GPU, T),
+                     B_PER_GPU, 4, 81, ('cd_sgp_filter', 'cd_sgp_smoother'), tf, ts, cpu_of(cpu3b, 16)))
+    # ---- config 4: harmonic model d = 8, cubature
+    _, ys4, _ = toymodels.synthetic_batch(B_PER_GPU, T, DT, num_harmonics=3, seed=4)
+    ys4d = torch.as_tensor(ys4).to(dev)
+    _, _, mc4, m04, P04, H4 = cg.build_harmonic_chirp_model(params, num_harmonics=3)
+    m04, P04, H4 = m04.to(dev), P04.to(dev), H4.to(dev)
+    sg4 = cg.SigmaPoints.cubature(8)
+    tf, ts = timed(lambda: cg.sgp_filter(mc4, sg4, H4, XI, m04, P04, DT, ys4d), lambda f: cg.sgp_smoother(mc4, sg4, f[0], f[1], DT))
+    spec4 = orc.ChirpSpec(PARAMS[0], PARAMS[1], PARAMS[3], PARAMS[4], num_harmonics=3)
+    m0o4, P0o4, Ho4 = orc.chirp_m0_P0_H(PARAMS[2], PARAMS[3], PARAMS[4], PARAMS[5], num_harmonics=3, kind='harmonic')
+
+    def cpu4(n):
+        yy = ys4 if n <= ys4.shape[0] else np.tile(ys4, (-(-n // ys4.shape[0]), 1))
+        f = orc.sgp_filter(spec4, sg4, Ho4, XI, m0o4, P0o4, DT, yy[:n], nthreads=threads)
+        orc.sgp_smoother(spec4, sg4, f[0], f[1], DT, nthreads=threads)
+    out.append(entry(4, 'configs[3]: %d harmonic chirps (3 harmonics, d=8) x T=%d, sgp_filter + sgp_smoother, cubature(8)'
+                     % (B_PER_GPU, T), B_PER_GPU, 8, 16, ('sgp_filter', 'sgp_smoother'), tf, ts, cpu_of(cpu4, 32)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ config 5: the MLE sweep
+MLE_CHIRPS, MLE_T, MLE_G = 10000, 100000, 16
+
+
+def run_mle_sweep(world, rank, dev, fp64_peak, chirps=MLE_CHIRPS, T5=MLE_T, reps=2):
+    """BASELINE.json configs[4]: EKF nll + adjoint gradient of 10 000 chirps x 16 hyper-parameter candidates
+    x T = 1e5, chirps sharded over the ranks (STRONG scaling: the total is fixed), one NCCL all-reduce of the 16 x (1 + 6)
+    objective / gradient block per evaluation -- the only collective on the path (demos/ekfs_mle.py:42-49,
+    tetralith/run_crlbs.sh:1-2)."""
+    import torch
+    import torch.distributed as dist
+    import chirpgp_b200 as cg
+    from chirpgp_b200 import mle
+    from chirpgp_b200.distributed import shard_range, allreduce_objective
+    from chirpgp_b200.models import g as gfun
+    dt5 = 3.141 / T5                                        # total duration < pi keeps toymodels.meow_freq valid
+    lo, hi = shard_range(chirps, rank, world)
+    nloc = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ts_ = torch.linspace(dt5, dt5 * T5, T5, dtype=torch.float64, device=dev)
+    phase = 500 * torch.exp(-5 / torch.sin(ts_)) + 8 * ts_
+    ys = torch.sin(2 * np.pi * phase)[None, :].repeat(nloc, 1)
+    for i in range(0, nloc, 256):                           # noise in slabs: no second 8 GB temporary
+        ys[i:i + 256] += np.sqrt(XI) * torch.randn((min(256, nloc - i), T5), dtype=torch.float64, device=dev, generator=gen)
+    lam = np.array([0.1, 0.4, 0.7, 1.0]); bb = np.array([0.05, 0.1, 0.2, 0.4])
+    grid = np.array([[l, b_, 0.1, 1., 1., 7.] for l in lam for b_ in bb])
+    theta = torch.tensor(np.log(np.exp(grid) - 1.), dtype=torch.float64, device=dev, requires_grad=True)
+    H = np.array([0., 1., 0., 0.])
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def objective(marks=None):
+        _, _, mc, m0, P0, _ = cg.build_chirp_model(gfun(theta))
+        nll = mle.ekf_nll(mc, H, XI, m0, P0, dt5, ys, candidates=True)              # (nloc, G): forward kernel
+        val = nll.sum(dim=0)
+        grad, = torch.autograd.grad(val.sum(), theta)                               # adjoint kernel; rows independent
+        if marks is not None:
+            marks[0].record()
+        out = allreduce_objective(val.detach(), grad)                               # G x (1 + 6) doubles, one NCCL call
+        if marks is not None:
+            marks[1].record()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    objective()
+    barrier()
+    ms, ms_ar = [], []
+    for _ in range(reps):
+        e0, e1, ea, eb = ev(), ev(), ev(), ev()
+        barrier()
+        e0.record()
+        val, grad = objective((ea, eb))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1)); ms_ar.append(ea.elapsed_time(eb))
+    t = torch.tensor([statistics.mean(ms), statistics.mean(ms_ar)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_eval, ms_allreduce = float(t[0]), float(t[1])
+    steps = chirps * MLE_G * T5
+    fl = 3 * flops_per_step('ekf')
+    free, total = torch.cuda.mem_get_info(dev)
+    res = {'workload': 'configs[4]: EKF nll + adjoint gradient, %d chirps x %d candidates x T=%d, chirps sharded x%d'
+                       % (chirps, MLE_G, T5, world),
+           'metric': 'nll+gradient chirp time-steps/sec (B x G x T)', 'value': steps / (ms_eval * 1e-3), 'unit': UNIT,
+           'n_gpus': world, 'scaling': 'strong', 'ms_per_evaluation': ms_eval, 'ms_in_allreduce': ms_allreduce,
+           'evaluations_timed': reps, 'problems_per_gpu': nloc * MLE_G,
+           'collective': 'one all-reduce of %d x (1 + 6) doubles per evaluation (NCCL)' % MLE_G,
+           'flops_per_step': fl, 'flops_convention': '3 x flops_per_step(ekf): forward + recomputation + adjoint (SURVEY 8d v1)',
+           'fp64_tflops_per_gpu': steps * fl / (ms_eval * 1e-3) / 1e12 / world,
+           'fp64_frac': steps * fl / (ms_eval * 1e-3) / 1e12 / world / fp64_peak if fp64_peak else None,
+           'nll_sum': float(val.sum()), 'grad_norm': float(grad.norm()), 'hbm_in_use_gb': (total - free) / 1e9}
+    del ys
+    torch.cuda.empty_cache()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -193,13 +423,7 @@ def run_ours(args):
     _, _, m_and_cov, m0, P0, H = cg.build_chirp_model(np.array(PARAMS))
     sgps = cg.SigmaPoints.gauss_hermite(d=D, order=3)
     m0, P0, H = m0.to(dev), P0.to(dev), H.to(dev)
-    mss_host = torch.empty((B_PER_GPU, T, D), dtype=torch.float64).pin_memory()
-    Pss_host = torch.empty((B_PER_GPU, T, D, D), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
-
-    def step():
-        f = cg.sgp_filter(m_and_cov, sgps, H, XI, m0, P0, DT, ys)
-        return f, None
 
     def barrier():
         if world > 1:
@@ -259,59 +483,43 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     ms_pipe = e0.elapsed_time(e1) / n_pipe
 
-    # ---- end-to-end through the public API: every step copies its inputs from pinned host memory, filters, smooths and
-    # copies the smoothed means / covariances back to pinned host memory.  Steps are issued on two alternating CUDA
-    # streams (what a user who processes batch after batch does), so the device->host copy of step i overlaps the
-    # filter of step i+1; all copies of all steps are inside the timed region.
+    # ---- end-to-end through the PRODUCT API, host buffers in, host buffers out, every copy inside the timed region:
+    #   e2e            cg.sgp_filter_smoother(..., ys_host, readout=('freq', 'v_var')): the posterior frequency estimate
+    #                  E[g(V_k)] and the marginal variance -- what the demos / jobs compute from the smoother output right
+    #                  afterwards (demos/ghfs_mle.py:87-89, quadratures.py:234-274) -- 16 bytes per step come back;
+    #   e2e_full       the same call returning all of (mss, Pss): 160 bytes per step come back (PCIe-bound);
+    #   e2e_numpy_api  the literal drop-in: NumPy in, sgp_filter then sgp_smoother as two calls, NumPy out.
+    # Blocking calls issued back to back on the default stream (what `for batch in batches: f(batch)` does).
     n_e2e = max(4, min(args.steps, 10))
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    outs = [(mss_host, Pss_host),
-            (torch.empty((B_PER_GPU, T, D), dtype=torch.float64).pin_memory(),
-             torch.empty((B_PER_GPU, T, D, D), dtype=torch.float64).pin_memory())]
+    H_h, m0_h, P0_h = H.cpu(), m0.cpu(), P0.cpu()
 
-    def e2e_step(i):
-        st = streams[i % 2]
-        with torch.cuda.stream(st):
-            ys_d = ys_host.to(dev, non_blocking=True)
-            f = cg.sgp_filter(m_and_cov, sgps, H, XI, m0, P0, DT, ys_d)
-            s = cg.sgp_smoother(m_and_cov, sgps, f[0], f[1], DT)
-            outs[i % 2][0].copy_(s[0], non_blocking=True)
-            outs[i % 2][1].copy_(s[1], non_blocking=True)
-
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    flush.fill_(1.)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    e0 = ev(); e0.record()
-    for st in streams:
-        st.wait_event(e0)
-    for i in range(n_e2e):
-        e2e_step(i)
-    e1 = ev()
-    for st in streams:
-        torch.cuda.current_stream(dev).wait_stream(st)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms_e2e = e0.elapsed_time(e1) / n_e2e
-    ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_e2e
-    clocks = sampler.stop()              # sampled through the three timed regions (serial, two-stream, end-to-end)
-    # single-step latency (one stream, no overlap) for reference; first pass warms the default stream's allocator pool
-    for _ in range(2):
+    def timed_calls(fn, n):
+        out = fn(); out = fn(); out = fn()      # steady state: the previous result is alive while the next call allocates
+        barrier()
         flush.fill_(1.)
         torch.cuda.synchronize(dev)
         e0, e1 = ev(), ev()
+        t0 = time.perf_counter()
         e0.record()
-        ys_d = ys_host.to(dev, non_blocking=True)
-        f = cg.sgp_filter(m_and_cov, sgps, H, XI, m0, P0, DT, ys_d)
-        s = cg.sgp_smoother(m_and_cov, sgps, f[0], f[1], DT)
-        mss_host.copy_(s[0], non_blocking=True)
-        Pss_host.copy_(s[1], non_blocking=True)
+        for _ in range(n):
+            out = fn()
         e1.record()
         torch.cuda.synchronize(dev)
-        ms_e2e_single = e0.elapsed_time(e1)
-        del f, s, ys_d
+        wall = (time.perf_counter() - t0) * 1e3 / n
+        return e0.elapsed_time(e1) / n, wall, out
+
+    ms_e2e, ms_e2e_wall, out_r = timed_calls(
+        lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('freq', 'v_var')), n_e2e)
+    ms_e2e_full, ms_e2e_full_wall, _ = timed_calls(
+        lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('mss', 'Pss')), n_e2e)
+    ys_np = ys_host.numpy()
+
+    def numpy_api():
+        f = cg.sgp_filter(m_and_cov, sgps, H_h.numpy(), XI, m0_h.numpy(), P0_h.numpy(), DT, ys_np)
+        return cg.sgp_smoother(m_and_cov, sgps, f[0], f[1], DT)
+    ms_e2e_np, _, _ = timed_calls(numpy_api, max(2, n_e2e // 2))
+    clocks = sampler.stop()              # sampled through the timed regions (serial, two-stream, end-to-end)
+    freq_mean = float(out_r[0].mean())
 
     # ---- FP64 peak (DFMA-only kernel) on this GPU
     L = _native.lib()
@@ -329,29 +537,38 @@ def run_ours(args):
             best = max(best, fl / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     fp64_peak = best
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.))
+    hbm_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+
+    # ---- the other BASELINE configs (rank 0 of a single-GPU run) and the MLE sweep (every N: sharded, with the all-reduce)
+    other = None
+    if world == 1 and not args.no_configs:
+        other = run_other_configs(dev, fp64_peak, hbm_peak, not args.no_cpu, flush)
+    torch.cuda.empty_cache()
+    mle_line = None
+    if not args.no_mle:
+        mle_line = run_mle_sweep(world, rank, dev, fp64_peak, chirps=args.mle_chirps, T5=args.mle_T)
+
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms_step, ms_filter, ms_e2e, ms_pipe], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, ms_filter, ms_e2e, ms_pipe = [float(x) for x in t.tolist()]
+        ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np = [float(x) for x in t.tolist()]
     n_steps_total = world * B_PER_GPU * T
     value = n_steps_total / (ms_step * 1e-3)
-    e2e_value = n_steps_total / (ms_e2e * 1e-3)
 
     line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:  # noqa: BLE001
-            pass
-        hbm_peak = float(peaks.get('hbm_gbs', 6650.))
-        hbm_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback'
         filt_bytes = B_PER_GPU * T * BYTES_FILTER
         filt_flops = B_PER_GPU * T * flops_per_step('sgp_filter')
         ach_gbs = filt_bytes / (ms_filter * 1e-3) / 1e9
         ach_tf = filt_flops / (ms_filter * 1e-3) / 1e12
-        step_flops = B_PER_GPU * T * (flops_per_step('sgp_filter') + flops_per_step('sgp_smoother'))
+        traffic, traffic_src = ncu_traffic_bytes('gh_duo_filter_kernel')
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -362,45 +579,52 @@ def run_ours(args):
             v, sec, threads = cpu_sample(n)
             cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                    'sample': '%d chirps x %d steps, GHF+GHS, oracle/ C restatement with OpenMP (%.1f s)' % (n, T, sec)}
+        cyc = ms_filter * 1e-3 * (clocks.get('sm_mhz') or 1965.) * 1e6 / T
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': 'configs[1]: %d toymodel chirps per GPU x T=%d, dt=1e-3, chirp model d=4, '
-                                   'sgp_filter + sgp_smoother with gauss_hermite(d=4, order=3) (81 points)' % (B_PER_GPU, T),
-                       'batch_per_gpu': B_PER_GPU, 'T': T, 'parallelism': 'chirps sharded x%d, no collective' % world,
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B_PER_GPU, 'T': T,
+                       'parallelism': 'chirps sharded x%d, no collective' % world,
                        'l2': 'flushed between timed steps (256 MiB write)'},
             'clocks': clocks,
             'value_two_streams': {'value': n_steps_total / (ms_pipe * 1e-3), 'unit': UNIT, 'ms_per_step': ms_pipe,
                                   'what': 'same passes, device-resident, issued on two alternating streams (no L2 flush)'},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': B_PER_GPU * T * 8,
-                    'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D), 'steps': n_e2e,
-                    'ms_per_step_wall_clock': ms_e2e_wall, 'ms_single_step_latency': ms_e2e_single,
-                    'd2h_gb_per_s': B_PER_GPU * T * 8 * (D + D * D) / (ms_e2e * 1e-3) / 1e9,
-                    'bound': 'PCIe device->host copy of the 503 MB result (kernels hidden behind the copy of the previous step)',
-                    'what': 'pinned host ys -> cg.sgp_filter -> cg.sgp_smoother -> pinned host (mss, Pss); steps issued on '
-                            'two alternating streams so the D2H copy of one step overlaps the filter of the next'},
+            'e2e': {'value': n_steps_total / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_e2e,
+                    'ms_per_step_wall_clock': ms_e2e_wall, 'check_mean_frequency_hz': freq_mean,
+                    'what': "blocking product call per step: cg.sgp_filter_smoother(m_and_cov, sgps, H, Xi, m0, P0, dt, ys_host, "
+                            "readout=('freq', 'v_var')) -- pinned host ys in; posterior frequency estimate E[g(V_k)] "
+                            "(gaussian_expectation on the device) and marginal variance out, 16 B/step (demos/ghfs_mle.py:87-89)"},
+            'e2e_full_outputs': {'value': n_steps_total / (ms_e2e_full * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_full,
+                                 'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D),
+                                 'd2h_gb_per_s': B_PER_GPU * T * 8 * (D + D * D) / (ms_e2e_full * 1e-3) / 1e9,
+                                 'what': "same call with readout=('mss', 'Pss'): 160 B/step come back, PCIe-bound"},
+            'e2e_numpy_api': {'value': n_steps_total / (ms_e2e_np * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_np,
+                              'what': 'literal drop-in: NumPy ys -> sgp_filter -> (mfs, Pfs, n_ell) NumPy -> sgp_smoother -> '
+                                      '(mss, Pss) NumPy; blocking, filtering result goes down and up again'},
             'gpu_launches': args.steps * 2,
             'kernels_per_step': ['gh_duo_filter_kernel (sgp_filter + smoother gains)', 'smoother_sweep_lane4_kernel (sgp_smoother)'],
-            'roofline': {'bound': 'hbm', 'kernel': 'gh_duo_filter_kernel (sgp_filter + smoother gains, producer/consumer warp pair per chirp)',
-                         'achieved': ach_gbs,
-                         'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': NCU_TRAFFIC_BYTES,
-                         'peak_source': hbm_src, 'kernel_ms': ms_filter,
-                         'algorithmic_bytes_per_step': BYTES_FILTER, 'workspace_bytes_per_step': BYTES_WORKSPACE,
-                         'note': 'latency-bound, not bandwidth-bound: see roofline_fp64 and DESIGN.md section 4'},
-            'roofline_fp64': {'bound': 'fp64', 'kernel': 'gh_duo_filter_kernel', 'achieved': ach_tf, 'peak': fp64_peak,
-                              'unit': 'TFLOP/s', 'frac': ach_tf / fp64_peak if fp64_peak else None,
-                              'flops_per_step': flops_per_step('sgp_filter'),
-                              'peak_source': 'DFMA-only kernel measured in this run',
-                              'whole_step_tflops': step_flops / (ms_step * 1e-3) / 1e12},
-            # neither of the two throughput rooflines binds at 1000 chirps per GPU: the kernel time is T x (cycles one
-            # producer warp needs per step); floor = the pure dependency latency of one step
+            # the binding bound of GHF+GHS is the FP64 pipe; HBM is the extra
+            'roofline': {'bound': 'fp64', 'kernel': 'gh_duo_filter_kernel (sgp_filter + smoother gains, producer/consumer warp pair per chirp)',
+                         'achieved': ach_tf, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / fp64_peak if fp64_peak else None,
+                         'traffic': traffic, 'traffic_source': traffic_src,
+                         'flops_per_step': flops_per_step('sgp_filter'), 'kernel_ms': ms_filter,
+                         'peak_source': 'DFMA-only kernel measured in this run (MEASURED_PEAKS.json holds no FP64 figure; nominal 37)',
+                         'note': 'algorithmic flops of sgp_filter only (convention v1); the kernel also evaluates the smoother '
+                                 'gains, which are not counted'},
+            'roofline_hbm': {'bound': 'hbm', 'kernel': 'gh_duo_filter_kernel', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                             'frac': ach_gbs / hbm_peak, 'peak_source': hbm_src, 'algorithmic_bytes_per_step': BYTES_FILTER,
+                             'workspace_bytes_per_step': BYTES_WORKSPACE},
+            # at 1000 chirps per GPU neither throughput roofline is reachable: the kernel time is T x (cycles one producer
+            # warp needs per step); floor = the pure dependency latency of one step
             'roofline_chain': {'bound': 'dependency-chain latency of one filter step', 'kernel': 'gh_duo_filter_kernel',
-                               'achieved_cycles_per_step': ms_filter * 1e-3 * (clocks.get('sm_mhz') or 1965.) * 1e6 / T,
-                               'floor_cycles_per_step': 840, 'scheduled_cycles_per_step': 1394,
-                               'frac': 840. / (ms_filter * 1e-3 * (clocks.get('sm_mhz') or 1965.) * 1e6 / T),
+                               'achieved_cycles_per_step': cyc, 'floor_cycles_per_step': 840, 'scheduled_cycles_per_step': 1394,
+                               'frac': 840. / cyc,
                                'source': 'profiles/sass_dyn.py (static schedule), profiles/microbench/fp64_latency.cu'},
             'cpu_baseline': cpu,
+            'configs': other,
+            'mle_sweep': mle_line,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -415,7 +639,11 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline legs')
+    ap.add_argument('--no-configs', action='store_true', help='skip the `configs` key (BASELINE configs 1, 3, 4)')
+    ap.add_argument('--no-mle', action='store_true', help='skip the `mle_sweep` key (BASELINE config 5)')
+    ap.add_argument('--mle-chirps', type=int, default=MLE_CHIRPS)
+    ap.add_argument('--mle-T', type=int, default=MLE_T)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -233,11 +233,12 @@ using namespace cgp;
 extern "C" {
 
 int64_t cgp_ekf_nll_default_ckpt(int64_t T) {
-    // segments of 32 steps keep the adjoint's per-warp scratch slot (32 x 17 x 256 bytes for d = 4) resident in L2; short
-    // series get ~sqrt(T)
+    // segments of 16 steps keep the adjoint's per-warp scratch slots (16 x 17 x 256 bytes for d = 4, 1776 warps: 124 MB)
+    // about the size of the L2; measured on 160 000 problems: 8 / 16 / 24 / 32 steps -> 19.7 / 18.5 / 16.7 / 16.1 G steps/s
+    // (profiles/r2_nll_sweeps.txt).  Short series get ~sqrt(T).
     int64_t c = 1;
     while (c * c < T) c++;
-    return c > 32 ? 32 : (c < 1 ? 1 : c);
+    return c > 16 ? 16 : (c < 1 ? 1 : c);
 }
 
 size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every) {

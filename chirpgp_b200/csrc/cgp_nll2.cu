@@ -404,7 +404,7 @@ bwd_kernel(const CgpProblem p, const double *__restrict__ ys, const double *__re
     const Sched sched{sched_words};
     const unsigned long long total = (unsigned long long)g.nunits * (unsigned long long)g.nchains;
     const int64_t worker = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    double *__restrict__ slot = scratch + worker * ((int64_t)g.every * REC * kLanes) + lane;
+    double *__restrict__ slot0 = scratch + worker * ((int64_t)g.every * REC * kLanes) + lane;
     double H[D];
     CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
     for (;;) {
@@ -419,51 +419,62 @@ bwd_kernel(const CgpProblem p, const double *__restrict__ ys, const double *__re
         mdl.load(p.consts + bb * p.consts_stride, p.dt);
         const double lw = nll_bar ? nll_bar[bb] : 1.;
         const double *__restrict__ yrow = ys + (bb / p.ys_repeat) * p.T;
+        const double Xi = p.Xi;
+
+        auto seg_len = [&](int s) { const int64_t t0 = (int64_t)s * g.every; return (int)((p.T - t0 < g.every) ? (p.T - t0) : g.every); };
+        auto rec_load = [&](int s, double (&m)[D], double (&P)[NS]) {
+            if (s == 0) {
+                load_vec<D>(p.m0 + bb * p.m0_stride, m);
+                load_sym<D>(p.P0 + bb * p.P0_stride, P);
+            } else {
+                const double *q = ckpt + ((int64_t)s * g.nchains + c) * (CK * kLanes) + lane;
+                CGP_UNROLL for (int i = 0; i < D; i++) m[i] = __ldcg(q + i * kLanes);
+                CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = __ldcg(q + (D + i) * kLanes);
+            }
+        };
+        // forward recomputation: record j = the inputs (m, P) of step j and its transcendental results, then advance
+        auto rec_step = [&](const bool advance, int j, const double *__restrict__ y, double (&m)[D], double (&P)[NS], double *__restrict__ slot) {
+            Lin<NH> tr;
+            trig<NH>(mdl, m[V], tr);
+            double *q = slot + (int64_t)j * (REC * kLanes);
+            CGP_UNROLL for (int i = 0; i < D; i++) q[i * kLanes] = m[i];
+            CGP_UNROLL for (int i = 0; i < NS; i++) q[(D + i) * kLanes] = P[i];
+            CGP_UNROLL for (int k = 0; k < NH; k++) { q[(D + NS + 2 * k) * kLanes] = tr.ce[k]; q[(D + NS + 2 * k + 1) * kLanes] = tr.se[k]; }
+            q[(D + NS + 2 * NH) * kLanes] = tr.sg;
+            if (advance) step_from<NH, H_E1, false>(mdl, tr, H, Xi, __ldg(y + j), m, P);
+        };
+        auto rev_step = [&](int j, const double *__restrict__ y, const double *__restrict__ slot, Carry<NH, RAW> &cy) {
+            const double *q = slot + (int64_t)j * (REC * kLanes);
+            double m[D], P[NS];
+            Lin<NH> tr;
+            CGP_UNROLL for (int i = 0; i < D; i++) m[i] = q[i * kLanes];
+            CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = q[(D + i) * kLanes];
+            CGP_UNROLL for (int k = 0; k < NH; k++) { tr.ce[k] = q[(D + NS + 2 * k) * kLanes]; tr.se[k] = q[(D + NS + 2 * k + 1) * kLanes]; }
+            tr.sg = q[(D + NS + 2 * NH) * kLanes];
+            reverse_step<NH, H_E1, RAW>(mdl, H, Xi, __ldg(y + j), lw, m, P, tr, cy);
+        };
+        auto recompute = [&](int s, double *__restrict__ slot) {
+            double m[D], P[NS];
+            rec_load(s, m, P);
+            const int nst = seg_len(s);
+            const double *__restrict__ y = yrow + (int64_t)s * g.every;
+            for (int j = 0; j + 1 < nst; j++) rec_step(true, j, y, m, P, slot);
+            rec_step(false, nst - 1, y, m, P, slot);
+        };
+        auto load_carry = [&](Carry<NH, RAW> &cy) -> bool {
+            if (round == 0) { cy.zero(); return true; }
+            if (!sched.wait(c, (unsigned)round, lane)) return false;
+            const double *q = carry + (int64_t)c * (NCARRY * kLanes) + lane;
+            cy.each([&](int k, double &x) { x = __ldcg(q + k * kLanes); });
+            return true;
+        };
+
         Carry<NH, RAW> cy;
         for (int s = s_hi; s >= s_lo; s--) {
-            const int64_t t0 = (int64_t)s * g.every;
-            const int nst = (int)((p.T - t0 < g.every) ? (p.T - t0) : g.every);
-            const double *__restrict__ y = yrow + t0;
-            {   // forward recomputation of the segment (independent of the chain's reverse state: runs before the wait)
-                double m[D], P[NS];
-                if (s == 0) {
-                    load_vec<D>(p.m0 + bb * p.m0_stride, m);
-                    load_sym<D>(p.P0 + bb * p.P0_stride, P);
-                } else {
-                    const double *q = ckpt + ((int64_t)s * g.nchains + c) * (CK * kLanes) + lane;
-                    CGP_UNROLL for (int i = 0; i < D; i++) m[i] = __ldcg(q + i * kLanes);
-                    CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = __ldcg(q + (D + i) * kLanes);
-                }
-                for (int j = 0; j < nst; j++) {
-                    Lin<NH> tr;
-                    trig<NH>(mdl, m[V], tr);
-                    double *q = slot + (int64_t)j * (REC * kLanes);
-                    CGP_UNROLL for (int i = 0; i < D; i++) q[i * kLanes] = m[i];
-                    CGP_UNROLL for (int i = 0; i < NS; i++) q[(D + i) * kLanes] = P[i];
-                    CGP_UNROLL for (int k = 0; k < NH; k++) { q[(D + NS + 2 * k) * kLanes] = tr.ce[k]; q[(D + NS + 2 * k + 1) * kLanes] = tr.se[k]; }
-                    q[(D + NS + 2 * NH) * kLanes] = tr.sg;
-                    if (j + 1 < nst) step_from<NH, H_E1, false>(mdl, tr, H, p.Xi, __ldg(y + j), m, P);
-                }
-            }
-            if (s == s_hi) {
-                if (round == 0) {
-                    cy.zero();
-                } else {
-                    if (!sched.wait(c, (unsigned)round, lane)) return;
-                    const double *q = carry + (int64_t)c * (NCARRY * kLanes) + lane;
-                    cy.each([&](int k, double &x) { x = __ldcg(q + k * kLanes); });
-                }
-            }
-            for (int j = nst - 1; j >= 0; j--) {
-                const double *q = slot + (int64_t)j * (REC * kLanes);
-                double m[D], P[NS];
-                Lin<NH> tr;
-                CGP_UNROLL for (int i = 0; i < D; i++) m[i] = q[i * kLanes];
-                CGP_UNROLL for (int i = 0; i < NS; i++) P[i] = q[(D + i) * kLanes];
-                CGP_UNROLL for (int k = 0; k < NH; k++) { tr.ce[k] = q[(D + NS + 2 * k) * kLanes]; tr.se[k] = q[(D + NS + 2 * k + 1) * kLanes]; }
-                tr.sg = q[(D + NS + 2 * NH) * kLanes];
-                reverse_step<NH, H_E1, RAW>(mdl, H, p.Xi, __ldg(y + j), lw, m, P, tr, cy);
-            }
+            recompute(s, slot0);                           // independent of the chain's reverse state: runs before the wait
+            if (s == s_hi && !load_carry(cy)) return;
+            const double *__restrict__ y = yrow + (int64_t)s * g.every;
+            for (int j = seg_len(s) - 1; j >= 0; j--) rev_step(j, y, slot0, cy);
         }
         if (s_lo > 0) {
             double *q = carry + (int64_t)c * (NCARRY * kLanes) + lane;
@@ -508,16 +519,17 @@ static int env_int(const char *name, int dflt) {      // tuning knobs for profil
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// lanes per chain: full warps while they give every SM sub-partition at least two warps; otherwise half / quarter warps (the
-// FP64 pipe takes 2 cycles per warp instruction whatever the number of active lanes -- profiles/microbench/fp64_lanes.cu --
-// so narrow chains cost pipe time, but two or more warps per sub-partition hide each other's dependency stalls)
+// lanes per chain: full warps unless they would leave SM sub-partitions without any warp; then half / quarter warps put the
+// problems on more sub-partitions.  (Narrow chains never pay once every sub-partition has a warp: the FP64 pipe takes 2 cycles
+// per warp instruction whatever the number of active lanes -- profiles/microbench/fp64_lanes.cu -- and 20 000 problems ran
+// 7.0 / 9.8 / 18.0 ms as chains of 32 / 16 / 8, profiles/r2_nll_sweeps.txt.)
 static int64_t pick_lanes(int64_t B, int sms) {
     const int forced = env_int("CGP_NLL_LANES", 0);
     if (forced == 8 || forced == 16 || forced == 32) return forced;
-    const int64_t want = (int64_t)sms * 4 * 2;
-    if ((B + 31) / 32 >= want) return 32;
-    if ((B + 15) / 16 >= want) return 16;
-    return (B + 15) / 16 >= (int64_t)sms * 4 ? 16 : 8;
+    const int64_t smsp = (int64_t)sms * 4;
+    if ((B + 31) / 32 >= smsp) return 32;
+    if ((B + 15) / 16 >= smsp) return 16;
+    return (B + 15) / 16 * 2 > smsp ? 16 : 8;
 }
 
 static Plan make_plan(const CgpProblem &p, int64_t every) {
@@ -581,8 +593,9 @@ template <int NH, bool H_E1>
 static int fwd_launch(const CgpProblem &p, const double *ys, double *nll, char *ws, const Plan &pl, cudaStream_t s) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwd_kernel<NH, H_E1>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
+    if (per_sm > 4) per_sm = 4;                            // measured: 3 / 4 / 5 blocks per SM -> 10.6 / 10.1 / 11.2 ms
     per_sm = env_int("CGP_NLL_KF", per_sm);
+    if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
     const int grid = grid_blocks(pl, per_sm);
     if (!ws) {
         Geo g{(int)p.T, 1, (int)pl.nchains, (int)pl.lanes, 1, 1};

@@ -30,7 +30,7 @@ from . import _native as N
 from .models import LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, KPTMeasurement, MODEL_KPT
 
 __all__ = ['kf', 'rts', 'ekf', 'ekf_for_kpt', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
-           'cd_sgp_smoother', 'sgp_filter_smoother']
+           'cd_sgp_smoother', 'sgp_filter_smoother', 'ekf_smoother', 'cd_ekf_smoother', 'cd_sgp_filter_smoother', 'READOUTS']
 
 _F64 = torch.float64
 
@@ -69,19 +69,22 @@ _PINNED_MIN_BYTES = 1 << 20
 
 
 def _back(t: torch.Tensor, kind):
-    if kind[0] == 'numpy':
-        # NumPy callers get arrays backed by pinned host memory (torch's caching host allocator recycles the blocks): the
-        # device->host copy of the (T, d, d) outputs runs at the PCIe rate instead of the pageable-memory rate
-        if t.is_cuda and t.numel() * t.element_size() >= _PINNED_MIN_BYTES:
-            try:
-                host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                host.copy_(t, non_blocking=True)
-                torch.cuda.current_stream(t.device).synchronize()
-                return host.numpy()
-            except RuntimeError:
-                pass                     # no pinned memory left: pageable copy below
-        return t.cpu().numpy()
-    return t.to(kind[1])
+    to_host = kind[0] == 'numpy' or (kind[0] == 'torch' and kind[1].type == 'cpu')
+    if not to_host:
+        return t.to(kind[1])
+    # host callers (NumPy arrays / CPU tensors) get results backed by pinned host memory (torch's caching host allocator
+    # recycles the blocks): the device->host copy of the (T, d, d) outputs runs at the PCIe rate instead of the pageable rate
+    host = None
+    if t.is_cuda and t.numel() * t.element_size() >= _PINNED_MIN_BYTES:
+        try:
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+        except RuntimeError:
+            host = None                  # no pinned memory left: pageable copy below
+    if host is None:
+        host = t.cpu()
+    return host.numpy() if kind[0] == 'numpy' else host
 
 
 def _ptr(t):
@@ -468,16 +471,96 @@ def sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt) -> Tuple:
     return _run_smoother('sgp_smoother', model, _consts_on_device(model, dt, _device(), dt), mfs, Pfs, dt, sgps=sgps)
 
 
-def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys) -> Tuple:
-    """``sgp_filter`` followed by ``sgp_smoother`` in one call (extension; what every demo / job does back to back,
-    demos/ghfs_mle.py:69-85): returns ``(mfs, Pfs, n_ell, mss, Pss)`` of the kind of ``ys``.  For host (NumPy) callers this is
-    the efficient form of the pair: the measurements are uploaded once, the filtering result never travels back up, and the
-    filter kernel hands the smoother its gains; the five results come down into pinned host memory."""
+READOUTS = ('mfs', 'Pfs', 'n_ell', 'mss', 'Pss', 'n_ell_last', 'freq', 'v_mean', 'v_var')
+
+
+def _frequency(mss: torch.Tensor, Pss: torch.Tensor, order: int = 10) -> torch.Tensor:
+    """E[g(V_k)] under the smoothing marginal V_k ~ N(mss[.., k, d-2], Pss[.., k, d-2, d-2]) on the device:
+    ``gaussian_expectation(ms=mss[:, 2], chol_Ps=sqrt(Pss[:, 2, 2]), force_shape=True)`` of demos/ghfs_mle.py:87-89
+    (quadratures.py:234-274), read straight out of the smoother result with element strides."""
+    from .quadratures import SigmaPoints
+    d = int(mss.shape[-1])
+    v = d - 2
+    n = int(mss.numel() // d)
+    out = torch.empty(tuple(mss.shape[:-1]), dtype=_F64, device=mss.device)
+    if n == 0:
+        return out
+    sg = SigmaPoints.gauss_hermite(d=1, order=order)
+    w = np.ascontiguousarray(sg.w, dtype=np.float64)
+    xi = np.ascontiguousarray(np.asarray(sg.xi)[:, 0], dtype=np.float64)
+    stream = C.c_void_p(torch.cuda.current_stream(mss.device).cuda_stream)
+    rc = N.lib().cgp_gaussian_expectation_softplus_f64(n, C.c_void_p(mss.data_ptr() + 8 * v), d,
+                                                       C.c_void_p(Pss.data_ptr() + 8 * (v * d + v)), d * d, 1,
+                                                       w.ctypes.data_as(C.c_void_p), xi.ctypes.data_as(C.c_void_p), int(order),
+                                                       C.c_void_p(out.data_ptr()), stream)
+    N.check(rc, 'frequency readout')
+    return out
+
+
+def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order):
+    """filter + smoother in one call on the device; only the requested results travel back to a host caller."""
     dev = _device()
     kind = _kind(ys)
-    f = sgp_filter(cond_m_cov, sgps, _dev(H, dev), Xi, _dev(m0, dev), _dev(P0, dev), dt, _dev(ys, dev))
-    s = sgp_smoother(cond_m_cov, sgps, f[0], f[1], dt)
-    return tuple(_back(t, kind) for t in f + s)
+    f = run_filter(_dev(H, dev), _dev(m0, dev), _dev(P0, dev), _dev(ys, dev))
+    sm = run_smoother(f[0], f[1])
+    if readout is None:
+        return tuple(_back(t, kind) for t in f + sm)
+    names = (readout,) if isinstance(readout, str) else tuple(readout)
+    d = int(sm[0].shape[-1])
+    have = {'mfs': f[0], 'Pfs': f[1], 'n_ell': f[2], 'mss': sm[0], 'Pss': sm[1]}
+    out = []
+    for nm in names:
+        if nm in have:
+            t = have[nm]
+        elif nm == 'n_ell_last':
+            t = f[2][..., -1].contiguous()
+        elif nm == 'freq':
+            t = _frequency(sm[0], sm[1], order)
+        elif nm == 'v_mean':
+            t = sm[0][..., d - 2].contiguous()
+        elif nm == 'v_var':
+            t = sm[1][..., d - 2, d - 2].contiguous()
+        else:
+            raise ValueError('unknown readout %r (choose from %s)' % (nm, ', '.join(READOUTS)))
+        out.append(_back(t, kind))
+    return tuple(out)
+
+
+def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+    """``sgp_filter`` followed by ``sgp_smoother`` in one call (extension; what every demo / job does back to back,
+    demos/ghfs_mle.py:69-85).  ``readout=None`` returns ``(mfs, Pfs, n_ell, mss, Pss)`` of the kind of ``ys``.  For host
+    (NumPy) callers this is the efficient form of the pair: the measurements are uploaded once, the filtering result never
+    travels back up, and the filter kernel hands the smoother its gains; the results come down into pinned host memory.
+
+    ``readout`` -- a name or tuple of names from ``READOUTS`` -- returns just those, in that order, and only those cross PCIe:
+    the five arrays above, ``'n_ell_last'`` (the MLE objective), and what the demos compute from the smoothing marginal of
+    the frequency state V = x[d-2] right afterwards (demos/ghfs_mle.py:87-89): ``'freq'`` = E[g(V_k)] by Gauss--Hermite of
+    ``order`` on the device (``gaussian_expectation``, quadratures.py:234-274), ``'v_mean'``, ``'v_var'``.  Asking for
+    ``('freq', 'v_var')`` returns 16 bytes per step instead of 328."""
+    dt = float(dt)
+    return _filter_smoother(lambda H_, m0_, P0_, ys_: sgp_filter(cond_m_cov, sgps, H_, Xi, m0_, P0_, dt, ys_),
+                            lambda mfs, Pfs: sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+
+
+def ekf_smoother(cond_m_cov, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+    """``ekf`` + ``eks`` in one call (demos/ekfs_mle.py:68-76); ``readout`` as in ``sgp_filter_smoother``."""
+    dt = float(dt)
+    return _filter_smoother(lambda H_, m0_, P0_, ys_: ekf(cond_m_cov, H_, Xi, m0_, P0_, dt, ys_),
+                            lambda mfs, Pfs: eks(cond_m_cov, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+
+
+def cd_ekf_smoother(a, b, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+    """``cd_ekf`` + ``cd_eks`` in one call (demos/cd_ekfs_mle.py); ``readout`` as in ``sgp_filter_smoother``."""
+    dt = float(dt)
+    return _filter_smoother(lambda H_, m0_, P0_, ys_: cd_ekf(a, b, H_, Xi, m0_, P0_, dt, ys_),
+                            lambda mfs, Pfs: cd_eks(a, b, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+
+
+def cd_sgp_filter_smoother(a, b, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+    """``cd_sgp_filter`` + ``cd_sgp_smoother`` in one call (demos/cd_ghfs_mle.py:61-75); ``readout`` as in ``sgp_filter_smoother``."""
+    dt = float(dt)
+    return _filter_smoother(lambda H_, m0_, P0_, ys_: cd_sgp_filter(a, b, sgps, H_, Xi, m0_, P0_, dt, ys_),
+                            lambda mfs, Pfs: cd_sgp_smoother(a, b, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
 
 
 def _qc(bm):

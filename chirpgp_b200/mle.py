@@ -123,11 +123,13 @@ class _EkfNllPath(torch.autograd.Function):
 
 
 def _default_ckpt(L, p, T, dev) -> int:
-    """Segment length of the checkpointed adjoint: the library default (32 steps: the per-warp scratch slot stays in L2),
-    lengthened until the checkpoints (one (m, P, nll) record per problem and segment) fit into half of the free memory."""
+    """Segment length of the checkpointed adjoint: the library default (16 steps: the per-warp scratch slots stay in L2),
+    lengthened until the checkpoints (one (m, P, nll) record per problem and segment; config 5 on one GPU: 120 GB at 16
+    steps) fit into three quarters of the free memory."""
     every = int(L.cgp_ekf_nll_default_ckpt(T))
     free, _ = torch.cuda.mem_get_info(dev)
-    while every < T and L.cgp_ekf_nll_workspace_bytes(C.byref(p), every) > 0.5 * free:
+    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)      # blocks the caching allocator can reuse
+    while every < T and L.cgp_ekf_nll_workspace_bytes(C.byref(p), every) > 0.75 * free:
         every *= 2
     return every
 

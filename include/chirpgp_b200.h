@@ -148,7 +148,7 @@ int cgp_smoother_sweep_f64(const CgpProblem *p, const double *mfs, const double 
  *        antisymmetric part of the covariance cotangent feeds nothing but itself and is not tracked.
  * The workspace is read and written by both calls (checkpoints, scheduling words, per-warp scratch); one workspace serves one
  * fwd / bwd pair at a time.  Its size depends on the current CUDA device (number of SMs). */
-int64_t cgp_ekf_nll_default_ckpt(int64_t T);                       /* min(32, ~sqrt(T)) */
+int64_t cgp_ekf_nll_default_ckpt(int64_t T);                       /* min(16, ~sqrt(T)) */
 size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every);
 int cgp_ekf_nll_fwd_f64(const CgpProblem *p, const double *ys, double *nll, void *workspace, size_t workspace_bytes,
                         int64_t ckpt_every, void *stream);

@@ -617,3 +617,44 @@ def test_long_sequence_fused_path():
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
     _check_filter([x[:2].cpu().numpy() for x in f], fo, 2e-8)
     _check_smoother([x[:2].cpu().numpy() for x in s], so, 2e-8)
+
+
+def test_filter_smoother_pairs_and_readout():
+    """One-call filter + smoother pairs (extension) == the two reference calls; `readout` returns just the requested
+    quantities, among them the demos' post-processing of the smoother output (demos/ghfs_mle.py:87-89): E[g(V_k)] by
+    Gauss-Hermite order 10 (quadratures.py:234-274) against the oracle-side NumPy evaluation."""
+    B, T, dt, Xi = 5, 300, 1e-3, 0.1
+    _, ys, _ = toymodels.synthetic_batch(B, T, dt, Xi=Xi, seed=8)
+    params = np.array([0.1, 0.1, 0.1, 1., 1., 7.])
+    drift, disp, mc, m0, P0, H = cg.build_chirp_model(params)
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    f = cg.sgp_filter(mc, sg, H, Xi, m0, P0, dt, ys)
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    full = cg.sgp_filter_smoother(mc, sg, H, Xi, m0, P0, dt, ys)
+    assert isinstance(full[0], np.ndarray) and len(full) == 5
+    for a, b in zip(full, f + s):
+        npt.assert_allclose(a, b, rtol=1e-9, atol=1e-11)         # fused gains vs stand-alone smoother: rounding only
+    freq, vvar, vmean, last = cg.sgp_filter_smoother(mc, sg, H, Xi, m0, P0, dt, ys, readout=('freq', 'v_var', 'v_mean', 'n_ell_last'))
+    assert freq.shape == (B, T) and isinstance(freq, np.ndarray)
+    npt.assert_array_equal(vvar, full[4][..., 2, 2])
+    npt.assert_array_equal(vmean, full[3][..., 2])
+    npt.assert_array_equal(last, full[2][..., -1])
+    want = cg.gaussian_expectation(ms=full[3][..., 2].reshape(-1), chol_Ps=np.sqrt(full[4][..., 2, 2]).reshape(-1), force_shape=True)
+    npt.assert_allclose(freq.reshape(-1), want.reshape(-1), rtol=1e-13)
+    only = cg.sgp_filter_smoother(mc, sg, H, Xi, m0, P0, dt, torch.as_tensor(ys).cuda(), readout='freq')
+    assert len(only) == 1 and only[0].is_cuda
+    npt.assert_array_equal(only[0].cpu().numpy(), freq)
+    with pytest.raises(ValueError):
+        cg.sgp_filter_smoother(mc, sg, H, Xi, m0, P0, dt, ys, readout=('nope',))
+    # siblings
+    e = cg.ekf_smoother(mc, H, Xi, m0, P0, dt, ys)
+    fe = cg.ekf(mc, H, Xi, m0, P0, dt, ys); se = cg.eks(mc, fe[0], fe[1], dt)
+    for a, b in zip(e, fe + se):
+        npt.assert_array_equal(a, b)
+    c = cg.cd_ekf_smoother(drift, disp, H, Xi, m0, P0, dt, ys, readout=('mss', 'Pss'))
+    fc = cg.cd_ekf(drift, disp, H, Xi, m0, P0, dt, ys); sc = cg.cd_eks(drift, disp, fc[0], fc[1], dt)
+    for a, b in zip(c, sc):
+        npt.assert_array_equal(a, b)
+    g2 = cg.cd_sgp_filter_smoother(drift, disp(None), sg, H, Xi, m0, P0, dt, ys[:2], readout=('mss',))
+    fg = cg.cd_sgp_filter(drift, disp(None), sg, H, Xi, m0, P0, dt, ys[:2])
+    npt.assert_array_equal(g2[0], cg.cd_sgp_smoother(drift, disp(None), sg, fg[0], fg[1], dt)[0])
