@@ -394,7 +394,8 @@ def run_mle_sweep(world, rank, dev, fp64_peak, chirps=MLE_CHIRPS, T5=MLE_T, reps
            'flops_per_step': fl, 'flops_convention': '3 x flops_per_step(ekf): forward + recomputation + adjoint (SURVEY 8d v1)',
            'fp64_tflops_per_gpu': steps * fl / (ms_eval * 1e-3) / 1e12 / world,
            'fp64_frac': steps * fl / (ms_eval * 1e-3) / 1e12 / world / fp64_peak if fp64_peak else None,
-           'nll_sum': float(val.sum()), 'grad_norm': float(grad.norm()), 'hbm_in_use_gb': (total - free) / 1e9}
+           'nll_sum': float(val.sum()), 'grad_norm': float(grad.norm()), 'hbm_in_use_gb': (total - free) / 1e9,
+           'checkpointing': getattr(mle._default_ckpt, 'last', None)}
     del ys
     torch.cuda.empty_cache()
     return res

@@ -39,7 +39,7 @@ FILTER_FUNCS = ('kf', 'ekf', 'ekf_for_kpt', 'sgp_filter', 'cd_ekf', 'cd_sgp_filt
 SMOOTHER_FUNCS = ('rts', 'eks', 'sgp_smoother', 'cd_eks', 'cd_sgp_smoother')
 EXPORTED = (['cgp_abi_version', 'cgp_workspace_bytes'] + ['cgp_%s_f64' % f for f in FILTER_FUNCS + SMOOTHER_FUNCS]
             + ['cgp_ekf_nll_default_ckpt', 'cgp_ekf_nll_workspace_bytes', 'cgp_ekf_nll_fwd_f64', 'cgp_ekf_nll_bwd_f64', 'cgp_ekf_nll_bwd_sym_f64',
-               'cgp_ekf_nll_path_fwd_f64', 'cgp_ekf_nll_path_bwd_f64', 'cgp_filter_nll_tangent_f64',
+               'cgp_ekf_nll_path_workspace_bytes', 'cgp_ekf_nll_path_fwd_f64', 'cgp_ekf_nll_path_bwd_f64', 'cgp_filter_nll_tangent_f64',
                'cgp_sgp_filter_gains_fused', 'cgp_sgp_filter_gains_f64', 'cgp_smoother_sweep_f64',
                'cgp_gaussian_expectation_softplus_f64', 'cgp_simulate_f64', 'cgp_test_philox', 'cgp_test_normals',
                'cgp_bench_dfma', 'cgp_test_math'])
@@ -91,6 +91,8 @@ def lib():
         L.cgp_ekf_nll_default_ckpt.argtypes = [C.c_int64]
         L.cgp_ekf_nll_workspace_bytes.restype = C.c_size_t
         L.cgp_ekf_nll_workspace_bytes.argtypes = [C.POINTER(CgpProblem), C.c_int64]
+        L.cgp_ekf_nll_path_workspace_bytes.restype = C.c_size_t
+        L.cgp_ekf_nll_path_workspace_bytes.argtypes = [C.POINTER(CgpProblem), C.c_int64]
         L.cgp_ekf_nll_fwd_f64.restype = C.c_int
         L.cgp_ekf_nll_fwd_f64.argtypes = [C.POINTER(CgpProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64,
                                           C.c_void_p]

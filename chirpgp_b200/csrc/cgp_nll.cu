@@ -242,11 +242,12 @@ int64_t cgp_ekf_nll_default_ckpt(int64_t T) {
 }
 
 size_t cgp_ekf_nll_workspace_bytes(const CgpProblem *p, int64_t ckpt_every) {
+    if (!p || ckpt_every < 1 || !nll2_supported(*p)) return 0;
+    return nll2_workspace_bytes(*p, ckpt_every);                      // persistent kernels (scalar nll)
+}
+size_t cgp_ekf_nll_path_workspace_bytes(const CgpProblem *p, int64_t ckpt_every) {
     if (!p || ckpt_every < 1) return 0;
-    // the larger of the two layouts: thread-per-problem kernels (n_ell path variants) / persistent kernels (scalar nll)
-    const size_t v1 = (ckpt_doubles(*p, ckpt_every) + scratch_doubles(*p, ckpt_every)) * sizeof(double);
-    const size_t v2 = nll2_supported(*p) ? nll2_workspace_bytes(*p, ckpt_every) : 0;
-    return v1 > v2 ? v1 : v2;
+    return (ckpt_doubles(*p, ckpt_every) + scratch_doubles(*p, ckpt_every)) * sizeof(double);   // thread-per-problem kernels
 }
 
 static int nll_fwd(const CgpProblem *p, const double *ys, double *nll, double *nell_path, void *workspace, size_t ws_bytes,
@@ -257,7 +258,7 @@ static int nll_fwd(const CgpProblem *p, const double *ys, double *nll, double *n
     double *ckpt = nullptr;
     if (workspace) {
         if (ckpt_every < 1) return CGP_ERR_BAD_ARG;
-        if (ws_bytes < cgp_ekf_nll_workspace_bytes(p, ckpt_every)) return CGP_ERR_WORKSPACE;
+        if (ws_bytes < cgp_ekf_nll_path_workspace_bytes(p, ckpt_every)) return CGP_ERR_WORKSPACE;
         ckpt = (double *)workspace;
     } else {
         ckpt_every = p->T;
@@ -297,7 +298,7 @@ static int nll_bwd(const CgpProblem *p, const double *ys, const double *nll_bar,
         !p->consts || !p->H || p->ys_repeat < 1)
         return CGP_ERR_BAD_ARG;
     if (p->model != CGP_MODEL_LCD || p->d != 2 * p->num_harmonics + 2) return CGP_ERR_UNSUPPORTED;
-    if (ws_bytes < cgp_ekf_nll_workspace_bytes(p, ckpt_every)) return CGP_ERR_WORKSPACE;
+    if (ws_bytes < cgp_ekf_nll_path_workspace_bytes(p, ckpt_every)) return CGP_ERR_WORKSPACE;
     double *ckpt = (double *)workspace;
     double *scratch = ckpt + ckpt_doubles(*p, ckpt_every);
     const int block = 128;

@@ -90,7 +90,7 @@ class _EkfNllPath(torch.autograd.Function):
         every = int(ckpt_every or L.cgp_ekf_nll_default_ckpt(T))
         ws, nbytes = None, 0
         if need_grad:
-            nbytes = L.cgp_ekf_nll_workspace_bytes(C.byref(p), every)
+            nbytes = L.cgp_ekf_nll_path_workspace_bytes(C.byref(p), every)
             ws = torch.empty((nbytes // 8,), dtype=_F64, device=dev)
         nell = torch.empty((B, T), dtype=_F64, device=dev)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -131,6 +131,8 @@ def _default_ckpt(L, p, T, dev) -> int:
     free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)      # blocks the caching allocator can reuse
     while every < T and L.cgp_ekf_nll_workspace_bytes(C.byref(p), every) > 0.75 * free:
         every *= 2
+    _default_ckpt.last = {'ckpt_every': every, 'free_bytes': int(free),
+                          'workspace_bytes': int(L.cgp_ekf_nll_workspace_bytes(C.byref(p), every))}
     return every
 
 

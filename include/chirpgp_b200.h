@@ -201,6 +201,7 @@ int cgp_test_normals(uint64_t seed, int64_t n, double *out_dev, void *stream);
  *   path_fwd: nell [B, T] = cumulative negative log-likelihood at every step (:180-184), checkpoints as above;
  *   path_bwd: step_weights [B, T], the weight of every step's increment = sum_{j >= k} ct_j (a reversed cumulative sum the
  *             caller forms), otherwise as cgp_ekf_nll_bwd_f64. */
+size_t cgp_ekf_nll_path_workspace_bytes(const CgpProblem *p, int64_t ckpt_every);
 int cgp_ekf_nll_path_fwd_f64(const CgpProblem *p, const double *ys, double *nell, void *workspace, size_t workspace_bytes,
                              int64_t ckpt_every, void *stream);
 int cgp_ekf_nll_path_bwd_f64(const CgpProblem *p, const double *ys, const double *step_weights, void *workspace,
