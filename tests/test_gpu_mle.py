@@ -118,6 +118,61 @@ def test_general_measurement_row_and_ragged_chains():
     npt.assert_allclose(grad, fd, rtol=1e-5, atol=1e-6)
 
 
+def test_config5_shape_nll_and_adjoint():
+    """BASELINE configs[4] shape: T = 1e5 steps (dt = 3.141e-5), chirps x hyper-parameter candidates, DEFAULT checkpoint stride
+    (6250 segments of 16 steps, units of several segments, chains migrating between warps).  nll against the filter kernel's
+    n_ell[-1] at rtol 1e-11; the adjoint gradient against (a) the forward-mode tangent kernel at full length -- an independent
+    derivative code path -- at rtol 1e-9, (b) central finite differences at full length, (c) the torch autodiff twin (jacfwd
+    of the model mean, reverse mode through the Python loop; ~15 ms per step on the host) on a T = 2000 prefix at rtol 1e-7."""
+    from oracle import ekf_torch
+    T, G, Xi = 100000, 4, 0.1
+    dt = 3.141 / T
+    rng = np.random.default_rng(5)
+    ts = np.linspace(dt, dt * T, T)
+    ys = np.sin(2 * np.pi * (500 * np.exp(-5 / np.sin(ts)) + 8 * ts))[None] + np.sqrt(Xi) * rng.standard_normal((2, T))
+    grid = np.array([[0.1, 0.05, 0.1, 1., 1., 7.], [0.4, 0.1, 0.1, 1., 1., 7.], [0.7, 0.2, 0.1, 1., 1., 7.], [1.0, 0.4, 0.1, 1., 1., 7.]])
+    theta_np = np.log(np.exp(grid) - 1.)
+    H = np.array([0., 1., 0., 0.])
+    theta = torch.tensor(theta_np, dtype=torch.float64, device='cuda', requires_grad=True)
+    _, _, mc, m0, P0, _ = cg.build_chirp_model(gfun(theta))
+    nll = mle.ekf_nll(mc, H, Xi, m0, P0, dt, ys, candidates=True)                       # (2, G), default ckpt_every
+    assert mle._default_ckpt.last['ckpt_every'] == 16
+    grad, = torch.autograd.grad(nll.sum(), theta)                                       # (G, 6): summed over the 2 chirps
+    nll, grad = nll.detach().cpu().numpy(), grad.cpu().numpy()
+    for gi in range(G):
+        _, _, mc1, m01, P01, _ = cg.build_chirp_model(grid[gi])
+        f = cg.ekf(mc1, H, Xi, m01, P01, dt, ys)
+        npt.assert_allclose(nll[:, gi], f[2][:, -1], rtol=1e-11)
+    # (a) tangent kernel, full length
+    for gi in (0, 3):
+        v, gt = mle.filter_nll_grad('ekf', cg.build_chirp_model, theta_np[gi], H, Xi, dt, ys)
+        npt.assert_allclose(v.cpu().numpy(), nll[:, gi], rtol=1e-11)
+        npt.assert_allclose(gt.sum(0).cpu().numpy(), grad[gi], rtol=1e-9, atol=1e-9)
+    # (b) central differences, full length, candidate 1
+    fd = np.zeros(6)
+    for i in range(6):
+        h = 1e-5 * max(1., abs(theta_np[1, i]))
+        v = []
+        for sgn in (1., -1.):
+            th = theta_np[1].copy(); th[i] += sgn * h
+            _, _, mcp, m0p, P0p, _ = cg.build_chirp_model(gfun(torch.tensor(th)))
+            v.append(float(mle.ekf_nll(mcp, H, Xi, m0p, P0p, dt, ys).sum()))
+        fd[i] = (v[0] - v[1]) / (2 * h)
+    npt.assert_allclose(grad[1], fd, rtol=1e-5, atol=1e-4)
+    # (c) autodiff twin on a prefix (one chirp, candidate 2)
+    Tp = 2000
+    th = torch.tensor(theta_np[2], dtype=torch.float64, requires_grad=True)
+    _, _, mct, m0t, P0t, Ht = cg.build_chirp_model(gfun(th))
+    want = ekf_torch.ekf_nll(mct.consts(dt), Ht, torch.tensor(Xi, dtype=torch.float64), m0t, P0t, dt, torch.as_tensor(ys[0, :Tp]), 1)
+    gw, = torch.autograd.grad(want, th)
+    th2 = torch.tensor(theta_np[2], dtype=torch.float64, device='cuda', requires_grad=True)
+    _, _, mc2, m02, P02, _ = cg.build_chirp_model(gfun(th2))
+    got = mle.ekf_nll(mc2, H, Xi, m02, P02, dt, ys[0, :Tp])
+    gg, = torch.autograd.grad(got, th2)
+    npt.assert_allclose(got.item(), want.item(), rtol=1e-11)
+    npt.assert_allclose(gg.cpu().numpy(), gw.numpy(), rtol=1e-7, atol=1e-9)
+
+
 def test_candidate_grid_and_fit():
     B, T, dt = 4, 400, 1e-3
     _, ys, _ = toymodels.synthetic_batch(B, 3141, dt, Xi=0.1, seed=5)

@@ -1,16 +1,19 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
 
 Tolerances (float64), stated once:
-  * golden fixtures (T <= 400):     means / covariances  |a - b| <= 1e-11 + 1e-9 |b|  (d = 8 cubature: 1e-10);
-  * full-length runs (T = 3141):    |a - b| <= ATOL_LONG + 1e-9 |b|, ATOL_LONG = 5e-9 (d = 4), 2e-8 (d = 8); states
-    and covariances are O(1)-O(10) and components that oscillate through zero cannot meet a relative bound;
-  * cumulative nll:                 rtol 1e-11 (fixtures), 1e-10 (T = 3141).
-They are set by the summation-order noise floor of the reference algorithm itself (the uncentred sigma-point
-covariance, filters_smoothers.py:120, cancels 4-5 digits).  Measured on the CPU oracle by doing nothing but
-permuting the sigma points (tests/test_noise_floor.py), T = 3141, 4 chirps:
-    chirp d=4, GH order 3:   filter mean 1.5e-10, smoother mean 4.4e-10, Ps 1.2e-10, nll 2.5e-12 (relative)
-    harmonic d=8, cubature:  filter mean 8.5e-10, smoother mean 1.2e-9,  Ps 1.9e-10, nll 1.9e-11 (relative)
-The long-run tolerances are ~10x those figures."""
+  * golden fixtures and every run with T <= 500, and ALL runs of the filters / smoothers without an uncentred sigma-point
+    covariance (kf, rts, ekf, ekf_for_kpt, cd_ekf, cd_eks, cd_sgp_filter, cd_sgp_smoother) at any length:
+        means / covariances  |a - b| <= 1e-11 + 1e-9 |b|   (SURVEY 8c;  d = 8 cubature fixtures: 1e-10),   nll rtol 1e-11;
+  * full-length discrete sigma-point runs (sgp_filter / sgp_smoother, T = 3141 and T = 20 000) and the full-length EKS:
+        |a - b| <= 3 x NOISE FLOOR + 1e-9 |b| per output, nll rtol 3 x its floor,
+    where the noise floor is what the REFERENCE ALGORITHM ITSELF moves by under a mathematically neutral change (permuting
+    the sigma points: the uncentred covariance of filters_smoothers.py:120 cancels 4-5 digits; transposing the EKF
+    covariances for the EKS), measured on the same data by tests/test_noise_floor.py and pinned in
+    tests/parity_tolerances.py -- e.g. chirp d = 4 Gauss-Hermite: filter mean 3.1e-10, smoother mean 8.6e-10, nll 6.5e-12.
+The margins every test actually achieves are written to gpurun_out/parity_report.txt (profiles/parity_r2.txt holds the
+committed copy): the CUDA path sits at or below 1.9 x the floor everywhere."""
+import os
+
 import numpy as np
 import numpy.testing as npt
 import pytest
@@ -19,30 +22,31 @@ import torch
 import chirpgp_b200 as cg
 from chirpgp_b200 import toymodels
 from oracle import oracle as orc
+from parity_tolerances import record, atol_long
 
 pytestmark = pytest.mark.gpu
 
 RT, AT = 1e-9, 1e-11
-ATOL_LONG = 5e-9
-ATOL_LONG_D8 = 2e-8
 AT_D8 = 1e-10
 NLL_RT = 1e-11
-NLL_RT_LONG = 1e-10     # cumulative sum over 3141 steps (harmonic d=8 reaches 2e-11)
 
 
-def _close(a, b, rtol=RT, atol=AT):
+def _close(a, b, rtol=RT, atol=AT, what=''):
+    test = os.environ.get('PYTEST_CURRENT_TEST', '').split('::')[-1].replace(' (call)', '')
+    record(test, what, a, b, rtol, atol)
     npt.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
 
 
-def _check_filter(got, want, atol=AT):
-    _close(got[0], want[0], atol=atol)
-    _close(got[1], want[1], atol=atol)
-    _close(got[2], want[2], rtol=NLL_RT if atol == AT else NLL_RT_LONG, atol=1e-9)
+def _check_filter(got, want, atol=AT, tag='', floor=None):
+    """floor = a key of parity_tolerances.NOISE_FLOOR: per-output tolerance 3 x floor (long sigma-point runs)."""
+    _close(got[0], want[0], atol=atol_long(floor, 'mf') if floor else atol, what=tag + ' mfs')
+    _close(got[1], want[1], atol=atol_long(floor, 'Pf') if floor else atol, what=tag + ' Pfs')
+    _close(got[2], want[2], rtol=max(NLL_RT, atol_long(floor, 'nll')) if floor else NLL_RT, atol=0., what=tag + ' n_ell')
 
 
-def _check_smoother(got, want, atol=AT):
-    _close(got[0], want[0], atol=atol)
-    _close(got[1], want[1], atol=atol)
+def _check_smoother(got, want, atol=AT, tag='', floor=None):
+    _close(got[0], want[0], atol=atol_long(floor, 'ms') if floor else atol, what=tag + ' mss')
+    _close(got[1], want[1], atol=atol_long(floor, 'Ps') if floor else atol, what=tag + ' Pss')
 
 
 class _SG:
@@ -122,9 +126,9 @@ def _run_all_nonlinear(z, builder, tags, atol=AT):
         for j, arr in enumerate(v):
             a = arr.cpu().numpy() if isinstance(arr, torch.Tensor) else arr
             if j == 2:
-                _close(a, z['%s_%d' % (k, j)], rtol=NLL_RT, atol=1e-9)
+                _close(a, z['%s_%d' % (k, j)], rtol=NLL_RT, atol=1e-9, what='%s[%d]' % (k, j))
             else:
-                _close(a, z['%s_%d' % (k, j)], atol=atol)
+                _close(a, z['%s_%d' % (k, j)], atol=atol, what='%s[%d]' % (k, j))
 
 
 @pytest.mark.parametrize('name,tags', [('chirp', ['gh3', 'cub']), ('chirp_lam0', ['gh3']), ('short', ['gh3'])])
@@ -164,10 +168,10 @@ def test_batched_ekf_eks_vs_oracle(batch):
     drift, disp, mc, m0, P0, H, spec = _chirp_setup()
     f = cg.ekf(mc, H, 0.1, m0, P0, dt, ys)
     fo = orc.ekf(spec, H, 0.1, m0, P0, dt, ys)
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, tag='ekf')
     s = cg.eks(mc, f[0], f[1], dt)
     so = orc.eks(spec, fo[0], fo[1], dt)
-    _check_smoother(s, so, ATOL_LONG)
+    _check_smoother(s, so, tag='eks', floor='chirp_eks')
 
 
 def test_batched_ghf_ghs_vs_oracle(batch):
@@ -176,10 +180,10 @@ def test_batched_ghf_ghs_vs_oracle(batch):
     sg = cg.SigmaPoints.gauss_hermite(4, 3)
     f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
     fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, floor='chirp_gh3', tag='sgp_filter')
     s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_smoother(s, so, ATOL_LONG)
+    _check_smoother(s, so, floor='chirp_gh3', tag='sgp_smoother')
 
 
 def test_batched_cd_vs_oracle(batch):
@@ -190,16 +194,16 @@ def test_batched_cd_vs_oracle(batch):
     sg = cg.SigmaPoints.gauss_hermite(4, 3)
     f = cg.cd_ekf(drift, disp, H, 0.1, m0, P0, dt, ys)
     fo = orc.cd_ekf(spec, Bm, H, 0.1, m0, P0, dt, ys)
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, tag='cd_ekf')
     s = cg.cd_eks(drift, disp, f[0], f[1], dt)
     so = orc.cd_eks(spec, Bm, fo[0], fo[1], dt)
-    _check_smoother(s, so, ATOL_LONG)
+    _check_smoother(s, so, tag='cd_eks')
     f = cg.cd_sgp_filter(drift, Bm, sg, H, 0.1, m0, P0, dt, ys)
     fo = orc.cd_sgp_filter(spec, Bm, sg, H, 0.1, m0, P0, dt, ys)
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, tag='cd_sgp_filter')
     s = cg.cd_sgp_smoother(drift, Bm, sg, f[0], f[1], dt)
     so = orc.cd_sgp_smoother(spec, Bm, sg, fo[0], fo[1], dt)
-    _check_smoother(s, so, ATOL_LONG)
+    _check_smoother(s, so, tag='cd_sgp_smoother')
 
 
 def test_batched_harmonic_ckf_cks_vs_oracle():
@@ -210,10 +214,10 @@ def test_batched_harmonic_ckf_cks_vs_oracle():
     sg = cg.SigmaPoints.cubature(8)
     f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
     fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
-    _check_filter(f, fo, ATOL_LONG_D8)
+    _check_filter(f, fo, floor='harmonic_cub', tag='sgp_filter')
     s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_smoother(s, so, ATOL_LONG_D8)
+    _check_smoother(s, so, floor='harmonic_cub', tag='sgp_smoother')
 
 
 def test_per_chirp_parameters_and_shared_signal(batch):
@@ -225,10 +229,10 @@ def test_per_chirp_parameters_and_shared_signal(batch):
     spec = orc.ChirpSpec(params[:, 0], params[:, 1], params[:, 3], params[:, 4])
     f = cg.ekf(mc, H, 0.1, m0, P0, dt, ys[:, :500])
     fo = orc.ekf(spec, H.numpy(), 0.1, m0.numpy(), P0.numpy(), dt, ys[:, :500])
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, tag='ekf')
     f1 = cg.ekf(mc, H, 0.1, m0, P0, dt, ys[3, :500])          # shared signal
     fo1 = orc.ekf(spec, H.numpy(), 0.1, m0.numpy(), P0.numpy(), dt, ys[3, :500])
-    _check_filter(f1, fo1, ATOL_LONG)
+    _check_filter(f1, fo1, tag='ekf')
 
 
 def test_edge_cases_T1_T2_and_cuda_tensors():
@@ -238,10 +242,10 @@ def test_edge_cases_T1_T2_and_cuda_tensors():
         ys = np.ones(T)
         f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, 1e-3, ys)
         fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, 1e-3, ys)
-        _check_filter(f, fo, ATOL_LONG)
+        _check_filter(f, fo, tag='sgp_filter')
         s = cg.sgp_smoother(mc, sg, f[0], f[1], 1e-3)
         so = orc.sgp_smoother(spec, sg, fo[0], fo[1], 1e-3)
-        _check_smoother(s, so, ATOL_LONG)
+        _check_smoother(s, so, tag='sgp_smoother')
         if T == 1:
             _close(s[0], f[0], rtol=0, atol=0)
     # CUDA tensors in -> CUDA tensors out
@@ -287,17 +291,18 @@ def test_fused_gains_ghf_ghs_vs_oracle(batch, T):
     ys = ys[:, :T]
     drift, disp, mc, m0, P0, H, spec = _chirp_setup()
     sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    floor = 'chirp_gh3' if T > 500 else None
     f = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
     rec = getattr(f[0], '_cgp_smoother_gains', None)
     assert rec is not None, 'the filter did not produce smoother gains'
     fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
-    _check_filter([x.cpu().numpy() for x in f], fo, ATOL_LONG)
+    _check_filter([x.cpu().numpy() for x in f], fo, floor=floor, tag='sgp_filter')
     s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_smoother([x.cpu().numpy() for x in s], so, ATOL_LONG)
+    _check_smoother([x.cpu().numpy() for x in s], so, floor=floor, tag='sgp_smoother')
     # the stand-alone smoother on the same filtering result (plain NumPy input: no attached gains) agrees to rounding
     s2 = cg.sgp_smoother(mc, sg, f[0].cpu().numpy(), f[1].cpu().numpy(), dt)
-    _check_smoother([x.cpu().numpy() for x in s], s2, ATOL_LONG)
+    _check_smoother([x.cpu().numpy() for x in s], s2, floor=floor, tag='sgp_smoother')
     # the gain records themselves: fused kernel vs the time-parallel gain kernel, through the C ABI
     import ctypes as C
     from chirpgp_b200 import _native as N
@@ -316,8 +321,8 @@ def test_fused_gains_ghf_ghs_vs_oracle(batch, T):
     torch.cuda.synchronize()
     a = rec.ws.reshape(B, T, 36)[:, :T - 1].cpu().numpy()
     b = ws.reshape(B, T, 36)[:, :T - 1].cpu().numpy()
-    _close(a[..., 16:], b[..., 16:], atol=ATOL_LONG)          # mp, Pp
-    _close(a[..., :16], b[..., :16], rtol=1e-7, atol=1e-9)    # G = D Pp^{-1}: conditioning of Pp amplifies rounding
+    _close(a[..., 16:], b[..., 16:], atol=atol_long('chirp_gh3', 'mf') if floor else AT, what='workspace mp, Pp')          # mp, Pp
+    _close(a[..., :16], b[..., :16], rtol=1e-7, atol=1e-9, what='workspace gain G')    # G = D Pp^{-1}: conditioning of Pp amplifies rounding
 
 
 def test_fused_gains_are_dropped_when_inputs_change(batch):
@@ -346,7 +351,7 @@ def test_fused_gains_are_dropped_when_inputs_change(batch):
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
     # (d) untouched inputs use the gains and agree with the stand-alone smoother to rounding
     got = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
-    _check_smoother([x.cpu().numpy() for x in got], [x.cpu().numpy() for x in ref], ATOL_LONG)
+    _check_smoother([x.cpu().numpy() for x in got], [x.cpu().numpy() for x in ref], tag='sgp_smoother')
     # (e) opt-out
     f3 = cg.sgp_filter(mc, sg, *args, smoother_gains=False)
     assert getattr(f3[0], '_cgp_smoother_gains', None) is None
@@ -451,14 +456,14 @@ def test_kpt_batched_vs_oracle(batch):
         f = cg.ekf_for_kpt(F, Sigma, h, 0.1, m0, P0, dt, yy)
         Fo = np.broadcast_to(F.numpy(), Sigma.shape).copy()
         fo = orc.ekf_for_kpt(Fo, Sigma.numpy(), nh, 0.1, m0.numpy(), P0.numpy(), yy)
-        _check_filter(f, fo, ATOL_LONG)
+        _check_filter(f, fo, tag='ekf_for_kpt')
         assert np.all(np.isfinite(f[0]))
     # shared parameters: rts on the filtering result
     F, Sigma, m0, P0, h = cg.build_kpt_chirp_model(np.array([0.02, 1e-3, 1e-2, 8., 1.]), 1. / dt, 3)
     f = cg.ekf_for_kpt(F, Sigma, h, 0.1, m0, P0, dt, yy)
     s = cg.rts(F, Sigma, f[0], f[1])
     so = orc.rts(F.numpy(), Sigma.numpy(), f[0], f[1])
-    _check_smoother(s, so, ATOL_LONG)
+    _check_smoother(s, so, tag='rts')
 
 
 def test_large_batch_onepass_eks_and_wide_stores():
@@ -474,18 +479,18 @@ def test_large_batch_onepass_eks_and_wide_stores():
     s_lo = cg.eks(mc, f[0][:half], f[1][:half], dt)                  # two kernels
     s_hi = cg.eks(mc, f[0][half:], f[1][half:], dt)
     for j in range(2):
-        _close(s[j][:half], s_lo[j], atol=ATOL_LONG)
-        _close(s[j][half:], s_hi[j], atol=ATOL_LONG)
+        _close(s[j][:half], s_lo[j], atol=AT, what='one-pass vs two-kernel eks')
+        _close(s[j][half:], s_hi[j], atol=AT, what='one-pass vs two-kernel eks')
     pick = np.r_[0:16, B - 5:B]
     fo = orc.ekf(spec, H, 0.1, m0, P0, dt, ys[pick])
-    _check_filter([x[pick] for x in f], fo, ATOL_LONG)
+    _check_filter([x[pick] for x in f], fo, tag='eks')
     so = orc.eks(spec, fo[0], fo[1], dt)
-    _check_smoother([x[pick] for x in s], so, ATOL_LONG)
+    _check_smoother([x[pick] for x in s], so, tag='eks')
     F = np.array([[0.9, 0.1], [0., 0.8]]); Sigma = np.diag([0.1, 0.2])
     fk = cg.kf(F, Sigma, np.array([1., 0.]), 0.5, np.zeros(2), np.eye(2), ys)
     sk = cg.rts(F, Sigma, fk[0], fk[1])
     sko = orc.rts(F, Sigma, fk[0][pick], fk[1][pick])
-    _check_smoother([x[pick] for x in sk], sko, ATOL_LONG)
+    _check_smoother([x[pick] for x in sk], sko, tag='rts')
 
 
 def test_full_size_config2_properties():
@@ -505,7 +510,7 @@ def test_full_size_config2_properties():
     s2 = cg.sgp_smoother(mc, sg, f2[0], f2[1], dt)
     for a, b in zip(f + s, f2 + s2):
         assert torch.isfinite(a).all()
-        _close(a.cpu().numpy(), b.cpu().numpy(), atol=ATOL_LONG)
+        _close(a.cpu().numpy(), b.cpu().numpy(), atol=atol_long('chirp_gh3', 'ms'), what='fused vs stand-alone')
     assert torch.equal(s[0][:, -1], f[0][:, -1]) and torch.equal(s[1][:, -1], f[1][:, -1])
     assert torch.equal(f[1], f[1].transpose(-1, -2))                       # packed-symmetric arithmetic: exact
     sym = (s[1] - s[1].transpose(-1, -2)).abs().max().item()
@@ -516,8 +521,71 @@ def test_full_size_config2_properties():
     pick = np.arange(0, B, 64)
     fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys[pick])
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_filter([x[pick].cpu().numpy() for x in f], fo, ATOL_LONG)
-    _check_smoother([x[pick].cpu().numpy() for x in s], so, ATOL_LONG)
+    _check_filter([x[pick].cpu().numpy() for x in f], fo, floor='chirp_gh3', tag='sgp_filter')
+    _check_smoother([x[pick].cpu().numpy() for x in s], so, floor='chirp_gh3', tag='sgp_smoother')
+
+
+def _size_independent_properties(f, s, sym_exact=True, var_contracts=True):
+    """Properties that hold at any size: finite; the last smoothed step is the last filtering step
+    (filters_smoothers.py:140-142); covariances symmetric; smoothing never increases a marginal variance (discrete smoothers:
+    Ps = Pf - G (Pp - Ps) G^T; NOT a property of the continuous-discrete smoothers, whose backward moment ODE is linearised
+    and integrated with one RK4 step per sample); the cumulative nll moves by increments bounded below."""
+    for a in f + s:
+        assert torch.isfinite(a).all()
+    assert torch.equal(s[0][:, -1], f[0][:, -1]) and torch.equal(s[1][:, -1], f[1][:, -1])
+    if sym_exact:
+        assert torch.equal(f[1], f[1].transpose(-1, -2))                   # packed-symmetric arithmetic: exact
+    assert (s[1] - s[1].transpose(-1, -2)).abs().max().item() < 1e-12
+    if var_contracts:
+        dvar = (torch.diagonal(s[1], dim1=-2, dim2=-1) - torch.diagonal(f[1], dim1=-2, dim2=-1)).max().item()
+        assert dvar < 1e-9, dvar
+    assert (f[2][:, 1:] - f[2][:, :-1]).min().item() > -20.
+
+
+def test_full_size_config3_properties():
+    """BASELINE configs[2] at full size (1000 chirps x 3141 steps): cd_ekf + cd_eks and cd_sgp_filter + cd_sgp_smoother, one
+    RK4 step per sample, through size-independent properties and a 16-chirp sample against the oracle (nominal tolerance: the
+    continuous-discrete moments are centred, there is no cancellation noise)."""
+    B, T, dt = 1000, 3141, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, T, dt, Xi=0.1, seed=2)
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    Bm = disp(None).numpy()
+    ys_d, H_d, m0_d, P0_d = _cuda(ys), _cuda(H), _cuda(m0), _cuda(P0)
+    pick = np.arange(0, B, 64)
+    f = cg.cd_ekf(drift, disp, H_d, 0.1, m0_d, P0_d, dt, ys_d)
+    s = cg.cd_eks(drift, disp, f[0], f[1], dt)
+    _size_independent_properties(f, s, var_contracts=False)
+    fo = orc.cd_ekf(spec, Bm, H, 0.1, m0, P0, dt, ys[pick])
+    so = orc.cd_eks(spec, Bm, fo[0], fo[1], dt)
+    _check_filter([x[pick].cpu().numpy() for x in f], fo, tag='cd_ekf')
+    _check_smoother([x[pick].cpu().numpy() for x in s], so, tag='cd_eks')
+    g = cg.cd_sgp_filter(drift, _cuda(Bm), sg, H_d, 0.1, m0_d, P0_d, dt, ys_d)
+    sgs = cg.cd_sgp_smoother(drift, _cuda(Bm), sg, g[0], g[1], dt)
+    _size_independent_properties(g, sgs, var_contracts=False)
+    go = orc.cd_sgp_filter(spec, Bm, sg, H, 0.1, m0, P0, dt, ys[pick])
+    gso = orc.cd_sgp_smoother(spec, Bm, sg, go[0], go[1], dt)
+    _check_filter([x[pick].cpu().numpy() for x in g], go, tag='cd_sgp_filter')
+    _check_smoother([x[pick].cpu().numpy() for x in sgs], gso, tag='cd_sgp_smoother')
+
+
+def test_full_size_config4_properties():
+    """BASELINE configs[3] at full size: 1000 harmonic chirps (3 harmonics, d = 8) x 3141 steps, cubature sgp_filter +
+    sgp_smoother; properties + the first 8 chirps against the oracle at 3 x the pinned noise floor of that very data."""
+    B, T, dt = 1000, 3141, 1e-3
+    _, ys, _ = toymodels.synthetic_batch(B, T, dt, Xi=0.1, num_harmonics=3, seed=4)
+    _, ys8, _ = toymodels.synthetic_batch(8, T, dt, Xi=0.1, num_harmonics=3, seed=4)
+    assert np.array_equal(ys[:8], ys8)                                     # chirp i depends on (seed, i) only
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup(h=3)
+    m0 = np.array([0., 1., 0., 1., 0., 1., 7., 0.])
+    sg = cg.SigmaPoints.cubature(8)
+    f = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    _size_independent_properties(f, s)
+    fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys[:8])
+    so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+    _check_filter([x[:8].cpu().numpy() for x in f], fo, floor='harmonic_cub', tag='sgp_filter d=8')
+    _check_smoother([x[:8].cpu().numpy() for x in s], so, floor='harmonic_cub', tag='sgp_smoother d=8')
 
 
 def test_fused_kernel_is_deterministic_under_load():
@@ -563,12 +631,12 @@ def test_general_measurement_row_and_nan_inputs_on_the_fused_path(batch):
     fo = orc.sgp_filter(spec, sg, Hg, 0.1, m0, P0, dt, ys)
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
     f = cg.sgp_filter(mc, sg, Hg, 0.1, m0, P0, dt, ys)                           # NumPy in: plain kernel
-    _check_filter(f, fo, ATOL_LONG)
+    _check_filter(f, fo, tag='sgp_filter')
     fd = cg.sgp_filter(mc, sg, _cuda(Hg), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))      # fused kernel
     assert getattr(fd[0], '_cgp_smoother_gains', None) is not None
     sd = cg.sgp_smoother(mc, sg, fd[0], fd[1], dt)
-    _check_filter([x.cpu().numpy() for x in fd], fo, ATOL_LONG)
-    _check_smoother([x.cpu().numpy() for x in sd], so, ATOL_LONG)
+    _check_filter([x.cpu().numpy() for x in fd], fo, tag='sgp_smoother')
+    _check_smoother([x.cpu().numpy() for x in sd], so, tag='sgp_smoother')
     ys[2, 50] = np.nan
     fn = cg.sgp_filter(mc, sg, _cuda(Hg), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
     sn = cg.sgp_smoother(mc, sg, fn[0], fn[1], dt)
@@ -590,11 +658,11 @@ def test_sgp_filter_smoother_one_call(batch):
     f = cg.sgp_filter(mc, sg, H, 0.1, m0, P0, dt, ys)
     s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
     for a, b in zip(out, f + s):
-        _close(a, b, atol=ATOL_LONG)
+        _close(a, b, what='one call vs two calls')
     fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_filter(out[:3], fo, ATOL_LONG)
-    _check_smoother(out[3:], so, ATOL_LONG)
+    _check_filter(out[:3], fo, tag='sgp_smoother')
+    _check_smoother(out[3:], so, tag='sgp_smoother')
 
 
 def test_long_sequence_fused_path():
@@ -612,11 +680,11 @@ def test_long_sequence_fused_path():
     f2 = cg.sgp_filter(mc, sg, *args, smoother_gains=False)
     s2 = cg.sgp_smoother(mc, sg, f2[0], f2[1], dt)
     assert torch.equal(f[0], f2[0]) and torch.equal(f[1], f2[1]) and torch.equal(f[2], f2[2])
-    _check_smoother([x.cpu().numpy() for x in s], [x.cpu().numpy() for x in s2], 2e-8)
+    _check_smoother([x.cpu().numpy() for x in s], [x.cpu().numpy() for x in s2], floor='chirp_gh3_T20000', tag='fused vs stand-alone')
     fo = orc.sgp_filter(spec, sg, H, Xi, m0, P0, dt, ys[:2])
     so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
-    _check_filter([x[:2].cpu().numpy() for x in f], fo, 2e-8)
-    _check_smoother([x[:2].cpu().numpy() for x in s], so, 2e-8)
+    _check_filter([x[:2].cpu().numpy() for x in f], fo, floor='chirp_gh3_T20000', tag='sgp_filter')
+    _check_smoother([x[:2].cpu().numpy() for x in s], so, floor='chirp_gh3_T20000', tag='sgp_smoother')
 
 
 def test_filter_smoother_pairs_and_readout():
