@@ -129,13 +129,16 @@ ffi::Error NllFwdImpl(cudaStream_t stream, int64_t num_harmonics, int64_t ys_rep
 }
 ffi::Error NllBwdImpl(cudaStream_t stream, int64_t num_harmonics, int64_t ys_repeat, int64_t h_unit_index, int64_t ckpt_every,
                       double Xi, double dt, F64 ys, F64 consts, F64 m0, F64 P0, F64 H, F64 nll_bar, F64 ws, RF64 consts_bar,
-                      RF64 m0_bar, RF64 P0_bar, RF64 Xi_bar) {
+                      RF64 m0_bar, RF64 P0_bar, RF64 Xi_bar, RF64 ws_out) {
+    // the workspace is read AND written by the adjoint kernel: the caller aliases the operand `ws` to the result `ws_out`
+    // (input_output_aliases={6: 4} in chirpgp_b200/jax_ffi.py), so this is the same buffer and XLA knows it is mutated
+    if (ws_out->typed_data() != ws.typed_data()) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "ws must be aliased to ws_out");
     const int64_t d = 2 * num_harmonics + 2, B = nll_bar.element_count(), T = ys.dimensions().back();
     const Attrs a{CGP_MODEL_LCD, num_harmonics, 0, 0, ys_repeat, h_unit_index, Xi, dt};
     CgpProblem p = make_problem(a, B, T, d, consts, m0.typed_data(), m0.element_count() / d, P0.typed_data(),
                                 P0.element_count() / (d * d), H.typed_data(), nullptr, 1, nullptr, nullptr, 0);
-    return status(cgp_ekf_nll_bwd_f64(&p, ys.typed_data(), nll_bar.typed_data(), const_cast<double *>(ws.typed_data()),
-                                      ws.element_count() * sizeof(double), ckpt_every, consts_bar->typed_data(), m0_bar->typed_data(),
+    return status(cgp_ekf_nll_bwd_f64(&p, ys.typed_data(), nll_bar.typed_data(), ws_out->typed_data(),
+                                      ws_out->element_count() * sizeof(double), ckpt_every, consts_bar->typed_data(), m0_bar->typed_data(),
                                       P0_bar->typed_data(), Xi_bar->typed_data(), stream), "chirpgp_b200 ekf_nll bwd");
 }
 
@@ -156,7 +159,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpFilterGains, FilterGainsImpl,
                                   .Attr<int64_t>("gh_order").Attr<int64_t>("ys_repeat").Attr<int64_t>("h_unit_index")
                                   .Attr<double>("Xi").Attr<double>("dt")
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
-                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
+                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpSmootherSweep, SweepImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>());
@@ -175,4 +178,4 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(CgpEkfNllBwd, NllBwdImpl,
                                   .Attr<int64_t>("num_harmonics").Attr<int64_t>("ys_repeat").Attr<int64_t>("h_unit_index")
                                   .Attr<int64_t>("ckpt_every").Attr<double>("Xi").Attr<double>("dt")
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
-                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
+                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
