@@ -6,7 +6,7 @@ namespace cgp {
 
 template <class T> struct Tag { using type = T; };
 
-// Compiled state dimensions.  Linear models: d in 1..5 (5: rts after ekf_for_kpt with three harmonics).  Chirp family: num_harmonics in 1..3 (d = 4, 6, 8).
+// Compiled state dimensions.  Linear models: d in 1..5 (5: rts after ekf_for_kpt with three harmonics).  Chirp family: discrete (LCD) models num_harmonics in 1..5 (d = 4 .. 12), SDE drifts 1..3.
 template <class F> int dispatch_disc(const CgpProblem &p, F &&f) {
     if (p.model == CGP_MODEL_LINEAR_DISC) {
         switch (p.d) {
@@ -24,6 +24,8 @@ template <class F> int dispatch_disc(const CgpProblem &p, F &&f) {
             case 1: return f(Tag<ModelLCD<1>>{});
             case 2: return f(Tag<ModelLCD<2>>{});
             case 3: return f(Tag<ModelLCD<3>>{});
+            case 4: return f(Tag<ModelLCD<4>>{});       // d = 10: real_applications/bats/myotis_myotis_analysis.py:50
+            case 5: return f(Tag<ModelLCD<5>>{});       // d = 12
             default: return CGP_ERR_UNSUPPORTED;
         }
     }

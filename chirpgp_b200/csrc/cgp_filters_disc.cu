@@ -1,5 +1,7 @@
 // kf / ekf / sgp_filter launchers (discrete-time models).
+#include <stdlib.h>
 #include "cgp_dispatch.cuh"
+#include "cgp_multi.cuh"
 
 namespace cgp {
 
@@ -69,6 +71,16 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s
                         // filter + smoother gains: producer / consumer warp pair per chirp (cgp_duo.cuh)
                         if (p.h_unit_index == 1) gh_duo_filter_kernel<true><<<(unsigned)p.B, 64, 0, s>>>(p, io);
                         else gh_duo_filter_kernel<false><<<(unsigned)p.B, 64, 0, s>>>(p, io);
+                        return check_launch();
+                    }
+                    // experiment (profiles/r2_multi_chirp.txt): NCH chirps interleaved per warp, nll-only
+                    const char *mv = getenv("CGP_GH_MULTI");
+                    const int nch = (mv && *mv) ? atoi(mv) : 0;
+                    if (nch >= 1 && nch <= 3 && io.mfs == nullptr && io.nell && io.nell_last_only && p.h_unit_index == 1) {
+                        const unsigned grid = (unsigned)ceil_div(p.B, nch);
+                        if (nch == 1) gh_warp_multi_nll_kernel<1, true><<<grid, 32, 0, s>>>(p, io.ys, io.nell);
+                        else if (nch == 2) gh_warp_multi_nll_kernel<2, true><<<grid, 32, 0, s>>>(p, io.ys, io.nell);
+                        else gh_warp_multi_nll_kernel<3, true><<<grid, 32, 0, s>>>(p, io.ys, io.nell);
                         return check_launch();
                     }
                     if (p.h_unit_index == 1) gh_warp_filter_kernel<Pred, false, true><<<(unsigned)p.B, 32, 0, s>>>(p, io);

@@ -406,7 +406,9 @@ template <class Model, int G, bool CD> struct GroupCfg {
     static constexpr int NA = CD ? D + D * D : D + NSym<D>::value;
     static constexpr bool kSmem = G > 1 && NA >= 24;
     static constexpr int kPerGroup = GroupSmem<NA, G>::kDoubles;
-    static constexpr int kBlock = (kSmem && (128 / G) * kPerGroup * 8 > 40960) ? 64 : 128;
+    static constexpr bool kFits128 = !kSmem || (128 / G) * kPerGroup * 8 <= 40960;
+    static constexpr bool kFits64 = !kSmem || (64 / G) * kPerGroup * 8 <= 40960;
+    static constexpr int kBlock = kFits128 ? 128 : ((kFits64 || G > 32) ? 64 : 32);        // d = 12: one 32-lane block
     static constexpr int kGroups = kBlock / G;
 };
 

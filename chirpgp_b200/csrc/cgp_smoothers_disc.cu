@@ -23,6 +23,8 @@ template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &
                 return check_launch();
             }
             using Cfg = SweepCfg<D>;
+            if (Cfg::smem_bytes() > 48 * 1024)             // d >= 10: opt in to the large dynamic shared-memory carve-out
+                cudaFuncSetAttribute(smoother_sweep_warp_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes());
             smoother_sweep_warp_kernel<D><<<(unsigned)p.B, 32, Cfg::smem_bytes(), s>>>(p, io);
             return check_launch();
         }
@@ -97,6 +99,8 @@ int launch_smoother_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_
         case 5: return launch_sweep<5>(p, io, s);
         case 6: return launch_sweep<6>(p, io, s);
         case 8: return launch_sweep<8>(p, io, s);
+        case 10: return launch_sweep<10>(p, io, s);
+        case 12: return launch_sweep<12>(p, io, s);
         default: return CGP_ERR_UNSUPPORTED;
     }
 }
