@@ -392,8 +392,22 @@ CGP_DEV void reverse_step(const ModelLCD<NH> &mdl, const double (&H)[2 * NH + 2]
     cy.fb[3] += mpb[V + 1] * m[V + 1] + Jb[V + 1][V + 1];
 }
 
-template <int NH, bool H_E1, bool RAW>
-__global__ void __launch_bounds__(128, (NH == 1 ? 3 : 1))
+// Named barriers of the PAIR variant (ids are immediates: a register id would reserve all 16 barriers of the CTA).
+#define CGP_NB(op, id) asm volatile(op " " #id ", 64;" ::: "memory")
+CGP_DEV void pair_full_arrive(int slot) { if (slot) CGP_NB("bar.arrive", 2); else CGP_NB("bar.arrive", 1); }
+CGP_DEV void pair_full_sync(int slot) { if (slot) CGP_NB("bar.sync", 2); else CGP_NB("bar.sync", 1); }
+CGP_DEV void pair_empty_arrive(int slot) { if (slot) CGP_NB("bar.arrive", 4); else CGP_NB("bar.arrive", 3); }
+CGP_DEV void pair_empty_sync(int slot) { if (slot) CGP_NB("bar.sync", 4); else CGP_NB("bar.sync", 3); }
+CGP_DEV void pair_ticket_sync() { CGP_NB("bar.sync", 5); }
+#undef CGP_NB
+
+// PAIR (few chains: every SM sub-partition would run a single warp, which cannot hide its own dependency stalls): the CTA is
+// a PAIR of warps working on the same unit.  Warp 0 recomputes segment after segment into two alternating scratch slots, warp
+// 1 sweeps them in reverse -- the two halves of the adjoint are independent dependency chains, and on separate warps the
+// hardware interleaves them (writing both into one loop body of one warp did not: profiles/r2_nll_sweeps.txt).  Hand-over:
+// one FULL and one EMPTY named barrier per slot (arrive by one warp, sync by the other, strictly alternating).
+template <int NH, bool H_E1, bool RAW, bool PAIR>
+__global__ void __launch_bounds__(PAIR ? 64 : 128, (NH == 1 ? (PAIR ? 6 : 3) : 1))
 bwd_kernel(const CgpProblem p, const double *__restrict__ ys, const double *__restrict__ nll_bar, const double *__restrict__ ckpt,
            double *__restrict__ scratch, double *__restrict__ carry, const Geo g, unsigned *__restrict__ sched_words,
            double *__restrict__ consts_bar, double *__restrict__ m0_bar, double *__restrict__ P0_bar, double *__restrict__ Xi_bar) {
@@ -403,12 +417,27 @@ bwd_kernel(const CgpProblem p, const double *__restrict__ ys, const double *__re
     const int lane = threadIdx.x & 31;
     const Sched sched{sched_words};
     const unsigned long long total = (unsigned long long)g.nunits * (unsigned long long)g.nchains;
-    const int64_t worker = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    double *__restrict__ slot0 = scratch + worker * ((int64_t)g.every * REC * kLanes) + lane;
+    const int64_t slot_doubles = (int64_t)g.every * REC * kLanes;
+    // scratch slots: one per warp; the PAIR variant uses the two slots of its CTA's two warps alternately
+    const int64_t worker = PAIR ? (int64_t)blockIdx.x * 2 : ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double *__restrict__ slot0 = scratch + worker * slot_doubles + lane;
+    const int role = PAIR ? (int)(threadIdx.x >> 5) : 0;           // PAIR: 0 = recompute, 1 = reverse
+    __shared__ unsigned long long pair_ticket;
+    if constexpr (PAIR) {
+        if (role == 1) { pair_empty_arrive(0); pair_empty_arrive(1); }    // both slots start empty
+    }
     double H[D];
     CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
     for (;;) {
-        const unsigned long long n = sched.ticket(lane);
+        unsigned long long n;
+        if constexpr (PAIR) {
+            if (role == 0 && lane == 0) pair_ticket = atomicAdd(reinterpret_cast<unsigned long long *>(sched_words), 1ull);
+            pair_ticket_sync();
+            n = pair_ticket;
+            pair_ticket_sync();                                    // both warps have read it before it is overwritten
+        } else {
+            n = sched.ticket(lane);
+        }
         if (n >= total) break;
         const int round = (int)(n / (unsigned)g.nchains), c = (int)(n % (unsigned)g.nchains);
         const int s_hi = g.nseg - 1 - round * g.spu, s_lo = (s_hi - g.spu + 1 > 0) ? s_hi - g.spu + 1 : 0;
@@ -470,11 +499,33 @@ bwd_kernel(const CgpProblem p, const double *__restrict__ ys, const double *__re
         };
 
         Carry<NH, RAW> cy;
-        for (int s = s_hi; s >= s_lo; s--) {
-            recompute(s, slot0);                           // independent of the chain's reverse state: runs before the wait
-            if (s == s_hi && !load_carry(cy)) return;
-            const double *__restrict__ y = yrow + (int64_t)s * g.every;
-            for (int j = seg_len(s) - 1; j >= 0; j--) rev_step(j, y, slot0, cy);
+        if constexpr (PAIR) {
+            if (role == 0) {
+                for (int s = s_hi; s >= s_lo; s--) {
+                    const int sl = (s_hi - s) & 1;
+                    pair_empty_sync(sl);
+                    recompute(s, slot0 + sl * slot_doubles);
+                    __threadfence_block();
+                    pair_full_arrive(sl);
+                }
+                continue;                                          // the reverse warp finishes the unit
+            }
+            const bool ok = load_carry(cy);                        // an aborted wait still drains the hand-over below
+            for (int s = s_hi; s >= s_lo; s--) {
+                const int sl = (s_hi - s) & 1;
+                pair_full_sync(sl);
+                const double *__restrict__ y = yrow + (int64_t)s * g.every;
+                for (int j = seg_len(s) - 1; j >= 0; j--) rev_step(j, y, slot0 + sl * slot_doubles, cy);
+                pair_empty_arrive(sl);
+            }
+            if (!ok) continue;
+        } else {
+            for (int s = s_hi; s >= s_lo; s--) {
+                recompute(s, slot0);                       // independent of the chain's reverse state: runs before the wait
+                if (s == s_hi && !load_carry(cy)) return;
+                const double *__restrict__ y = yrow + (int64_t)s * g.every;
+                for (int j = seg_len(s) - 1; j >= 0; j--) rev_step(j, y, slot0, cy);
+            }
         }
         if (s_lo > 0) {
             double *q = carry + (int64_t)c * (NCARRY * kLanes) + lane;
@@ -545,7 +596,9 @@ static Plan make_plan(const CgpProblem &p, int64_t every) {
     pl.nchains = (p.B + pl.lanes - 1) / pl.lanes;
     const int64_t cap = (int64_t)pl.sms * kMaxBlocksPerSM * 4;
     const int64_t chains4 = (pl.nchains + 3) / 4 * 4;          // blocks hold 4 warps
-    pl.workers_max = chains4 < cap ? chains4 : cap;
+    pl.workers_max = chains4 < cap ? chains4 : cap;            // scratch slots = persistent warps ...
+    const int64_t pairs2 = 2 * (pl.nchains < (int64_t)pl.sms * 4 ? pl.nchains : (int64_t)pl.sms * 4);
+    if (pl.workers_max < pairs2) pl.workers_max = pairs2;      // ... or two per recompute / reverse pair
     const size_t sched_bytes = align_up((size_t)(4 + pl.nchains) * sizeof(unsigned), 256);
     size_t off = 0;
     pl.off_sched_f = off; off += sched_bytes;
@@ -626,25 +679,44 @@ int nll2_fwd(const CgpProblem &p, const double *ys, double *nll, void *workspace
     }
 }
 
-template <int NH, bool H_E1, bool RAW>
-static int bwd_launch(const CgpProblem &p, const double *ys, const double *nll_bar, char *ws, const Plan &pl, double *consts_bar,
-                      double *m0_bar, double *P0_bar, double *Xi_bar, cudaStream_t s) {
+template <int NH, bool H_E1, bool RAW, bool PAIR>
+static int bwd_launch_v(const CgpProblem &p, const double *ys, const double *nll_bar, char *ws, const Plan &pl, double *consts_bar,
+                        double *m0_bar, double *P0_bar, double *Xi_bar, cudaStream_t s) {
+    constexpr int kBlockThreads = PAIR ? 64 : 128;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bwd_kernel<NH, H_E1, RAW>, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
-    per_sm = env_int("CGP_NLL_KB", per_sm);
-    if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
-    const int grid = grid_blocks(pl, per_sm);
-    if ((int64_t)grid * 4 > pl.workers_max) return CGP_ERR_WORKSPACE;      // one scratch slot per persistent warp
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bwd_kernel<NH, H_E1, RAW, PAIR>, kBlockThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int grid;
+    if (PAIR) {
+        // one pair per chain, at most one pair per SM sub-partition
+        const int64_t cap = (int64_t)pl.sms * 4;
+        grid = (int)(pl.nchains < cap ? pl.nchains : cap);
+        if ((int64_t)grid * 2 > pl.workers_max) return CGP_ERR_WORKSPACE;
+    } else {
+        if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
+        per_sm = env_int("CGP_NLL_KB", per_sm);
+        if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
+        grid = grid_blocks(pl, per_sm);
+        if ((int64_t)grid * 4 > pl.workers_max) return CGP_ERR_WORKSPACE;  // one scratch slot per persistent warp
+    }
     unsigned *sched = reinterpret_cast<unsigned *>(ws + pl.off_sched_b);
     cudaError_t e = cudaMemsetAsync(sched, 0, (size_t)(4 + pl.nchains) * sizeof(unsigned), s);
     if (e != cudaSuccess) return (int)e;
-    bwd_kernel<NH, H_E1, RAW><<<grid, 128, 0, s>>>(p, ys, nll_bar, reinterpret_cast<const double *>(ws + pl.off_ckpt),
-                                                   reinterpret_cast<double *>(ws + pl.off_scratch),
-                                                   reinterpret_cast<double *>(ws + pl.off_carry),
-                                                   make_geo(pl, env_int("CGP_NLL_UNIT_B", 128)), sched, consts_bar, m0_bar, P0_bar,
-                                                   Xi_bar);
+    bwd_kernel<NH, H_E1, RAW, PAIR><<<grid, kBlockThreads, 0, s>>>(
+        p, ys, nll_bar, reinterpret_cast<const double *>(ws + pl.off_ckpt), reinterpret_cast<double *>(ws + pl.off_scratch),
+        reinterpret_cast<double *>(ws + pl.off_carry), make_geo(pl, env_int("CGP_NLL_UNIT_B", PAIR ? 512 : 128)), sched, consts_bar,
+        m0_bar, P0_bar, Xi_bar);
     return check_launch();
+}
+template <int NH, bool H_E1, bool RAW>
+static int bwd_launch(const CgpProblem &p, const double *ys, const double *nll_bar, char *ws, const Plan &pl, double *consts_bar,
+                      double *m0_bar, double *P0_bar, double *Xi_bar, cudaStream_t s) {
+    if constexpr (NH == 1) {
+        // fewer than 1.5 chains per SM sub-partition: recompute / reverse warp pairs
+        if (env_int("CGP_NLL_PAIR", 2 * pl.nchains < 3 * (int64_t)pl.sms * 4 ? 1 : 0) != 0)
+            return bwd_launch_v<NH, H_E1, RAW, true>(p, ys, nll_bar, ws, pl, consts_bar, m0_bar, P0_bar, Xi_bar, s);
+    }
+    return bwd_launch_v<NH, H_E1, RAW, false>(p, ys, nll_bar, ws, pl, consts_bar, m0_bar, P0_bar, Xi_bar, s);
 }
 
 int nll2_bwd(const CgpProblem &p, const double *ys, const double *nll_bar, void *workspace, int64_t every, bool raw_p0_bar,
