@@ -521,6 +521,25 @@ def run_ours(args):
     ms_e2e_np, _, _ = timed_calls(numpy_api, max(2, n_e2e // 2))
     clocks = sampler.stop()              # sampled through the timed regions (serial, two-stream, end-to-end)
     freq_mean = float(out_r[0].mean())
+    # bare device->host ceiling with every rank copying at once: the 402 MB of Pss into an existing pinned buffer (what bounds
+    # e2e_full_outputs; the ranks of one box share the host's PCIe / DRAM path)
+    src = torch.empty((B_PER_GPU, T, D, D), dtype=torch.float64, device=dev)
+    dst = torch.empty((B_PER_GPU, T, D, D), dtype=torch.float64).pin_memory()
+    dst.copy_(src, non_blocking=True)
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_d2h = e0.elapsed_time(e1) / 3
+    del src, dst
+    try:
+        import jax  # noqa: F401
+        jax_note = 'importable: version %s' % getattr(jax, '__version__', '?')
+    except Exception:  # noqa: BLE001
+        jax_note = 'not installed (reference arm = C restatement; chirpgp_b200/jax_ffi.py never executed)'
 
     # ---- FP64 peak (DFMA-only kernel) on this GPU
     L = _native.lib()
@@ -557,9 +576,9 @@ def run_ours(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np, ms_d2h], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np = [float(x) for x in t.tolist()]
+        ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np, ms_d2h = [float(x) for x in t.tolist()]
     n_steps_total = world * B_PER_GPU * T
     value = n_steps_total / (ms_step * 1e-3)
 
@@ -595,12 +614,15 @@ def run_ours(args):
                     'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_e2e,
                     'ms_per_step_wall_clock': ms_e2e_wall, 'check_mean_frequency_hz': freq_mean,
                     'what': "blocking product call per step: cg.sgp_filter_smoother(m_and_cov, sgps, H, Xi, m0, P0, dt, ys_host, "
-                            "readout=('freq', 'v_var')) -- pinned host ys in; posterior frequency estimate E[g(V_k)] "
-                            "(gaussian_expectation on the device) and marginal variance out, 16 B/step (demos/ghfs_mle.py:87-89)"},
+                            "readout=('freq', 'v_var')) -- pinned host ys in (read in place over PCIe by the filter kernel: h2d bytes "
+                            "cross the bus inside the kernel); posterior frequency estimate E[g(V_k)] (gaussian_expectation on the "
+                            "device) and marginal variance out, 16 B/step (demos/ghfs_mle.py:87-89)"},
             'e2e_full_outputs': {'value': n_steps_total / (ms_e2e_full * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_full,
                                  'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D),
                                  'd2h_gb_per_s': B_PER_GPU * T * 8 * (D + D * D) / (ms_e2e_full * 1e-3) / 1e9,
-                                 'what': "same call with readout=('mss', 'Pss'): 160 B/step come back, PCIe-bound"},
+                                 'bare_d2h_gb_per_s_per_rank': B_PER_GPU * T * 8 * D * D / (ms_d2h * 1e-3) / 1e9,
+                                 'what': "same call with readout=('mss', 'Pss'): 160 B/step come back, PCIe-bound; bare_d2h = a plain "
+                                         "402 MB device->pinned-host copy issued by all ranks at once (max over ranks)"},
             'e2e_numpy_api': {'value': n_steps_total / (ms_e2e_np * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_np,
                               'what': 'literal drop-in: NumPy ys -> sgp_filter -> (mfs, Pfs, n_ell) NumPy -> sgp_smoother -> '
                                       '(mss, Pss) NumPy; blocking, filtering result goes down and up again'},
@@ -624,6 +646,7 @@ def run_ours(args):
                                'frac': 840. / cyc,
                                'source': 'profiles/sass_dyn.py (static schedule), profiles/microbench/fp64_latency.cu'},
             'cpu_baseline': cpu,
+            'jax': jax_note,
             'configs': other,
             'mle_sweep': mle_line,
         }

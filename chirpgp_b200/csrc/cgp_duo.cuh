@@ -65,6 +65,7 @@ struct DuoSmem4 {                       // D = 4 (chirp model)
     double ring2[32][WROW];
     double nl[32];
     double prevP[NS + 2];               // filtering covariance of the last step of the previous 32-block
+    double ybuf[2][32];                 // measurements of two 32-step blocks: written by the consumer, read by the producer
     int producer_warp;
     int consumed;                       // steps the consumer has finished reading (EMPTY side of the hand-over)
 };
@@ -90,6 +91,11 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         sm.producer_warp = (int)(((wid >> 2) ^ wid) & 1u);
         sm.consumed = 0;
     }
+    // Measurements: the CONSUMER fetches them, 32 per coalesced load, two blocks ahead of the producer, into a double buffer in
+    // shared memory -- no global load (and no register for a block in flight) on the chain, and the load latency stays hidden
+    // even when `ys` is pinned HOST memory read over PCIe (zero-copy input of host callers).  Blocks 0 and 1 before the loops:
+    const double *__restrict__ y = io.ys + (b / p.ys_repeat) * T;
+    sm.ybuf[warp][lane] = (32 * warp + lane < T) ? __ldg(y + 32 * warp + lane) : 0.;
     constexpr int BAR_FULL = 0;                             // barriers 0 .. NBUF - 1
     static_assert(NBUF <= 8, "named_bar_* cover ids 0..7");
     named_bar_sync(BAR_FULL);                               // (first use of barrier 0; completes before the loops start)
@@ -103,13 +109,14 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         load_vec<D>(p.m0 + b * p.m0_stride, m);
         load_sym<D>(p.P0 + b * p.P0_stride, Pc);
         CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
-        const double *__restrict__ y = io.ys + (b / p.ys_repeat) * T;
-        double yv = (lane < T) ? __ldg(y + lane) : 0.;      // 32 measurements per load, broadcast by shuffle
+        double yv = sm.ybuf[0][lane];                       // one block in a register, broadcast by shuffle
         int cons = 0;
         for (int64_t t = 0; t < T; t++) {
             const int slot = (int)(t & 31), buf = (int)(t % NBUF);
             const double yt = __shfl_sync(0xffffffffu, yv, slot);
-            if (slot == 31 && t + 1 < T) yv = (t + 1 + lane < T) ? __ldg(y + t + 1 + lane) : 0.;
+            // block (t + 1) / 32 was stored by the consumer while it flushed block (t + 1) / 32 - 2, i.e. before it published
+            // step t - 60; the producer is never more than NBUF steps ahead of the published count
+            if (slot == 31) yv = sm.ybuf[((t + 1) >> 5) & 1][lane];
             // buffer `buf` is free once the consumer has finished step t - NBUF (value read during the previous step)
             while (cons < (int)t - NBUF + 1) cons = ld_volatile_shared(&sm.consumed);
             const int cons_next = ld_volatile_shared(&sm.consumed);
@@ -155,6 +162,8 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         // ---- every 32 steps (and at the end): nll increments in SIMD, sequential accumulation, coalesced stores
         const int n = slot + 1;
         const int64_t t0 = t - slot;
+        // measurements of the block after the next one (the producer took this buffer's previous content 32 steps ago)
+        const double ynew = (slot == 31 && t + 33 + lane < T) ? __ldg(y + t + 33 + lane) : 0.;
         sm.nl[lane] = lane < n ? nll_increment(sm.ring[lane][D + NS], sm.ring[lane][D + NS + 1]) : 0.;
         __syncwarp();
         if (lane == 0) {
@@ -185,6 +194,7 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         for (int i = lane; i < (n - j0) * (WREC / 2); i += 32)
             dw[i] = *reinterpret_cast<const double2 *>(&sm.ring2[j0 + i / (WREC / 2)][2 * (i % (WREC / 2))]);
         if (lane < NS) sm.prevP[lane] = sm.ring[31][D + lane];
+        if (slot == 31) sm.ybuf[(t >> 5) & 1][lane] = ynew;
         __syncwarp();
     }
     if (store_nell && io.nell_last_only && lane == 0) io.nell[b] = carry;

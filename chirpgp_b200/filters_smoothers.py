@@ -36,6 +36,9 @@ _F64 = torch.float64
 
 # sgp_filter on CUDA tensors also produces the smoother gains (see `sgp_filter`); CHIRPGP_B200_FUSE_GAINS=0 turns it off
 FUSE_SMOOTHER_GAINS = os.environ.get('CHIRPGP_B200_FUSE_GAINS', '1') != '0'
+# sgp_filter_smoother reads PINNED host measurements in place over PCIe (zero-copy) where the filter kernel streams them
+# 32 samples per coalesced load, two blocks ahead (cgp_duo.cuh); CHIRPGP_B200_ZERO_COPY=0 makes it upload them first
+ZERO_COPY_YS = os.environ.get('CHIRPGP_B200_ZERO_COPY', '1') != '0'
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -278,12 +281,15 @@ class _SmootherGains:
 
 
 def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, store=True, last_only=False,
-                gains_for=None):
+                gains_for=None, ys_host=None):
+    """ys_host (internal, sgp_filter_smoother): a pinned float64 CPU tensor the kernel reads in place (zero-copy) instead of
+    `ys`; honoured only on the fused filter + gains path, whose producer warp streams the measurements in coalesced 256-byte
+    blocks two blocks ahead.  Results stay on the device (the caller is responsible for synchronising before `ys_host` dies)."""
     dev = _device()
     L = N.lib()
-    kind = _kind(ys)
+    kind = _kind(ys) if ys_host is None else ('torch', dev)
     model_id, d, nh = _model_fields(model)
-    ys_t = _dev(ys, dev)
+    ys_t = _dev(ys, dev) if ys_host is None else ys_host
     if ys_t.dim() == 0:
         raise ValueError('ys must have at least one axis (T,)')
     out_lead = tuple(ys_t.shape[:-1])
@@ -318,9 +324,13 @@ def _run_filter(name, model, consts, H, Xi, m0, P0, dt, ys, sgps=None, Qc=None, 
     nell = torch.empty((B,) if last_only else (B, T), dtype=_F64, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rec = None
+    fused = (gains_for is not None and store and kind[0] == 'torch' and kind[1] == dev and T > 1
+             and L.cgp_sgp_filter_gains_fused(C.byref(p)) == 1)
+    if ys_host is not None and not fused:                # no zero-copy kernel on this path: upload and run as usual
+        ys_t = _dev(ys_host, dev)
+        ys2 = ys_t.reshape(ys2.shape)
     # only where the filter kernel itself produces the gains: elsewhere the same gain kernel would merely run earlier
-    if (gains_for is not None and store and kind[0] == 'torch' and kind[1] == dev and T > 1
-            and L.cgp_sgp_filter_gains_fused(C.byref(p)) == 1):
+    if fused:
         nbytes = L.cgp_workspace_bytes(b'sgp_filter_gains', C.byref(p))
         try:
             ws = torch.empty((max(nbytes, 8) // 8,), dtype=_F64, device=dev)
@@ -449,7 +459,7 @@ def eks(cond_m_cov, mfs, Pfs, dt) -> Tuple:
     return _run_smoother('eks', model, _consts_on_device(model, dt, _device(), dt), mfs, Pfs, dt)
 
 
-def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, *, smoother_gains=None) -> Tuple:
+def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, *, smoother_gains=None, _ys_host=None) -> Tuple:
     """Sigma-point (Gauss--Hermite / cubature) filter (filters_smoothers.py:446-490).
 
     ``smoother_gains`` (extension; default: on for CUDA-tensor ``ys`` where a fused kernel exists -- chirp LCD model with
@@ -461,7 +471,7 @@ def sgp_filter(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, *, smoother_gains=None) 
     model = _disc_model(cond_m_cov, _state_dim(m0), dt)
     fuse = FUSE_SMOOTHER_GAINS if smoother_gains is None else bool(smoother_gains)
     return _run_filter('sgp_filter', model, _consts_on_device(model, dt, _device(), dt), H, Xi, m0, P0, dt, ys, sgps=sgps,
-                       gains_for='sgp_smoother' if fuse else None)
+                       gains_for='sgp_smoother' if fuse else None, ys_host=_ys_host)
 
 
 def sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt) -> Tuple:
@@ -497,14 +507,20 @@ def _frequency(mss: torch.Tensor, Pss: torch.Tensor, order: int = 10) -> torch.T
     return out
 
 
-def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order):
+def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order, zero_copy=False):
     """filter + smoother in one call on the device; only the requested results travel back to a host caller."""
     dev = _device()
     kind = _kind(ys)
-    f = run_filter(_dev(H, dev), _dev(m0, dev), _dev(P0, dev), _dev(ys, dev))
+    if (zero_copy and ZERO_COPY_YS and isinstance(ys, torch.Tensor) and not ys.is_cuda and ys.dtype == _F64
+            and ys.is_contiguous() and ys.is_pinned() and ys.data_ptr() % 32 == 0):
+        f = run_filter(_dev(H, dev), _dev(m0, dev), _dev(P0, dev), ys, True)
+    else:
+        f = run_filter(_dev(H, dev), _dev(m0, dev), _dev(P0, dev), _dev(ys, dev), False)
     sm = run_smoother(f[0], f[1])
     if readout is None:
-        return tuple(_back(t, kind) for t in f + sm)
+        out = tuple(_back(t, kind) for t in f + sm)
+        torch.cuda.current_stream(dev).synchronize()      # a zero-copy input must outlive the kernels that read it
+        return out
     names = (readout,) if isinstance(readout, str) else tuple(readout)
     d = int(sm[0].shape[-1])
     have = {'mfs': f[0], 'Pfs': f[1], 'n_ell': f[2], 'mss': sm[0], 'Pss': sm[1]}
@@ -523,6 +539,8 @@ def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order):
         else:
             raise ValueError('unknown readout %r (choose from %s)' % (nm, ', '.join(READOUTS)))
         out.append(_back(t, kind))
+    if kind[0] == 'numpy' or (kind[0] == 'torch' and kind[1].type == 'cpu'):
+        torch.cuda.current_stream(dev).synchronize()      # a zero-copy input must outlive the kernels that read it
     return tuple(out)
 
 
@@ -538,28 +556,32 @@ def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, readout=None, o
     ``order`` on the device (``gaussian_expectation``, quadratures.py:234-274), ``'v_mean'``, ``'v_var'``.  Asking for
     ``('freq', 'v_var')`` returns 16 bytes per step instead of 328."""
     dt = float(dt)
-    return _filter_smoother(lambda H_, m0_, P0_, ys_: sgp_filter(cond_m_cov, sgps, H_, Xi, m0_, P0_, dt, ys_),
-                            lambda mfs, Pfs: sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+    def run_filter(H_, m0_, P0_, ys_, host):
+        if host:                                       # pinned host measurements, read in place by the filter kernel
+            return sgp_filter(cond_m_cov, sgps, H_, Xi, m0_, P0_, dt, ys_, _ys_host=ys_)
+        return sgp_filter(cond_m_cov, sgps, H_, Xi, m0_, P0_, dt, ys_)
+    return _filter_smoother(run_filter, lambda mfs, Pfs: sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout,
+                            order, zero_copy=True)
 
 
 def ekf_smoother(cond_m_cov, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
     """``ekf`` + ``eks`` in one call (demos/ekfs_mle.py:68-76); ``readout`` as in ``sgp_filter_smoother``."""
     dt = float(dt)
-    return _filter_smoother(lambda H_, m0_, P0_, ys_: ekf(cond_m_cov, H_, Xi, m0_, P0_, dt, ys_),
+    return _filter_smoother(lambda H_, m0_, P0_, ys_, host: ekf(cond_m_cov, H_, Xi, m0_, P0_, dt, ys_),
                             lambda mfs, Pfs: eks(cond_m_cov, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
 
 
 def cd_ekf_smoother(a, b, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
     """``cd_ekf`` + ``cd_eks`` in one call (demos/cd_ekfs_mle.py); ``readout`` as in ``sgp_filter_smoother``."""
     dt = float(dt)
-    return _filter_smoother(lambda H_, m0_, P0_, ys_: cd_ekf(a, b, H_, Xi, m0_, P0_, dt, ys_),
+    return _filter_smoother(lambda H_, m0_, P0_, ys_, host: cd_ekf(a, b, H_, Xi, m0_, P0_, dt, ys_),
                             lambda mfs, Pfs: cd_eks(a, b, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
 
 
 def cd_sgp_filter_smoother(a, b, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
     """``cd_sgp_filter`` + ``cd_sgp_smoother`` in one call (demos/cd_ghfs_mle.py:61-75); ``readout`` as in ``sgp_filter_smoother``."""
     dt = float(dt)
-    return _filter_smoother(lambda H_, m0_, P0_, ys_: cd_sgp_filter(a, b, sgps, H_, Xi, m0_, P0_, dt, ys_),
+    return _filter_smoother(lambda H_, m0_, P0_, ys_, host: cd_sgp_filter(a, b, sgps, H_, Xi, m0_, P0_, dt, ys_),
                             lambda mfs, Pfs: cd_sgp_smoother(a, b, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
 
 

@@ -753,3 +753,21 @@ def test_filter_smoother_pairs_and_readout():
     g2 = cg.cd_sgp_filter_smoother(drift, disp(None), sg, H, Xi, m0, P0, dt, ys[:2], readout=('mss',))
     fg = cg.cd_sgp_filter(drift, disp(None), sg, H, Xi, m0, P0, dt, ys[:2])
     npt.assert_array_equal(g2[0], cg.cd_sgp_smoother(drift, disp(None), sg, fg[0], fg[1], dt)[0])
+
+
+def test_zero_copy_pinned_measurements():
+    """sgp_filter_smoother on a PINNED host tensor lets the filter kernel read the measurements in place (no upload); results
+    are bit-identical to the uploaded path, for ragged lengths around the 32-sample blocks the producer streams."""
+    from chirpgp_b200 import filters_smoothers as fs
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    for T in (1, 31, 32, 33, 64, 65, 700):
+        _, ys, _ = toymodels.synthetic_batch(7, max(T, 2), 1e-3, Xi=0.1, seed=13)
+        ys = np.ascontiguousarray(ys[:, :T])
+        pinned = torch.as_tensor(ys).pin_memory()
+        assert fs.ZERO_COPY_YS
+        a = cg.sgp_filter_smoother(mc, sg, H, 0.1, m0, P0, 1e-3, pinned)
+        b = cg.sgp_filter_smoother(mc, sg, H, 0.1, m0, P0, 1e-3, torch.as_tensor(ys).cuda())
+        for x, y in zip(a, b):
+            assert not x.is_cuda
+            npt.assert_array_equal(x.numpy(), y.cpu().numpy())
