@@ -771,3 +771,44 @@ def test_zero_copy_pinned_measurements():
         for x, y in zip(a, b):
             assert not x.is_cuda
             npt.assert_array_equal(x.numpy(), y.cpu().numpy())
+
+
+def test_misaligned_views_and_recycled_measurement_rows():
+    """Inputs that are views with a storage offset (x[1:5]: 8-byte aligned only) are cloned by the wrapper instead of
+    faulting in the kernels' vector loads; and the `H == e_j` hint is tied to the tensor OBJECT, not its address: a new H at
+    a recycled address with different contents must not inherit the old answer."""
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    _, ys, _ = toymodels.synthetic_batch(3, 64, 1e-3, Xi=0.1, seed=3)
+    big = torch.zeros(9, dtype=torch.float64, device='cuda')
+    big[1:5] = _cuda(m0)
+    m0_view = big[1:5]
+    assert m0_view.data_ptr() % 16 != 0
+    Pbig = torch.zeros(17, dtype=torch.float64, device='cuda')
+    Pbig[1:] = _cuda(P0).reshape(-1)
+    P0_view = Pbig[1:].reshape(4, 4)
+    f = cg.ekf(mc, _cuda(H), 0.1, m0_view, P0_view, 1e-3, _cuda(ys))
+    fo = orc.ekf(spec, H, 0.1, m0, P0, 1e-3, ys)
+    _check_filter([x.cpu().numpy() for x in f], fo, tag='ekf misaligned views')
+    # recycled address: H1 = e_1 is inspected and cached, freed, and H2 (general row) is very likely allocated at the same address
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    H1 = _cuda(np.array([0., 1., 0., 0.]))
+    cg.sgp_filter(mc, sg, H1, 0.1, _cuda(m0), _cuda(P0), 1e-3, _cuda(ys))
+    ptr = H1.data_ptr()
+    del H1
+    Hg = np.array([0.3, 1., 0., 0.1])
+    H2 = _cuda(Hg)
+    f2 = cg.sgp_filter(mc, sg, H2, 0.1, _cuda(m0), _cuda(P0), 1e-3, _cuda(ys))
+    fo2 = orc.sgp_filter(spec, sg, Hg, 0.1, m0, P0, 1e-3, ys)
+    _check_filter([x.cpu().numpy() for x in f2], fo2, tag='sgp_filter recycled H (same address: %s)' % (H2.data_ptr() == ptr))
+
+
+def test_filter_nll_kf():
+    """mle.filter_nll('kf', (F, Sigma), ...) == kf(...)[2][-1] (nll-only kernel mode)."""
+    from chirpgp_b200 import mle
+    rng = np.random.default_rng(2)
+    F = np.array([[0.9, 0.1], [0., 0.8]]); Sigma = np.diag([0.1, 0.2])
+    ys = rng.standard_normal((5, 40))
+    Hk, m0k, P0k = np.array([1., 0.]), np.zeros(2), np.eye(2)
+    want = cg.kf(F, Sigma, Hk, 0.5, m0k, P0k, ys)[2][:, -1]
+    got = mle.filter_nll('kf', (F, Sigma), Hk, 0.5, m0k, P0k, 0., ys)
+    npt.assert_allclose(np.asarray(got), want, rtol=1e-14)
