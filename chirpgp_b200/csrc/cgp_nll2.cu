@@ -421,9 +421,21 @@ bwd_kernel(const CgpProblem p, const double *__restrict__ ys, const double *__re
     // scratch slots: one per warp; the PAIR variant uses the two slots of its CTA's two warps alternately
     const int64_t worker = PAIR ? (int64_t)blockIdx.x * 2 : ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *__restrict__ slot0 = scratch + worker * slot_doubles + lane;
-    const int role = PAIR ? (int)(threadIdx.x >> 5) : 0;           // PAIR: 0 = recompute, 1 = reverse
     __shared__ unsigned long long pair_ticket;
+    __shared__ int pair_rec_warp;
+    int role = 0;                                                  // PAIR: 0 = recompute, 1 = reverse
     if constexpr (PAIR) {
+        // Hardware warp slot w runs on sub-partition w % 4 and the two warps of a CTA take adjacent slots: with warp 0 always
+        // the recompute warp, all recompute warps of an SM would sit on sub-partitions 0 and 2 and all (FP64-pipe hungry)
+        // reverse warps on 1 and 3 (measured: reverse warps alone 3.9 ms, twice their time when spread).  Alternate the
+        // roles between neighbouring CTAs so that every sub-partition gets one warp of each kind.
+        if (threadIdx.x == 0) {
+            unsigned wid;
+            asm("mov.u32 %0, %%warpid;" : "=r"(wid));
+            pair_rec_warp = (int)(((wid >> 2) ^ wid) & 1u);
+        }
+        __syncthreads();
+        role = ((int)(threadIdx.x >> 5) == pair_rec_warp) ? 0 : 1;
         if (role == 1) { pair_empty_arrive(0); pair_empty_arrive(1); }    // both slots start empty
     }
     double H[D];
