@@ -61,7 +61,7 @@ def ncu_traffic_bytes(kernel_substr: str):
 # algorithmic bytes / flops per chirp time-step (DESIGN.md "Roofline accounting")
 BYTES_FILTER = 8 + 8 * (D + D * D + 1)          # ys in, mf + Pf + nell out                      = 176
 BYTES_SMOOTHER = 2 * 8 * (D + D * D)            # mf, Pf in; ms, Ps out                          = 320
-BYTES_WORKSPACE = 8 * (2 * D * D + D)           # [G | mp | Pp] record the filter leaves for the sweep  = 288 (not algorithmic)
+BYTES_WORKSPACE = 8 * (D * D + D + D * (D + 1) // 2)   # [G | c | C packed] record the filter leaves for the sweep = 240 (not algorithmic)
 FLOPS_FILTER = 9403                             # sgp_filter, d=4, n=81, counting convention v1
 FLOPS_SMOOTHER = 13668                          # sgp_smoother
 

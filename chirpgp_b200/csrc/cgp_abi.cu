@@ -32,7 +32,7 @@ int check_smoother(const CgpProblem *p, const double *mfs, const double *Pfs, do
     return 0;
 }
 size_t disc_ws_bytes(const CgpProblem *p) {
-    return (size_t)p->B * (size_t)p->T * (size_t)(2 * p->d * p->d + p->d) * sizeof(double);
+    return (size_t)p->B * (size_t)p->T * (size_t)ws_record_doubles(p->d) * sizeof(double);
 }
 
 }  // namespace

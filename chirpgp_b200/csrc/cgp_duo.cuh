@@ -11,7 +11,7 @@
 //             cross-covariance partial sums are made of (GhPredictLCD::cross_partials);
 //   consumer  does everything that is not on the chain: the nll increments (32 at a time, in SIMD, accumulated in the
 //             reference's order), the coalesced 16-byte stores of mfs / Pfs / nell, and the smoother workspace
-//             [G | mp | Pp] that sgp_smoother's time-parallel half would otherwise recompute from (mf, Pf)
+//             [G | c | C] that sgp_smoother's time-parallel half would otherwise recompute from (mf, Pf)
 //             (filters_smoothers.py:520-527): the cross sums reduced over the lanes, then gain_record.
 //
 // Hand-over: NBUF buffers.  FULL: one named barrier per buffer (producer bar.arrive -- it never waits --, consumer bar.sync).
@@ -53,7 +53,7 @@ CGP_DEV void st_volatile_shared(int *q, int v) {
 struct DuoSmem4 {                       // D = 4 (chirp model)
     static constexpr int D = 4, V = 2, NS = 10, DD = 16, NA = 14, NE = 6, OTOT = 8, NBUF = 4;
     static constexpr int SROW = 18;     // consumer state ring row: m (4) | P packed (10) | S | r | pad 2  (9 x 16 bytes: odd)
-    static constexpr int WROW = 38;     // consumer gain ring row: E (6) | pad | tot (14) -> [G | mp | Pp] (36)   (19 x 16 bytes)
+    static constexpr int WROW = 38;     // consumer gain ring row: E (6) | pad | tot (14) -> [G | c | C] (30)   (19 x 16 bytes)
     // producer <-> consumer hand-over, NBUF deep
     double red[NA][33];                 // producer: transposition scratch of the moment sums
     double res[NBUF][16];               // moment totals of the step (producer reads them back, consumer keeps them)
@@ -64,7 +64,7 @@ struct DuoSmem4 {                       // D = 4 (chirp model)
     double ring[32][SROW];
     double ring2[32][WROW];
     double nl[32];
-    double prevP[NS + 2];               // filtering covariance of the last step of the previous 32-block
+    double prev[D + NS + 2];            // filtering mean and covariance of the last step of the previous 32-block
     double ybuf[2][32];                 // measurements of two 32-step blocks: written by the consumer, read by the producer
     int producer_warp;
     int consumed;                       // steps the consumer has finished reading (EMPTY side of the hand-over)
@@ -76,7 +76,7 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
     using Pred = GhPredictLCD<1, 3>;
     using S = DuoSmem4;
     constexpr int D = S::D, V = S::V, NS = S::NS, DD = S::DD, NA = S::NA, NE = S::NE, OTOT = S::OTOT, NBUF = S::NBUF;
-    constexpr int WREC = 2 * DD + D;
+    constexpr int WREC = ws_record<D>();
     static_assert(Pred::D == D && Pred::NA == NA && Pred::NE == NE && Pred::V == V, "layout");
     __shared__ __align__(16) S sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,7 +142,7 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
     mdl.load(p.consts + b * p.consts_stride, p.dt);
     const bool store_nell = io.nell != nullptr;
     double carry = 0.;                 // cumulative nll up to the last flushed step
-    if (lane < NS + 2) sm.prevP[lane] = 0.;
+    if (lane < D + NS + 2) sm.prev[lane] = 0.;
     for (int64_t t = 0; t < T; t++) {
         const int slot = (int)(t & 31), buf = (int)(t % NBUF);
         named_bar_sync(BAR_FULL + buf);
@@ -183,17 +183,16 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         }
         // lane j: record of iteration t0 + j = workspace record t0 + j - 1 (its prediction started from step t0 + j - 1)
         if (lane < n) {
-            double Pq[NS];
-            load_vec<NS>((lane == 0) ? &sm.prevP[0] : &sm.ring[lane - 1][D], Pq);
             const double f[4] = {mdl.f00, mdl.f01, mdl.f10, mdl.f11};
-            gain_record<1>(&sm.ring2[lane][0], &sm.ring2[lane][OTOT], Pq, f, &sm.ring2[lane][0]);
+            gain_record<1>(&sm.ring2[lane][0], &sm.ring2[lane][OTOT], (lane == 0) ? &sm.prev[0] : &sm.ring[lane - 1][0], f,
+                           &sm.ring2[lane][0]);
         }
         __syncwarp();
         const int j0 = (t0 == 0) ? 1 : 0;              // iteration 0 predicts from (m0, P0): no smoother record
         double2 *dw = reinterpret_cast<double2 *>(io.ws + (b * T + t0 - 1 + j0) * WREC);
         for (int i = lane; i < (n - j0) * (WREC / 2); i += 32)
             dw[i] = *reinterpret_cast<const double2 *>(&sm.ring2[j0 + i / (WREC / 2)][2 * (i % (WREC / 2))]);
-        if (lane < NS) sm.prevP[lane] = sm.ring[31][D + lane];
+        if (lane < D + NS) sm.prev[lane] = sm.ring[31][lane];
         if (slot == 31) sm.ybuf[(t >> 5) & 1][lane] = ynew;
         __syncwarp();
     }

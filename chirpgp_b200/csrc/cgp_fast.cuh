@@ -224,52 +224,58 @@ template <int NH, int P> struct GhRhsSDE {
     }
 };
 
-// Smoother workspace record [G | mp | Pp] of one step (filters_smoothers.py:520-527, :81-82) for ModelLCD<NH> from
+// Smoother workspace record [G | c | C] of one step (filters_smoothers.py:520-527, :81-84; layout: cgp_kernels.cuh) for
+// ModelLCD<NH> from
 //   Ein  (D-1) x V cross sums (GhPredictLCD::cross_partials),
 //   tot  D + NSym moment totals (sum_i w_i mu_i | sum_i w_i (mu_i mu_i^T + Sigma), packed lower),
-//   Pq   packed filtering covariance the prediction started from,
+//   mPq  [m (D) | P packed (NSym)]: the filtering mean and covariance the prediction started from,
 //   f    the Matern transition block [f00, f01, f10, f11] (models.py:61-73).
 // L = chol(Pq);  D[:, q] = L E[:, q] for the chirp columns,  D[:, V+t] = f_t0 P[:, V] + f_t1 P[:, V+1] for the linear ones;
-// mp = tot[0..D),  Pp = tot - mp mp^T;  G = D Pp^{-1} (row r of G solves Pp g = D_r^T).
-// `rec` may alias Ein / tot (everything is read before anything is written).
+// mp = tot[0..D),  Pp = tot - mp mp^T;  G = D Pp^{-1} (row r of G solves Pp g = D_r^T);  c = m - G mp;  C = P - G D^T.
+// `rec` may alias Ein / tot (they are read before anything is written); mPq must not overlap rec.
 template <int NH>
-CGP_DEV void gain_record(const double *Ein, const double *tot, const double (&Pq)[NSym<2 * NH + 2>::value], const double (&f)[4],
-                         double *rec) {
+CGP_DEV void gain_record(const double *Ein, const double *tot, const double *mPq, const double (&f)[4], double *rec) {
     constexpr int D = 2 * NH + 2, V = D - 2, NS = NSym<D>::value, DD = D * D, NE = (D - 1) * V;
-    double E[NE], mp[D], Pp[NS], L[NS];
-    chol_lower_sym_rsqrt<D>(Pq, L);
-    load_vec<NE>(Ein, E);
+    double Dx[D][D], mp[D], Lq[NS], rinv[D];
+    {
+        double E[NE], Pq[NS], L[NS];
+        load_vec<NS>(mPq + D, Pq);
+        chol_lower_sym_rsqrt<D>(Pq, L);
+        load_vec<NE>(Ein, E);
+        CGP_UNROLL for (int r = 0; r < D; r++) {
+            CGP_UNROLL for (int q = 0; q < V; q++) {             // chirp columns of row r of D = L E  (E[D-1][.] = 0)
+                double sacc = L[sidx(r, 0)] * E[q];
+                CGP_UNROLL for (int k = 1; k <= r && k < D - 1; k++) sacc = fma(L[sidx(r, k)], E[k * V + q], sacc);
+                Dx[r][q] = sacc;
+            }
+            Dx[r][V] = fma(f[1], Pq[sidx(r, V + 1)], f[0] * Pq[sidx(r, V)]);
+            Dx[r][V + 1] = fma(f[3], Pq[sidx(r, V + 1)], f[2] * Pq[sidx(r, V)]);
+        }
+    }
     load_vec<D>(tot, mp);
     {
-        double tp[NS];
+        double tp[NS], Pp[NS];
         load_vec<NS>(tot + D, tp);
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++)
             Pp[sidx(r, q)] = fma(-mp[r], mp[q], tp[sidx(r, q)]);              // as GhPredictLCD::predict_impl
-    }
-    double Lq[NS], rinv[D];
-    CGP_UNROLL for (int j = 0; j < D; j++) {                 // chol_lower_sym_rsqrt, keeping 1 / L_jj
-        double sacc = Pp[sidx(j, j)];
-        CGP_UNROLL for (int k = 0; k < j; k++) sacc = fma(-Lq[sidx(j, k)], Lq[sidx(j, k)], sacc);
-        const double r = fast_rsqrt(sacc);
-        rinv[j] = r;
-        Lq[sidx(j, j)] = sacc * r;
-        CGP_UNROLL for (int i = j + 1; i < D; i++) {
-            double tacc = Pp[sidx(i, j)];
-            CGP_UNROLL for (int k = 0; k < j; k++) tacc = fma(-Lq[sidx(i, k)], Lq[sidx(j, k)], tacc);
-            Lq[sidx(i, j)] = tacc * r;
+        CGP_UNROLL for (int j = 0; j < D; j++) {                 // chol_lower_sym_rsqrt, keeping 1 / L_jj
+            double sacc = Pp[sidx(j, j)];
+            CGP_UNROLL for (int k = 0; k < j; k++) sacc = fma(-Lq[sidx(j, k)], Lq[sidx(j, k)], sacc);
+            const double r = fast_rsqrt(sacc);
+            rinv[j] = r;
+            Lq[sidx(j, j)] = sacc * r;
+            CGP_UNROLL for (int i = j + 1; i < D; i++) {
+                double tacc = Pp[sidx(i, j)];
+                CGP_UNROLL for (int k = 0; k < j; k++) tacc = fma(-Lq[sidx(i, k)], Lq[sidx(j, k)], tacc);
+                Lq[sidx(i, j)] = tacc * r;
+            }
         }
     }
+    double cv[D];
     CGP_UNROLL for (int r = 0; r < D; r++) {
         double z[D];
-        CGP_UNROLL for (int q = 0; q < V; q++) {             // chirp columns of row r of D = L E  (E[D-1][.] = 0)
-            double sacc = L[sidx(r, 0)] * E[q];
-            CGP_UNROLL for (int k = 1; k <= r && k < D - 1; k++) sacc = fma(L[sidx(r, k)], E[k * V + q], sacc);
-            z[q] = sacc;
-        }
-        z[V] = fma(f[1], Pq[sidx(r, V + 1)], f[0] * Pq[sidx(r, V)]);
-        z[V + 1] = fma(f[3], Pq[sidx(r, V + 1)], f[2] * Pq[sidx(r, V)]);
         CGP_UNROLL for (int i = 0; i < D; i++) {
-            double sacc = z[i];
+            double sacc = Dx[r][i];
             CGP_UNROLL for (int k = 0; k < i; k++) sacc = fma(-Lq[sidx(i, k)], z[k], sacc);
             z[i] = sacc * rinv[i];
         }
@@ -279,9 +285,16 @@ CGP_DEV void gain_record(const double *Ein, const double *tot, const double (&Pq
             z[i] = sacc * rinv[i];
         }
         store_vec<D>(rec + r * D, z);
+        double sacc = mPq[r];
+        CGP_UNROLL for (int k = 0; k < D; k++) sacc = fma(-z[k], mp[k], sacc);
+        cv[r] = sacc;
+        CGP_UNROLL for (int q = 0; q <= r; q++) {                // C_rq = P_rq - (G D^T)_rq
+            double cacc = mPq[D + sidx(r, q)];
+            CGP_UNROLL for (int k = 0; k < D; k++) cacc = fma(-z[k], Dx[q][k], cacc);
+            rec[DD + D + sidx(r, q)] = cacc;
+        }
     }
-    store_vec<D>(rec + DD, mp);
-    store_sym<D>(rec + DD + D, Pp);
+    store_vec<D>(rec + DD, cv);
 }
 
 // sgp_filter (filters_smoothers.py:446-490, Pred = GhPredictLCD) / cd_sgp_filter (:534-582, Pred = GhRhsSDE + RK4) with a
@@ -463,14 +476,14 @@ __global__ void __launch_bounds__(32) cd_ghs_warp_kernel(const CgpProblem p, con
 // ------------------------------------------------------------------------------------------------ smoother sweep, warp per chirp
 // Sequential part of rts / eks / sgp_smoother (filters_smoothers.py:83-84):
 //     ms = mf + G (ms - mp),   Ps = Pf + G (Ps - Pp) G^T        for k = T-2 .. 0.
-// One warp owns one chirp.  Tiles of TS consecutive steps ([G | mp | Pp] records of the gain kernel plus mf, Pf)
-// are staged in shared memory with cp.async (double buffered), the recursion runs with ONE MATRIX ENTRY PER LANE
-// (operands exchanged through shared memory), and the TS results are written back with coalesced 16-byte stores.
+// One warp owns one chirp.  Tiles of TS consecutive [G | c | C] records (cgp_kernels.cuh) are staged in shared memory with
+// cp.async (double buffered), the recursion  ms = c + G ms',  Ps = C + G Ps' G^T  runs with ONE MATRIX ENTRY PER LANE
+// (operands exchanged through shared memory), and the TS results are written back with coalesced stores.
 template <int D> struct SweepCfg {
-    static constexpr int R = 2 * D * D + D;                   // workspace record
+    static constexpr int R = ws_record<D>();                  // workspace record
     static constexpr int TS = (D <= 4) ? 16 : 8;
     static constexpr int OUT = D + D * D;                     // ms | Ps per step
-    static constexpr int TILE_DOUBLES = TS * (R + D + D * D); // ws + mf + Pf
+    static constexpr int TILE_DOUBLES = TS * R;
     static constexpr int WARPS = 1;
     static constexpr size_t smem_bytes() {
         return sizeof(double) * (2 * TILE_DOUBLES + TS * OUT + 2 * D * D + 2 * D);
@@ -489,7 +502,7 @@ __global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProble
     using Cfg = SweepCfg<D>;
     constexpr int R = Cfg::R, TS = Cfg::TS, DD = D * D, OUT = Cfg::OUT, TILE = Cfg::TILE_DOUBLES;
     constexpr int EPL = (DD + 31) / 32;                    // matrix entries per lane
-    // shared-memory map (doubles): two input tiles, the output tile, X = Ps - Pp, T1 = G X, dm = ms - mp
+    // shared-memory map (doubles): two input tiles, the output tile, X = Ps', T1 = G X, the mean ms'
     constexpr int O_OUT = 2 * TILE, O_X = O_OUT + TS * OUT, O_T1 = O_X + DD, O_DM = O_T1 + DD;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x;
@@ -502,13 +515,15 @@ __global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProble
     double *__restrict__ Pss = io.Pss + b * T * DD;
 
     // entry e of the covariance handled by this lane (clamped duplicates keep every lane busy: no divergence)
-    int er[EPL], ec[EPL];
+    int er[EPL], ec[EPL], es[EPL];
     bool own[EPL];
     CGP_UNROLL for (int q = 0; q < EPL; q++) {
         const int e = lane + 32 * q;
         own[q] = e < DD;
         const int ee = own[q] ? e : e % DD;
         er[q] = ee / D; ec[q] = ee % D;
+        const int rr = er[q] > ec[q] ? er[q] : ec[q], cc = er[q] > ec[q] ? ec[q] : er[q];
+        es[q] = rr * (rr + 1) / 2 + cc;                    // position of (r, c) in the packed lower triangle C
     }
     const int mr = lane % D;                               // mean component handled by this lane
     // last step: copy the filter result (filters_smoothers.py:140-142)
@@ -525,10 +540,6 @@ __global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProble
         double *dst = smem + buf * TILE;
         const double *s0 = ws + lo * R;
         for (int i = lane; i < n * R / 2; i += 32) cp_async16(dst + 2 * i, s0 + 2 * i);
-        const double *s1 = mfs + lo * D;
-        for (int i = lane; i < n * D / 2; i += 32) cp_async16(dst + TS * R + 2 * i, s1 + 2 * i);
-        const double *s2 = Pfs + lo * DD;
-        for (int i = lane; i < n * DD / 2; i += 32) cp_async16(dst + TS * (R + D) + 2 * i, s2 + 2 * i);
         cp_async_commit();
     };
     int64_t hi = T - 1;                                    // steps [lo, hi) of the current tile, walking backwards
@@ -548,14 +559,14 @@ __global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProble
             cp_async_wait<0>();
         }
         __syncwarp();
-        const int o_ws = buf * TILE, o_mf = o_ws + TS * R, o_Pf = o_ws + TS * (R + D);
+        const int o_ws = buf * TILE;
         for (int j = n - 1; j >= 0; j--) {
-            const int oG = o_ws + j * R, omp = oG + DD, oPp = omp + D;
-            // X = Ps - Pp ; dm = ms - mp
-            CGP_UNROLL for (int q = 0; q < EPL; q++) smem[O_X + er[q] * D + ec[q]] = Pcur[q] - smem[oPp + er[q] * D + ec[q]];
-            smem[O_DM + mr] = mcur - smem[omp + mr];
+            const int oG = o_ws + j * R, oc = oG + DD, oC = oc + D;
+            // X = Ps' ; the mean ms'
+            CGP_UNROLL for (int q = 0; q < EPL; q++) smem[O_X + er[q] * D + ec[q]] = Pcur[q];
+            smem[O_DM + mr] = mcur;
             __syncwarp();
-            // T1 = G X ; ms = mf + G dm
+            // T1 = G X ; ms = c + G ms'
             CGP_UNROLL for (int q = 0; q < EPL; q++) {
                 double s = smem[oG + er[q] * D] * smem[O_X + ec[q]];
                 CGP_UNROLL for (int k = 1; k < D; k++) s = fma(smem[oG + er[q] * D + k], smem[O_X + k * D + ec[q]], s);
@@ -564,15 +575,15 @@ __global__ void __launch_bounds__(32) smoother_sweep_warp_kernel(const CgpProble
             {
                 double s = smem[oG + mr * D] * smem[O_DM];
                 CGP_UNROLL for (int k = 1; k < D; k++) s = fma(smem[oG + mr * D + k], smem[O_DM + k], s);
-                mcur = smem[o_mf + j * D + mr] + s;
+                mcur = smem[oc + mr] + s;
                 smem[O_OUT + j * OUT + mr] = mcur;
             }
             __syncwarp();
-            // Ps = Pf + T1 G^T
+            // Ps = C + T1 G^T
             CGP_UNROLL for (int q = 0; q < EPL; q++) {
                 double s = smem[O_T1 + er[q] * D] * smem[oG + ec[q] * D];
                 CGP_UNROLL for (int k = 1; k < D; k++) s = fma(smem[O_T1 + er[q] * D + k], smem[oG + ec[q] * D + k], s);
-                Pcur[q] = smem[o_Pf + j * DD + er[q] * D + ec[q]] + s;
+                Pcur[q] = smem[oC + es[q]] + s;
                 smem[O_OUT + j * OUT + D + er[q] * D + ec[q]] = Pcur[q];
             }
             __syncwarp();
@@ -800,11 +811,11 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
 // ------------------------------------------------------------------------------------------------ smoother sweep, d = 4, 16 lanes per chirp
 // Same recursion as smoother_sweep_warp_kernel, for d = 4: lane (i, j) of a half-warp holds Ps_ij, the two small matrix
 // products exchange their operands with shuffles (no shared-memory round trips on the dependency chain), and the 16
-// entries of a step are written with one coalesced 128-byte store.  Tiles of the gain records and of (mf, Pf) are
-// staged with cp.async, double buffered, per half-warp.
+// entries of a step are written with one coalesced 128-byte store.  Tiles of [G | c | C] records (30 doubles per step) are
+// staged with cp.async, NSTAGE deep, per half-warp.
 template <int TS_, int NSTAGE>
 __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProblem p, const SmootherIO io) {
-    constexpr int D = 4, DD = 16, R = 2 * DD + D, TS = TS_, TILE = TS * (R + D + DD);
+    constexpr int D = 4, DD = 16, R = ws_record<4>(), TS = TS_, TILE = TS * R;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x;
     const HalfWarp hw(lane);
@@ -819,6 +830,7 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProbl
     const double *__restrict__ Pfs = io.Pfs + b * T * DD;
     double *__restrict__ mss = io.mss + b * T * D;
     double *__restrict__ Pss = io.Pss + b * T * DD;
+    const int eC = DD + D + sidx(hw.i, hw.j);             // this lane's entry of the packed C within a record
     double Pe = Pfs[(T - 1) * DD + hw.l];
     double ms[D];
     CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mfs[(T - 1) * D + q];
@@ -831,10 +843,6 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProbl
         double *dst = my + buf * TILE;
         const double *s0 = ws + lo * R;
         for (int i = hw.l; i < n * R / 2; i += 16) cp_async16(dst + 2 * i, s0 + 2 * i);
-        const double *s1 = mfs + lo * D;
-        for (int i = hw.l; i < n * D / 2; i += 16) cp_async16(dst + TS * R + 2 * i, s1 + 2 * i);
-        const double *s2 = Pfs + lo * DD;
-        for (int i = hw.l; i < n * DD / 2; i += 16) cp_async16(dst + TS * (R + D) + 2 * i, s2 + 2 * i);
         cp_async_commit();
     };
     // NSTAGE-deep cp.async pipeline over tiles walking backwards from step T-2; empty commit groups keep the group
@@ -865,23 +873,22 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProbl
         ibuf = (ibuf + 1) % NSTAGE;
         cp_async_wait<NSTAGE - 1>();
         __syncwarp();
-        const double *tw = my + buf * TILE, *tm = tw + TS * R, *tP = tm + TS * D;
+        const double *tw = my + buf * TILE;
         double *pP = Pss + (lo + n - 1) * DD, *pm = mss + (lo + n - 1) * D;
         for (int jj = n - 1; jj >= 0; jj--) {
-            const double *Gm = tw + jj * R, *mp = Gm + DD, *Pp = mp + D;
-            // rows i and j of the gain (each lane needs both), this lane's Pp / Pf entries, mf, mp
+            const double *Gm = tw + jj * R, *cv = Gm + DD;
+            // rows i and j of the gain (each lane needs both)
             double gi[D], gj[D];
             CGP_UNROLL for (int k = 0; k < D; k++) { gi[k] = Gm[hw.i * D + k]; gj[k] = Gm[hw.j * D + k]; }
-            const double X = Pe - Pp[hw.l];                                        // (Ps - Pp)_ij
-            double t1 = gi[0] * hw.get(X, hw.j);                                   // (G X)_ij = sum_k G_ik X_kj
-            CGP_UNROLL for (int k = 1; k < D; k++) t1 = fma(gi[k], hw.get(X, 4 * k + hw.j), t1);
+            double t1 = gi[0] * hw.get(Pe, hw.j);                                  // (G Ps')_ij = sum_k G_ik Ps'_kj
+            CGP_UNROLL for (int k = 1; k < D; k++) t1 = fma(gi[k], hw.get(Pe, 4 * k + hw.j), t1);
             double t2 = hw.get(t1, 4 * hw.i) * gj[0];                              // (T1 G^T)_ij = sum_k T1_ik G_jk
             CGP_UNROLL for (int k = 1; k < D; k++) t2 = fma(hw.get(t1, 4 * hw.i + k), gj[k], t2);
-            Pe = tP[jj * DD + hw.l] + t2;
-            // ms = mf + G (ms - mp): lane (i, .) forms row i, the four rows are then gathered from lanes (k, 0)
-            double msi = gi[0] * (ms[0] - mp[0]);
-            CGP_UNROLL for (int k = 1; k < D; k++) msi = fma(gi[k], ms[k] - mp[k], msi);
-            msi = tm[jj * D + hw.i] + msi;
+            Pe = Gm[eC] + t2;
+            // ms = c + G ms': lane (i, .) forms row i, the four rows are then gathered from lanes (k, 0)
+            double msi = gi[0] * ms[0];
+            CGP_UNROLL for (int k = 1; k < D; k++) msi = fma(gi[k], ms[k], msi);
+            msi = cv[hw.i] + msi;
             CGP_UNROLL for (int k = 0; k < D; k++) ms[k] = hw.get(msi, 4 * k);
             if (active) {
                 pP[hw.l] = Pe;
@@ -899,10 +906,10 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProbl
 // ------------------------------------------------------------------------------------------------ smoother sweep, d = 8, one warp per chirp
 // Lane (i, jq) = (l / 4, l % 4) holds the two covariance entries (i, jq) and (i, jq + 4); the 8 x 8 products take their
 // operands by shuffle: (G X)_ij needs column j of X (lanes (k, j % 4), slot j / 4), (T1 G^T)_ij needs row i of T1 (the
-// four lanes of row i, both slots).  Gain rows come from the cp.async-staged tile in shared memory.
+// four lanes of row i, both slots).  Gain rows come from the cp.async-staged tile of [G | c | C] records in shared memory.
 template <int TS_, int NSTAGE>
 __global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProblem p, const SmootherIO io) {
-    constexpr int D = 8, DD = 64, R = 2 * DD + D, TS = TS_, TILE = TS * (R + D + DD);
+    constexpr int D = 8, DD = 64, R = ws_record<8>(), TS = TS_, TILE = TS * R;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x, li = lane >> 2, jq = lane & 3;
     const int64_t b = blockIdx.x;
@@ -913,6 +920,7 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProbl
     double *__restrict__ mss = io.mss + b * T * D;
     double *__restrict__ Pss = io.Pss + b * T * DD;
     const int ea = li * D + jq, eb = ea + 4;
+    const int ca = DD + D + sidx(li, jq), cb = DD + D + sidx(li, jq + 4);      // the two entries of the packed C within a record
     double Pa = Pfs[(T - 1) * DD + ea], Pb = Pfs[(T - 1) * DD + eb];
     double ms[D];
     CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mfs[(T - 1) * D + q];
@@ -924,10 +932,6 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProbl
         double *dst = smem + buf * TILE;
         const double *s0 = ws + lo * R;
         for (int i = lane; i < n * R / 2; i += 32) cp_async16(dst + 2 * i, s0 + 2 * i);
-        const double *s1 = mfs + lo * D;
-        for (int i = lane; i < n * D / 2; i += 32) cp_async16(dst + TS * R + 2 * i, s1 + 2 * i);
-        const double *s2 = Pfs + lo * DD;
-        for (int i = lane; i < n * DD / 2; i += 32) cp_async16(dst + TS * (R + D) + 2 * i, s2 + 2 * i);
         cp_async_commit();
     };
     int64_t hi = T - 1, next_hi = T - 1;
@@ -955,17 +959,16 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProbl
         ibuf = (ibuf + 1) % NSTAGE;
         cp_async_wait<NSTAGE - 1>();
         __syncwarp();
-        const double *tw = smem + buf * TILE, *tm = tw + TS * R, *tP = tm + TS * D;
+        const double *tw = smem + buf * TILE;
         double *pP = Pss + (lo + n - 1) * DD, *pm = mss + (lo + n - 1) * D;
         for (int jj = n - 1; jj >= 0; jj--) {
-            const double *Gm = tw + jj * R, *mp = Gm + DD, *Pp = mp + D;
+            const double *Gm = tw + jj * R, *cv = Gm + DD;
             double gi[D], ga[D], gb[D];
             CGP_UNROLL for (int k = 0; k < D; k++) { gi[k] = Gm[li * D + k]; ga[k] = Gm[jq * D + k]; gb[k] = Gm[(jq + 4) * D + k]; }
-            const double Xa = Pa - Pp[ea], Xb = Pb - Pp[eb];
-            double ta = gi[0] * __shfl_sync(0xffffffffu, Xa, jq), tb = gi[0] * __shfl_sync(0xffffffffu, Xb, jq);
+            double ta = gi[0] * __shfl_sync(0xffffffffu, Pa, jq), tb = gi[0] * __shfl_sync(0xffffffffu, Pb, jq);
             CGP_UNROLL for (int k = 1; k < D; k++) {
-                ta = fma(gi[k], __shfl_sync(0xffffffffu, Xa, 4 * k + jq), ta);
-                tb = fma(gi[k], __shfl_sync(0xffffffffu, Xb, 4 * k + jq), tb);
+                ta = fma(gi[k], __shfl_sync(0xffffffffu, Pa, 4 * k + jq), ta);
+                tb = fma(gi[k], __shfl_sync(0xffffffffu, Pb, 4 * k + jq), tb);
             }
             double ua = 0., ub = 0.;
             CGP_UNROLL for (int k = 0; k < 4; k++) {                  // T1_ik for k < 4 sits in slot a of lane (i, k)
@@ -978,11 +981,11 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane8_kernel(const CgpProbl
                 ua = fma(t1, ga[k + 4], ua);
                 ub = fma(t1, gb[k + 4], ub);
             }
-            Pa = tP[jj * DD + ea] + ua;
-            Pb = tP[jj * DD + eb] + ub;
-            double msi = gi[0] * (ms[0] - mp[0]);
-            CGP_UNROLL for (int k = 1; k < D; k++) msi = fma(gi[k], ms[k] - mp[k], msi);
-            msi = tm[jj * D + li] + msi;
+            Pa = Gm[ca] + ua;
+            Pb = Gm[cb] + ub;
+            double msi = gi[0] * ms[0];
+            CGP_UNROLL for (int k = 1; k < D; k++) msi = fma(gi[k], ms[k], msi);
+            msi = cv[li] + msi;
             CGP_UNROLL for (int k = 0; k < D; k++) ms[k] = __shfl_sync(0xffffffffu, msi, 4 * k);
             pP[ea] = Pa;
             pP[eb] = Pb;
@@ -1022,7 +1025,7 @@ __global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, c
     mdl.load(p.consts + b * p.consts_stride, p.dt);
     double m[D];
     load_vec<D>(io.mfs + (b * p.T + t) * D, m);
-    double *__restrict__ rec = io.ws + (b * p.T + t) * ws_record<D>();      // [G | mp | Pp]
+    double *__restrict__ rec = io.ws + (b * p.T + t) * ws_record<D>();      // [G | c | C]
     {
         double Pf[NS], L[NS];
         load_sym<D>(io.Pfs + (b * p.T + t) * (D * D), Pf);
@@ -1057,13 +1060,11 @@ __global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, c
         CGP_UNROLL for (int r = j; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
             Ds[r * D + c][tid] = fma(lj[r], evp[c], Ds[r * D + c][tid]);
     }
-    // mp, Pp of the record; chol(Pp) into the registers the accumulators leave behind
-    gstore_vec_auto<D>(rec + D * D, am);                  // whole 32-byte sectors where the record allows (cgp_device.cuh)
+    // chol(Pp) into the registers the accumulators leave behind
     double Lq[NS], rinv[D];
     {
         double Pps[NS];
         CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++) Pps[sidx(r, c)] = aP[sidx(r, c)] - am[r] * am[c];
-        gstore_sym_auto<D>(rec + D * D + D, Pps);
         CGP_UNROLL for (int j = 0; j < D; j++) {             // chol_lower_sym_rsqrt, keeping 1 / L_jj
             double sacc = Pps[sidx(j, j)];
             CGP_UNROLL for (int k = 0; k < j; k++) sacc = fma(-Lq[sidx(j, k)], Lq[sidx(j, k)], sacc);
@@ -1077,7 +1078,10 @@ __global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, c
             }
         }
     }
-    // G = D Pp^{-1}: row r of G solves Pp g = (row r of D)^T
+    // G = D Pp^{-1}: row r of G solves Pp g = (row r of D)^T;  c = m - G mp;  C = Pf - G D^T goes through the shared-memory
+    // columns chol(Pf) has left (Ls), so that it can leave in whole sectors
+    const double *__restrict__ Pfg = io.Pfs + (b * p.T + t) * (D * D);
+    double cv[D];
     CGP_UNROLL for (int r = 0; r < D; r++) {
         double z[D];
         CGP_UNROLL for (int c = 0; c < D; c++) z[c] = Ds[r * D + c][tid];
@@ -1092,6 +1096,21 @@ __global__ void __launch_bounds__(64) cubature_gain_kernel(const CgpProblem p, c
             z[i] = sacc * rinv[i];
         }
         gstore_vec_auto<D>(rec + r * D, z);
+        double sacc = m[r];
+        CGP_UNROLL for (int k = 0; k < D; k++) sacc = fma(-z[k], am[k], sacc);
+        cv[r] = sacc;
+        CGP_UNROLL for (int q = 0; q <= r; q++) {
+            double cacc = __ldg(Pfg + r * D + q);
+            CGP_UNROLL for (int k = 0; k < D; k++) cacc = fma(-z[k], Ds[q * D + k][tid], cacc);
+            Ls[sidx(r, q)][tid] = cacc;
+        }
+    }
+    gstore_vec_auto<D>(rec + D * D, cv);
+    {
+        constexpr int NSP = ws_record<D>() - D * D - D;      // packed C + padding
+        double Cs[NSP];
+        CGP_UNROLL for (int i = 0; i < NSP; i++) Cs[i] = i < NS ? Ls[i < NS ? i : 0][tid] : 0.;
+        gstore_vec_auto<NSP>(rec + D * D + D, Cs);
     }
 }
 

@@ -9,8 +9,15 @@
 //     butterfly __shfl_xor all-reduce (every lane gets the bit-identical sum, so replicas never diverge);
 //   * discrete smoothers (rts / eks / sgp_smoother) are split into a TIME-PARALLEL gain kernel (one thread per
 //     (chirp, step): smoother gain G_k, predicted mean/cov -- these depend on the filtering result only) and
-//     a sequential sweep kernel that only evaluates ms = mf + G (ms - mp), Ps = Pf + G (Ps - Pp) G^T.
-//     Same arithmetic per step as the reference's reverse scan (filters_smoothers.py:71-85), re-scheduled.
+//     a sequential sweep kernel.  The reference's step (filters_smoothers.py:83-84)
+//         ms = mf + G (ms' - mp),   Ps = Pf + G (Ps' - Pp) G^T
+//     is regrouped so that everything that does not depend on (ms', Ps') is formed in the time-parallel half:
+//         c = mf - G mp,   C = Pf - G Pp G^T = Pf - G D^T   (G Pp = D),      ms = c + G ms',   Ps = C + G Ps' G^T.
+//     The workspace record [G | c | C packed] is 30 doubles at d = 4 (it was [G | mp | Pp], 36) and the sweep no longer
+//     reads (mf, Pf): 400 instead of 608 bytes per step through the sweep.  C is the covariance of x_k given x_{k+1}
+//     (positive semi-definite), so Ps is a sum of two PSD terms; the regrouped recursion differs from the reference's
+//     order by ~1e-13 over T = 3141 (profiles/scripts/regroup_noise.py), three orders below the reference's own
+//     summation-order noise.
 #pragma once
 #include "cgp_device.cuh"
 
@@ -29,10 +36,12 @@ struct SmootherIO {
     const double *__restrict__ Pfs;
     double *__restrict__ mss;
     double *__restrict__ Pss;
-    double *__restrict__ ws;     // per (chirp, step): [G d*d | mp d | Pp d*d]
+    double *__restrict__ ws;     // per (chirp, step): [G d*d | c d | C packed lower d(d+1)/2 | pad to an even count]
 };
 
-template <int D> CGP_DEV constexpr int ws_record() { return 2 * D * D + D; }
+// doubles per smoother record (even, so that records stay 16-byte aligned): d = 4: 30, d = 6: 64, d = 8: 108
+__host__ __device__ constexpr int ws_record_doubles(int d) { return (d * d + d + d * (d + 1) / 2 + 1) & ~1; }
+template <int D> CGP_DEV constexpr int ws_record() { return ws_record_doubles(D); }
 
 // ================================================================================================ thread-per-chirp filters
 // kf (filters_smoothers.py:145-184) and ekf (:222-264): Model = ModelLinearDisc<D> | ModelLCD<NH>
@@ -490,10 +499,27 @@ __global__ void __launch_bounds__(GroupCfg<Model, G, CD>::kBlock) sgp_filter_ker
 }
 
 // ================================================================================================ discrete smoothers
-// Shared tail of the gain kernels: G = (cho_solve(chol(Pp), DT))^T (filters_smoothers.py:81-82), then the
-// workspace record [G | mp | Pp] of this (chirp, step) is written.
+// One lane writes R doubles (R even, dst 16-byte aligned) in whole 32-byte sectors wherever dst allows: a record that starts
+// in the middle of a sector goes out as 16 bytes + 256-bit stores + the rest (records of 30 doubles alternate between the two).
+template <int R> CGP_DEV void gstore_flat(double *__restrict__ dst, const double (&v)[R]) {
+    static_assert(R % 2 == 0, "even record");
+    auto st16 = [](double *q, double a, double b) { *reinterpret_cast<double2 *>(q) = make_double2(a, b); };
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+        CGP_UNROLL for (int i = 0; i + 4 <= R; i += 4) stg256(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if constexpr (R % 4 != 0) st16(dst + R - 2, v[R - 2], v[R - 1]);
+    } else {
+        st16(dst, v[0], v[1]);
+        CGP_UNROLL for (int i = 2; i + 4 <= R; i += 4) stg256(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if constexpr ((R - 2) % 4 != 0) st16(dst + R - 2, v[R - 2], v[R - 1]);
+    }
+}
+
+// Shared tail of the gain kernels: G = (cho_solve(chol(Pp), DT))^T (filters_smoothers.py:81-82), then the workspace
+// record [G | c | C] of this (chirp, step): c = mf - G mp, C = Pf - G D^T (lower triangle of Pf, as cho_factor would read).
 template <int D>
-CGP_DEV void gain_and_store(const double (&DT)[D][D], const double (&mp)[D], const double (&Pp)[D][D], double *__restrict__ rec) {
+CGP_DEV void gain_and_store(const double (&DT)[D][D], const double (&mp)[D], const double (&Pp)[D][D], const double (&mf)[D],
+                            const double (&Pfl)[NSym<D>::value], double *__restrict__ rec) {
+    constexpr int NS = NSym<D>::value, R = ws_record<D>();
     double L[D][D], rinv[D], Gm[D][D];
     chol_lower_rsqrt<D>(Pp, L, rinv);
     CGP_UNROLL for (int c = 0; c < D; c++) {          // column c of X = Pp^{-1} DT is row c of G^T ... G = X^T
@@ -502,14 +528,31 @@ CGP_DEV void gain_and_store(const double (&DT)[D][D], const double (&mp)[D], con
         chol_solve_vec_rinv<D>(L, rinv, col);
         CGP_UNROLL for (int i = 0; i < D; i++) Gm[c][i] = col[i];
     }
-    gstore_mat_auto<D>(rec, Gm);
-    if constexpr (D % 2 == 0) {
-        gstore_vec_auto<D>(rec + D * D, mp);
-        gstore_mat_auto<D>(rec + D * D + D, Pp);
-    } else {
-        CGP_UNROLL for (int i = 0; i < D; i++) rec[D * D + i] = mp[i];
-        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) rec[D * D + D + r * D + c] = Pp[r][c];
+    double cv[D], Cs[NS];
+    CGP_UNROLL for (int r = 0; r < D; r++) {
+        double sacc = mf[r];
+        CGP_UNROLL for (int k = 0; k < D; k++) sacc = fma(-Gm[r][k], mp[k], sacc);
+        cv[r] = sacc;
     }
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int q = 0; q <= r; q++) {
+        double sacc = Pfl[sidx(r, q)];
+        CGP_UNROLL for (int k = 0; k < D; k++) sacc = fma(-Gm[r][k], DT[k][q], sacc);      // (G D^T)_rq, D_qk = DT_kq
+        Cs[sidx(r, q)] = sacc;
+    }
+    if constexpr (D <= 6) {
+        if ((reinterpret_cast<uintptr_t>(rec) & 15u) == 0) {
+            double v[R];
+            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int k = 0; k < D; k++) v[r * D + k] = Gm[r][k];
+            CGP_UNROLL for (int r = 0; r < D; r++) v[D * D + r] = cv[r];
+            CGP_UNROLL for (int i = 0; i < NS; i++) v[D * D + D + i] = Cs[i];
+            CGP_UNROLL for (int i = D * D + D + NS; i < R; i++) v[i] = 0.;
+            gstore_flat<R>(rec, v);
+            return;
+        }
+    }
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int k = 0; k < D; k++) rec[r * D + k] = Gm[r][k];
+    CGP_UNROLL for (int r = 0; r < D; r++) rec[D * D + r] = cv[r];
+    CGP_UNROLL for (int i = 0; i < NS; i++) rec[D * D + D + i] = Cs[i];
 }
 
 // rts (filters_smoothers.py:187-219) / eks (:317-349) gains: one thread per (chirp, step k), k in [0, T-2].
@@ -531,7 +574,9 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const CgpProblem p, const
     mul_jt<Model, D>(DT, J, Pp);                      // :344
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++)
         if (Model::has_sig(r, c)) Pp[r][c] += mdl.sig(r, c);
-    gain_and_store<D>(DT, mp, Pp, io.ws + (b * p.T + t) * ws_record<D>());
+    double Pfl[NSym<D>::value];
+    CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c <= r; c++) Pfl[sidx(r, c)] = Pf[r][c];
+    gain_and_store<D>(DT, mp, Pp, mf, Pfl, io.ws + (b * p.T + t) * ws_record<D>());
 }
 
 // rts / eks in ONE pass, one thread per chirp, no workspace: for k = T-2 .. 0 the gain is formed from (mf_k, Pf_k)
@@ -611,15 +656,15 @@ __global__ void __launch_bounds__(128) sgp_gain_kernel(const CgpProblem p, const
     double DT[D][D], Pp[D][D];
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) DT[r][c] = Dx[c][r];
     sym_to_full<D>(Pps, Pp);
-    gain_and_store<D>(DT, mp, Pp, io.ws + (b * p.T + t) * ws_record<D>());
+    gain_and_store<D>(DT, mp, Pp, mf, Pf, io.ws + (b * p.T + t) * ws_record<D>());
 }
 
-// Sequential sweep (filters_smoothers.py:83-84, scan :218/:348/:530, stacking :140-142): one thread per chirp.
-//   ms = mf + G (ms - mp);   Ps = Pf + G (Ps - Pp) G^T
-// Records of the next step are fetched into registers while the current step is evaluated.
+// Sequential sweep (filters_smoothers.py:83-84 regrouped, scan :218/:348/:530, stacking :140-142): one thread per chirp.
+//   ms = c + G ms';   Ps = C + G Ps' G^T
+// The record of the next step is fetched into registers while the current step is evaluated.
 template <int D>
 __global__ void __launch_bounds__(64) smoother_sweep_kernel(const CgpProblem p, const SmootherIO io) {
-    constexpr int R = 2 * D * D + D;
+    constexpr int R = ws_record<D>(), NS = NSym<D>::value;
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;
     const int64_t T = p.T;
@@ -629,34 +674,28 @@ __global__ void __launch_bounds__(64) smoother_sweep_kernel(const CgpProblem p, 
     gstore_vec_auto<D>(io.mss + (b * T + T - 1) * D, ms);
     gstore_mat_auto<D>(io.Pss + (b * T + T - 1) * (D * D), Ps);
     if (T < 2) return;
-    double Gn[D][D], mpn[D], Ppn[D][D], mfn[D], Pfn[D][D];
+    double Gn[D][D], cn[D], Cn[NS];
     auto fetch = [&](int64_t t) {
         const double *rec = io.ws + (b * T + t) * R;
-        load_mat<D>(rec, Gn);
-        if constexpr (D % 2 == 0) { load_vec<D>(rec + D * D, mpn); load_mat<D>(rec + D * D + D, Ppn); }
-        else {
-            CGP_UNROLL for (int i = 0; i < D; i++) mpn[i] = rec[D * D + i];
-            CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ppn[r][c] = rec[D * D + D + r * D + c];
-        }
-        load_vec<D>(io.mfs + (b * T + t) * D, mfn);
-        load_mat<D>(io.Pfs + (b * T + t) * (D * D), Pfn);
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Gn[r][c] = rec[r * D + c];
+        CGP_UNROLL for (int i = 0; i < D; i++) cn[i] = rec[D * D + i];
+        CGP_UNROLL for (int i = 0; i < NS; i++) Cn[i] = rec[D * D + D + i];
     };
     fetch(T - 2);
     for (int64_t t = T - 2; t >= 0; t--) {
-        double Gm[D][D], mp[D], Pp[D][D], mf[D], Pf[D][D];
+        double Gm[D][D], cv[D], Cs[NS];
         CGP_UNROLL for (int r = 0; r < D; r++) {
-            mp[r] = mpn[r]; mf[r] = mfn[r];
-            CGP_UNROLL for (int c = 0; c < D; c++) { Gm[r][c] = Gn[r][c]; Pp[r][c] = Ppn[r][c]; Pf[r][c] = Pfn[r][c]; }
+            cv[r] = cn[r];
+            CGP_UNROLL for (int c = 0; c < D; c++) Gm[r][c] = Gn[r][c];
         }
+        CGP_UNROLL for (int i = 0; i < NS; i++) Cs[i] = Cn[i];
         if (t > 0) fetch(t - 1);
-        double dm[D], dP[D][D], t1[D][D], t2[D][D], gm[D];
-        CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = ms[r] - mp[r];
-        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) dP[r][c] = Ps[r][c] - Pp[r][c];
-        matvec<D>(Gm, dm, gm);
-        CGP_UNROLL for (int r = 0; r < D; r++) ms[r] = mf[r] + gm[r];
-        matmul<D>(Gm, dP, t1);
+        double t1[D][D], t2[D][D], gm[D];
+        matvec<D>(Gm, ms, gm);
+        CGP_UNROLL for (int r = 0; r < D; r++) ms[r] = cv[r] + gm[r];
+        matmul<D>(Gm, Ps, t1);
         matmul_nt<D>(t1, Gm, t2);
-        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ps[r][c] = Pf[r][c] + t2[r][c];
+        CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) Ps[r][c] = Cs[sidx(r, c)] + t2[r][c];
         gstore_vec_auto<D>(io.mss + (b * T + t) * D, ms);
         gstore_mat_auto<D>(io.Pss + (b * T + t) * (D * D), Ps);
     }

@@ -7,18 +7,18 @@ namespace cgp {
 // copies are legal (even d, 16-byte aligned buffers); otherwise the thread-per-chirp fallback.
 template <int D> static int launch_sweep(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
     if constexpr (D % 2 == 0) {
-        if (aligned16(io.ws) && aligned16(io.mfs) && aligned16(io.Pfs) && aligned16(io.mss) && aligned16(io.Pss)) {
+        if (aligned16(io.ws)) {
             if constexpr (D == 4) {
                 // tile of 16 steps, double buffered (measured at B = 1000 / 10 000 / 64 000: 0.66 / 4.01 / 24.5 ms; 8 steps x 4 stages:
                 // 0.71 / 4.11 / 25.4; 16 x 4 needs 57 KB per warp and loses occupancy at large B)
                 constexpr int TS = 16, NSTAGE = 2;
-                const size_t smem = sizeof(double) * 2 * NSTAGE * TS * (2 * 16 + 4 + 4 + 16);
+                const size_t smem = sizeof(double) * 2 * NSTAGE * TS * ws_record<4>();
                 smoother_sweep_lane4_kernel<TS, NSTAGE><<<(unsigned)ceil_div(p.B, 2), 32, smem, s>>>(p, io);
                 return check_launch();
             }
             if constexpr (D == 8) {
                 constexpr int TS = 4, NSTAGE = 4;
-                const size_t smem = sizeof(double) * NSTAGE * TS * (2 * 64 + 8 + 8 + 64);
+                const size_t smem = sizeof(double) * NSTAGE * TS * ws_record<8>();
                 smoother_sweep_lane8_kernel<TS, NSTAGE><<<(unsigned)p.B, 32, smem, s>>>(p, io);
                 return check_launch();
             }

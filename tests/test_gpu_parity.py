@@ -346,10 +346,20 @@ def test_fused_gains_ghf_ghs_vs_oracle(batch, T):
                                 C.c_size_t(nbytes), None)
     assert rc == 0
     torch.cuda.synchronize()
-    a = rec.ws.reshape(B, T, 36)[:, :T - 1].cpu().numpy()
-    b = ws.reshape(B, T, 36)[:, :T - 1].cpu().numpy()
-    _close(a[..., 16:], b[..., 16:], atol=atol_long('chirp_gh3', 'mf') if floor else AT, what='workspace mp, Pp')          # mp, Pp
-    _close(a[..., :16], b[..., :16], rtol=1e-7, atol=1e-9, what='workspace gain G')    # G = D Pp^{-1}: conditioning of Pp amplifies rounding
+    a = rec.ws.reshape(B, T, 30)[:, :T - 1].cpu().numpy()          # [G 16 | c 4 | C packed 10] per (chirp, step)
+    b = ws.reshape(B, T, 30)[:, :T - 1].cpu().numpy()
+    # G = D Pp^{-1}: the conditioning of Pp amplifies rounding; c = mf - G mp and C = Pf - G D^T inherit it
+    _close(a[..., :16], b[..., :16], rtol=1e-7, atol=1e-9, what='workspace gain G')
+    # (c cancels: |c| << |mf| ~ |G mp|, so the absolute error is the one of G times |mp|)
+    scale = float(np.abs(fo[0]).max())
+    _close(a[..., 16:20], b[..., 16:20], rtol=1e-7, atol=1e-8 * scale, what='workspace c = mf - G mp')
+    _close(a[..., 20:], b[..., 20:], rtol=1e-7, atol=1e-9, what='workspace C = Pf - G Pp G^T')
+    # C is the covariance of x_k given x_{k+1}: positive semi-definite
+    Cm = np.zeros((B, T - 1, 4, 4))
+    il = np.tril_indices(4)
+    Cm[..., il[0], il[1]] = a[..., 20:]
+    Cm = Cm + np.tril(Cm, -1).swapaxes(-1, -2)
+    assert np.linalg.eigvalsh(Cm).min() > -1e-12
 
 
 def test_fused_gains_are_dropped_when_inputs_change(batch):
@@ -635,7 +645,7 @@ def test_fused_kernel_is_deterministic_under_load():
                     noise = noise @ noise * 1e-4
         f = cg.sgp_filter(mc, sg, Hd, 0.1, m0d, P0d, dt, ys_d)
         s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
-        ws = f[0]._cgp_smoother_gains.ws.reshape(B, T, 36)[:, :T - 1]
+        ws = f[0]._cgp_smoother_gains.ws.reshape(B, T, 30)[:, :T - 1]
         cur = [x.clone() for x in f + s] + [ws.clone()]
         torch.cuda.synchronize()
         if ref is None:

@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
     p = _native.CgpProblem()
     lib.cgp_workspace_bytes.restype = ctypes.c_size_t
     p.B, p.T, p.d = 3, 5, 4
-    assert lib.cgp_workspace_bytes(b'eks', ctypes.byref(p)) == 3 * 5 * 36 * 8
+    assert lib.cgp_workspace_bytes(b'eks', ctypes.byref(p)) == 3 * 5 * 30 * 8          # [G 16 | c 4 | C 10] per (chirp, step)
 
 
 def test_struct_layout_matches_header():
