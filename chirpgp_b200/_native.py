@@ -12,6 +12,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 
 CGP_MODEL_LINEAR_DISC, CGP_MODEL_LCD, CGP_MODEL_LINEAR_SDE, CGP_MODEL_SDE, CGP_MODEL_KPT = 0, 1, 2, 3, 4
 CGP_SIGMA_GENERIC, CGP_SIGMA_GAUSS_HERMITE, CGP_SIGMA_CUBATURE = 0, 1, 2
+CGP_H_HARMONIC = -2            # CgpProblem.h_unit_index: H = [0 1 0 1 ... 0 0] (include/chirpgp_b200.h)
 ABI_VERSION = 3
 
 _ERRORS = {-1: 'CGP_ERR_BAD_ARG', -2: 'CGP_ERR_UNSUPPORTED (no kernel compiled for this model / state dimension)',

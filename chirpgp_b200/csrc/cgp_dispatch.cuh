@@ -1,6 +1,6 @@
 // cgp_dispatch.cuh -- runtime (model, d, group size) -> compiled kernel instance.
 #pragma once
-#include "cgp_duo.cuh"
+#include "cgp_cubduo.cuh"
 
 namespace cgp {
 

@@ -43,8 +43,30 @@ static int launch_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t 
 
 // The filter kernel that also fills the smoother workspace exists for the headline configuration (chirp LCD model,
 // Gauss-Hermite order 3, warp per chirp); everything else runs the filter and then the time-parallel gain kernel.
+// Harmonic chirp models (d = 6, 8) with the cubature rule: cub_duo_filter_kernel (cgp_cubduo.cuh), two chirps per CTA.
+static bool use_cub_duo(const CgpProblem &p) {
+    return p.model == CGP_MODEL_LCD && (p.num_harmonics == 2 || p.num_harmonics == 3) && p.d == 2 * p.num_harmonics + 2 &&
+           p.sigma_kind == CGP_SIGMA_CUBATURE && p.n_sigma == 2 * p.d && p.B < kThreadPerChirpMinB;
+}
 bool sgp_filter_fuses_gains(const CgpProblem &p) {
-    return p.model == CGP_MODEL_LCD && p.num_harmonics == 1 && p.d == 4 && use_share(p);
+    return (p.model == CGP_MODEL_LCD && p.num_harmonics == 1 && p.d == 4 && use_share(p)) || use_cub_duo(p);
+}
+
+template <int NH, bool H_HARM> static int launch_cub_duo_h(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = (int)sizeof(CubDuoSmem<NH>);
+    if (!configured) {
+        cudaFuncSetAttribute(cub_duo_filter_kernel<NH, H_HARM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(cub_duo_filter_kernel<NH, H_HARM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    cub_duo_filter_kernel<NH, H_HARM><<<(unsigned)ceil_div(p.B, 2), 64, smem, s>>>(p, io);
+    return check_launch();
+}
+template <int NH> static int launch_cub_duo(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    if (p.h_unit_index == CGP_H_HARMONIC) return launch_cub_duo_h<NH, true>(p, io, s);
+    return launch_cub_duo_h<NH, false>(p, io, s);
 }
 
 int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s) {
@@ -62,6 +84,11 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s
             if (p.B >= kThreadPerChirpMinB && io.ws == nullptr) {
                 if (share) return launch_sgp_one<Model, 1, 3>(p, io, s);
                 return launch_sgp_one<Model, 1, 0>(p, io, s);
+            }
+            if constexpr (Model::NH == 2 || Model::NH == 3) {
+                // the 16-byte stores of the consumer warp need aligned outputs; everything else takes the generic kernel
+                if (use_cub_duo(p) && (io.mfs == nullptr || (aligned16(io.mfs) && aligned16(io.Pfs))))
+                    return launch_cub_duo<Model::NH>(p, io, s);
             }
             if constexpr (Model::NH == 1) {
                 // headline path: chirp model, Gauss-Hermite order 3 -> 27 base indices, one per lane

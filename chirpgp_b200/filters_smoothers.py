@@ -99,7 +99,8 @@ _h_cache = {}
 
 
 def _h_unit_index(H) -> int:
-    """j if H is exactly the unit vector e_j, else -1 (a kernel specialisation hint: the H_E1 kernels never read H).
+    """j if H is exactly the unit vector e_j, CGP_H_HARMONIC if it is the measurement row of a harmonic chirp model, else -1
+    (a kernel specialisation hint: the H_E1 / H_HARM kernels never read H).
     Device tensors are inspected once per tensor OBJECT and version so that steady-state calls do not synchronise the
     stream.  The cache entry holds a weak reference to the tensor and is honoured only while that very object is alive and
     unmodified -- an address can be recycled by the caching allocator for a different H, an object identity cannot."""
@@ -114,6 +115,9 @@ def _h_unit_index(H) -> int:
         host = (H.detach().numpy() if isinstance(H, torch.Tensor) else np.asarray(H, dtype=np.float64)).reshape(-1)
     ones = np.flatnonzero(host)
     out = int(ones[0]) if ones.size == 1 and host[ones[0]] == 1. else -1
+    d = host.shape[0]
+    if out < 0 and d >= 6 and d % 2 == 0 and np.array_equal(host, np.array([0., 1.] * ((d - 2) // 2) + [0., 0.])):
+        out = N.CGP_H_HARMONIC             # measurement row of the harmonic chirp models (models.py:257)
     if key is not None:
         if len(_h_cache) > 64:
             _h_cache.clear()

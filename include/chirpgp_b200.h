@@ -52,6 +52,8 @@ enum {
     CGP_SIGMA_CUBATURE = 2       /* table is bit-identical to quadratures.py:139-150 (2d points +-sqrt(d) e_j)       */
 };
 
+#define CGP_H_HARMONIC (-2)    /* CgpProblem::h_unit_index: H = [0 1 0 1 ... 0 0], models.py:257 */
+
 enum {
     CGP_ERR_BAD_ARG = -1,      /* null pointer, B/T < 1, stride mismatch                       */
     CGP_ERR_UNSUPPORTED = -2,  /* (model, d, n_sigma) combination has no compiled kernel       */
@@ -72,7 +74,9 @@ typedef struct CgpProblem {
     int32_t sigma_kind;        /* CGP_SIGMA_*                                                  */
     int32_t gh_order;          /* nodes per dimension when sigma_kind == GAUSS_HERMITE         */
     int64_t ys_repeat;         /* >= 1                                                         */
-    int32_t h_unit_index;      /* hint: j if H is exactly the unit vector e_j, else -1 (results identical)  */
+    int32_t h_unit_index;      /* hint: j if H is exactly the unit vector e_j; CGP_H_HARMONIC if H = sum_k e_(2k+1),
+                                  k < num_harmonics (the measurement row of the harmonic chirp models); else -1.
+                                  Results are identical with and without the hint                            */
     int32_t reserved0;
     const double *consts;  int64_t consts_stride;   /* model constants, see model ids          */
     const double *m0;      int64_t m0_stride;       /* [B|1, d]                                */

@@ -3,6 +3,9 @@
 import csv, io, re, subprocess, sys
 
 WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__waves_per_multiprocessor', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'launch__occupancy_limit_warps', 'launch__occupancy_limit_barriers', 'launch__occupancy_limit_blocks',
+        'launch__shared_mem_per_block_dynamic', 'launch__shared_mem_per_block_static', 'launch__shared_mem_config_size',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',

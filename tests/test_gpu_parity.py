@@ -395,28 +395,19 @@ def test_fused_gains_are_dropped_when_inputs_change(batch):
     assert torch.equal(f3[0], f[0]) and torch.equal(f3[1], f[1]) and torch.equal(f3[2], f[2])
 
 
-def test_filter_gains_abi_unfused_models(golden):
-    """cgp_sgp_filter_gains_f64 for a configuration without a fused kernel (harmonic d = 8, cubature): filter, then the
-    time-parallel gain kernel, then cgp_smoother_sweep_f64 -- same result as cgp_sgp_smoother_f64.  The Python API does not
-    precompute gains there (nothing would be saved)."""
+def _gains_abi_roundtrip(mc, sg, m0, P0, H, Xi, dt, ys, nh):
+    """cgp_sgp_filter_gains_f64 + cgp_smoother_sweep_f64 through ctypes; returns (fused?, mfs, Pfs, mss, Pss)."""
     import ctypes as C
     from chirpgp_b200 import _native as N
     from chirpgp_b200 import filters_smoothers as fs
-    z = golden('harmonic')
-    drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(z['params'], num_harmonics=3)
-    dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
-    sg = cg.SigmaPoints.cubature(8)
-    f = cg.sgp_filter(mc, sg, H.cuda(), Xi, m0.cuda(), P0.cuda(), dt, _cuda(ys))
-    assert getattr(f[0], '_cgp_smoother_gains', None) is None
-    s_ref = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
     L = N.lib()
     dev = torch.device('cuda', 0)
-    T, d = ys.shape[0], 8
+    T, d = ys.shape[0], 2 * nh + 2
     consts = fs._consts_on_device(mc, dt, dev, dt)
     sig = fs._sigma_tables(sg, dev)
     m0d, P0d, Hd, ysd = m0.cuda(), P0.cuda(), H.cuda(), _cuda(ys)
-    p = fs._problem(1, T, N.CGP_MODEL_LCD, d, 3, consts, 0, m0d, 0, P0d, 0, Hd, None, 0, sig, Xi, dt, 1, fs._h_unit_index(H))
-    assert L.cgp_sgp_filter_gains_fused(C.byref(p)) == 0
+    p = fs._problem(1, T, N.CGP_MODEL_LCD, d, nh, consts, 0, m0d, 0, P0d, 0, Hd, None, 0, sig, Xi, dt, 1, fs._h_unit_index(H))
+    fused = L.cgp_sgp_filter_gains_fused(C.byref(p))
     nbytes = L.cgp_workspace_bytes(b'sgp_filter_gains', C.byref(p))
     ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
     mfs, Pfs, nell = torch.empty((T, d), dtype=torch.float64, device=dev), torch.empty((T, d, d), dtype=torch.float64, device=dev), \
@@ -429,10 +420,55 @@ def test_filter_gains_abi_unfused_models(golden):
                                   C.c_size_t(nbytes), None)
     assert rc == 0
     torch.cuda.synchronize()
+    return fused, mfs, Pfs, mss, Pss
+
+
+def test_filter_gains_abi_harmonic_fused(golden):
+    """Harmonic chirp model d = 8 with the cubature rule: the filter kernel (cgp_cubduo.cuh, two chirps per CTA, producer /
+    consumer warps) also leaves the smoother records.  Python path == C-ABI path bit for bit; the stand-alone smoother (gain
+    kernel + sweep on NumPy copies, no attached gains) agrees to rounding; everything matches the reference fixtures.  Also the
+    general-H instantiation (no CGP_H_HARMONIC hint) gives the same filtering result."""
+    z = golden('harmonic')
+    drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(z['params'], num_harmonics=3)
+    dt, Xi, ys = float(z['dt']), float(z['Xi']), z['ys']
+    sg = cg.SigmaPoints.cubature(8)
+    f = cg.sgp_filter(mc, sg, H.cuda(), Xi, m0.cuda(), P0.cuda(), dt, _cuda(ys))
+    assert getattr(f[0], '_cgp_smoother_gains', None) is not None, 'the d = 8 cubature filter did not produce smoother gains'
+    s = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    fused, mfs, Pfs, mss, Pss = _gains_abi_roundtrip(mc, sg, m0, P0, H, Xi, dt, ys, 3)
+    assert fused == 1
     assert torch.equal(mfs, f[0]) and torch.equal(Pfs, f[1])
-    assert torch.equal(mss, s_ref[0]) and torch.equal(Pss, s_ref[1])
+    assert torch.equal(mss, s[0]) and torch.equal(Pss, s[1])
+    s2 = cg.sgp_smoother(mc, sg, f[0].cpu().numpy(), f[1].cpu().numpy(), dt)
+    _close(s[0].cpu().numpy(), s2[0], rtol=1e-8, atol=AT_D8, what='fused vs stand-alone mss')
+    _close(s[1].cpu().numpy(), s2[1], rtol=1e-8, atol=AT_D8, what='fused vs stand-alone Pss')
     for j in range(3):
         _close(f[j].cpu().numpy(), z['sgp_filter_cub_%d' % j], rtol=NLL_RT if j == 2 else RT, atol=1e-9 if j == 2 else AT_D8)
+    for j in range(2):
+        _close(s[j].cpu().numpy(), z['sgp_smoother_cub_%d' % j], atol=AT_D8)
+    Hg = H.clone() * 1.0
+    Hg[0] = 1e-300                                      # not the harmonic pattern: general-H kernel, same numbers
+    fg = cg.sgp_filter(mc, sg, Hg.cuda(), Xi, m0.cuda(), P0.cuda(), dt, _cuda(ys))
+    for j in range(3):
+        _close(fg[j].cpu().numpy(), f[j].cpu().numpy(), rtol=1e-12, atol=1e-13, what='general-H vs harmonic-H kernel')
+
+
+def test_filter_gains_abi_unfused_models():
+    """cgp_sgp_filter_gains_f64 for a configuration without a fused kernel (4 harmonics, d = 10, cubature): filter, then the
+    time-parallel gain kernel, then cgp_smoother_sweep_f64 -- same result as cgp_sgp_smoother_f64.  The Python API does not
+    precompute gains there (nothing would be saved)."""
+    dt, Xi, T = 1e-3, 0.1, 300
+    _, ys, _ = toymodels.synthetic_batch(1, T, dt, Xi=Xi, num_harmonics=4, seed=11)
+    ys = ys[0]
+    drift, disp, mc, m0, P0, H = cg.build_harmonic_chirp_model(PARAMS, num_harmonics=4)
+    sg = cg.SigmaPoints.cubature(10)
+    f = cg.sgp_filter(mc, sg, H.cuda(), Xi, m0.cuda(), P0.cuda(), dt, _cuda(ys))
+    assert getattr(f[0], '_cgp_smoother_gains', None) is None
+    s_ref = cg.sgp_smoother(mc, sg, f[0], f[1], dt)
+    fused, mfs, Pfs, mss, Pss = _gains_abi_roundtrip(mc, sg, m0, P0, H, Xi, dt, ys, 4)
+    assert fused == 0
+    assert torch.equal(mfs, f[0]) and torch.equal(Pfs, f[1])
+    assert torch.equal(mss, s_ref[0]) and torch.equal(Pss, s_ref[1])
 
 
 # ---------------------------------------------------------------------------------------- post-processing on the device
