@@ -24,21 +24,6 @@
 
 namespace cgp {
 
-// bar.arrive / bar.sync on barrier `id` (0 .. 4) without a branch tree: the id must be an immediate (cgp_duo.cuh), so one
-// predicated instruction per candidate.
-CGP_DEV void named_bar_arrive5(int id) {
-    asm volatile("{\n .reg .pred q;\n"
-                 " setp.eq.s32 q, %0, 0;\n @q bar.arrive 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.arrive 1, 64;\n"
-                 " setp.eq.s32 q, %0, 2;\n @q bar.arrive 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.arrive 3, 64;\n"
-                 " setp.eq.s32 q, %0, 4;\n @q bar.arrive 4, 64;\n}" ::"r"(id) : "memory");
-}
-CGP_DEV void named_bar_sync5(int id) {
-    asm volatile("{\n .reg .pred q;\n"
-                 " setp.eq.s32 q, %0, 0;\n @q bar.sync 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.sync 1, 64;\n"
-                 " setp.eq.s32 q, %0, 2;\n @q bar.sync 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.sync 3, 64;\n"
-                 " setp.eq.s32 q, %0, 4;\n @q bar.sync 4, 64;\n}" ::"r"(id) : "memory");
-}
-
 template <int NH> struct CubDuoCfg {
     static constexpr int D = 2 * NH + 2, V = D - 2, NS = NSym<D>::value, NA = D + NS, DD = D * D;
     static constexpr int NBUF = 5, BLK = 8;              // the consumer's 8-step flush lasts ~3 producer steps

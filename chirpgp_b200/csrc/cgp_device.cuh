@@ -287,6 +287,22 @@ template <int D> CGP_DEV void chol_lower_sym_rsqrt(const double (&P)[NSym<D>::va
         }
     }
 }
+// the same without the last pivot: L[D-1][D-1] = piv * fast_rsqrt(piv) is left to the caller (bit-identical; lets the caller
+// place the last rsqrt where its latency is hidden)
+template <int D> CGP_DEV void chol_lower_sym_rsqrt_head(const double (&P)[NSym<D>::value], double (&L)[NSym<D>::value], double &piv) {
+    CGP_UNROLL for (int j = 0; j < D; j++) {
+        double s = P[sidx(j, j)];
+        CGP_UNROLL for (int k = 0; k < j; k++) s = fma(-L[sidx(j, k)], L[sidx(j, k)], s);
+        if (j == D - 1) { piv = s; L[sidx(j, j)] = 0.; break; }
+        const double r = fast_rsqrt(s);
+        L[sidx(j, j)] = s * r;
+        CGP_UNROLL for (int i = j + 1; i < D; i++) {
+            double t = P[sidx(i, j)];
+            CGP_UNROLL for (int k = 0; k < j; k++) t = fma(-L[sidx(i, k)], L[sidx(j, k)], t);
+            L[sidx(i, j)] = t * r;
+        }
+    }
+}
 // full-storage variant that also returns 1 / L_jj (for the triangular solves)
 template <int D> CGP_DEV void chol_lower_rsqrt(const double (&P)[D][D], double (&L)[D][D], double (&rinv)[D]) {
     CGP_UNROLL for (int j = 0; j < D; j++) {
@@ -497,8 +513,12 @@ template <int NH_> struct ModelLCD {
     }
     // trig depends on u[V] only (angles dt * k * w, w = 2 pi g(u_V) freq_scale; models.py:296-298, :370-372)
     template <bool WARP_UNIFORM = false> CGP_DEV Trig prep_v(double uv) const {
+        return prep_g(WARP_UNIFORM ? fast_softplus_warp(uv) : fast_softplus(uv));
+    }
+    // the same from gv = g(u_V) (callers that pick the softplus branch themselves)
+    CGP_DEV Trig prep_g(double gv) const {
         Trig t;
-        double w = (kTwoPi * (WARP_UNIFORM ? fast_softplus_warp(uv) : fast_softplus(uv))) * fs;
+        double w = (kTwoPi * gv) * fs;
         double s1, c1;
         fast_sincos(dt * w, &s1, &c1);
         double sk = s1, ck = c1;

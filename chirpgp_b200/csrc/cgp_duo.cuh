@@ -14,7 +14,8 @@
 //             [G | c | C] that sgp_smoother's time-parallel half would otherwise recompute from (mf, Pf)
 //             (filters_smoothers.py:520-527): the cross sums reduced over the lanes, then gain_record.
 //
-// Hand-over: NBUF buffers.  FULL: one named barrier per buffer (producer bar.arrive -- it never waits --, consumer bar.sync).
+// Hand-over: NBUF buffers.  FULL: one mbarrier per buffer (an elected producer lane arrives -- it never waits --, the consumer
+// spins on try_wait; a named barrier needs an immediate id, and dispatching on it cost ~45-60 cycles at the end of every step).
 // EMPTY: a bar.sync on the producer side would put the barrier's ~100-cycle latency on the chain at every step, so the
 // consumer publishes the number of steps it has finished in a shared-memory word instead; the producer reads it one step
 // ahead of the use (latency hidden) and only spins if the consumer has fallen NBUF steps behind, which does not happen
@@ -26,21 +27,47 @@
 namespace cgp {
 
 // Named barriers with IMMEDIATE ids (a register id makes ptxas reserve all 16 hardware barriers of the CTA, and barriers
-// are an SM resource: 16 per CTA would cap the SM at 4 CTAs).  64 = both warps of the CTA.
-#define CGP_BAR_CASE(op, k) case k: asm volatile(op " " #k ", 64;" ::: "memory"); break;
-CGP_DEV void named_bar_sync(int id) {
-    switch (id) {
-        CGP_BAR_CASE("bar.sync", 0) CGP_BAR_CASE("bar.sync", 1) CGP_BAR_CASE("bar.sync", 2) CGP_BAR_CASE("bar.sync", 3)
-        CGP_BAR_CASE("bar.sync", 4) CGP_BAR_CASE("bar.sync", 5) CGP_BAR_CASE("bar.sync", 6) CGP_BAR_CASE("bar.sync", 7)
-    }
+// are an SM resource: 16 per CTA would cap the SM at 4 CTAs).  64 = both warps of the CTA.  One predicated instruction per
+// candidate id instead of a branch tree: the producer's bar.arrive sits at the end of every step of the chain (a switch cost
+// ~45 cycles per step there: BSSY / BRA / WARPSYNC / BSYNC with their fixed stall counts).
+CGP_DEV void named_bar_arrive5(int id) {
+    asm volatile("{\n .reg .pred q;\n"
+                 " setp.eq.s32 q, %0, 0;\n @q bar.arrive 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.arrive 1, 64;\n"
+                 " setp.eq.s32 q, %0, 2;\n @q bar.arrive 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.arrive 3, 64;\n"
+                 " setp.eq.s32 q, %0, 4;\n @q bar.arrive 4, 64;\n}" ::"r"(id) : "memory");
 }
-CGP_DEV void named_bar_arrive(int id) {
-    switch (id) {
-        CGP_BAR_CASE("bar.arrive", 0) CGP_BAR_CASE("bar.arrive", 1) CGP_BAR_CASE("bar.arrive", 2) CGP_BAR_CASE("bar.arrive", 3)
-        CGP_BAR_CASE("bar.arrive", 4) CGP_BAR_CASE("bar.arrive", 5) CGP_BAR_CASE("bar.arrive", 6) CGP_BAR_CASE("bar.arrive", 7)
-    }
+CGP_DEV void named_bar_sync5(int id) {
+    asm volatile("{\n .reg .pred q;\n"
+                 " setp.eq.s32 q, %0, 0;\n @q bar.sync 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.sync 1, 64;\n"
+                 " setp.eq.s32 q, %0, 2;\n @q bar.sync 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.sync 3, 64;\n"
+                 " setp.eq.s32 q, %0, 4;\n @q bar.sync 4, 64;\n}" ::"r"(id) : "memory");
 }
-#undef CGP_BAR_CASE
+CGP_DEV void named_bar_arrive4(int id) {
+    asm volatile("{\n .reg .pred q;\n"
+                 " setp.eq.s32 q, %0, 0;\n @q bar.arrive 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.arrive 1, 64;\n"
+                 " setp.eq.s32 q, %0, 2;\n @q bar.arrive 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.arrive 3, 64;\n}" ::"r"(id) : "memory");
+}
+CGP_DEV void named_bar_sync4(int id) {
+    asm volatile("{\n .reg .pred q;\n"
+                 " setp.eq.s32 q, %0, 0;\n @q bar.sync 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.sync 1, 64;\n"
+                 " setp.eq.s32 q, %0, 2;\n @q bar.sync 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.sync 3, 64;\n}" ::"r"(id) : "memory");
+}
+// mbarrier (shared-memory barrier object, address in a register): the FULL side of the hand-over in gh_duo_filter_kernel.
+// One elected lane arrives (release), the consumer spins on try_wait (acquire); no convergence barrier, no id dispatch.
+CGP_DEV void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+CGP_DEV void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+CGP_DEV void mbar_wait(unsigned long long *bar, int parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
 CGP_DEV int ld_volatile_shared(const int *q) {
     int v;
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(q)) : "memory");
@@ -55,7 +82,7 @@ struct DuoSmem4 {                       // D = 4 (chirp model)
     static constexpr int SROW = 18;     // consumer state ring row: m (4) | P packed (10) | S | r | pad 2  (9 x 16 bytes: odd)
     static constexpr int WROW = 38;     // consumer gain ring row: E (6) | pad | tot (14) -> [G | c | C] (30)   (19 x 16 bytes)
     // producer <-> consumer hand-over, NBUF deep
-    double red[NA][33];                 // producer: transposition scratch of the moment sums
+    double red[RedRows<NA>::value][kRedPitch];  // producer: transposition scratch of the moment sums
     double res[NBUF][16];               // moment totals of the step (producer reads them back, consumer keeps them)
     double stp[NBUF][16];               // m | P packed | S | r   after the measurement update
     double xop[NBUF][V][33];            // per-lane cross-covariance operands ev[0..V-1]
@@ -66,6 +93,7 @@ struct DuoSmem4 {                       // D = 4 (chirp model)
     double nl[32];
     double prev[D + NS + 2];            // filtering mean and covariance of the last step of the previous 32-block
     double ybuf[2][32];                 // measurements of two 32-step blocks: written by the consumer, read by the producer
+    unsigned long long full[NBUF];      // mbarriers: buffer b holds step t (t % NBUF == b, phase parity (t / NBUF) & 1)
     int producer_warp;
     int consumed;                       // steps the consumer has finished reading (EMPTY side of the hand-over)
 };
@@ -90,15 +118,14 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         asm("mov.u32 %0, %%warpid;" : "=r"(wid));
         sm.producer_warp = (int)(((wid >> 2) ^ wid) & 1u);
         sm.consumed = 0;
+        CGP_UNROLL for (int i = 0; i < NBUF; i++) mbar_init(&sm.full[i], 1);
     }
     // Measurements: the CONSUMER fetches them, 32 per coalesced load, two blocks ahead of the producer, into a double buffer in
     // shared memory -- no global load (and no register for a block in flight) on the chain, and the load latency stays hidden
     // even when `ys` is pinned HOST memory read over PCIe (zero-copy input of host callers).  Blocks 0 and 1 before the loops:
     const double *__restrict__ y = io.ys + (b / p.ys_repeat) * T;
     sm.ybuf[warp][lane] = (32 * warp + lane < T) ? __ldg(y + 32 * warp + lane) : 0.;
-    constexpr int BAR_FULL = 0;                             // barriers 0 .. NBUF - 1
-    static_assert(NBUF <= 8, "named_bar_* cover ids 0..7");
-    named_bar_sync(BAR_FULL);                               // (first use of barrier 0; completes before the loops start)
+    __syncthreads();                                        // mbarriers initialised, measurement blocks 0 and 1 in place
     const bool producer = warp == sm.producer_warp;
 
     if (producer) {
@@ -111,26 +138,31 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
         CGP_UNROLL for (int i = 0; i < D; i++) H[i] = p.H[i];
         double yv = sm.ybuf[0][lane];                       // one block in a register, broadcast by shuffle
         int cons = 0;
-        for (int64_t t = 0; t < T; t++) {
-            const int slot = (int)(t & 31), buf = (int)(t % NBUF);
-            const double yt = __shfl_sync(0xffffffffu, yv, slot);
-            // block (t + 1) / 32 was stored by the consumer while it flushed block (t + 1) / 32 - 2, i.e. before it published
-            // step t - 60; the producer is never more than NBUF steps ahead of the published count
-            if (slot == 31) yv = sm.ybuf[((t + 1) >> 5) & 1][lane];
-            // buffer `buf` is free once the consumer has finished step t - NBUF (value read during the previous step)
-            while (cons < (int)t - NBUF + 1) cons = ld_volatile_shared(&sm.consumed);
-            const int cons_next = ld_volatile_shared(&sm.consumed);
-            double mp[D], Pp[NS];
-            pred.template predict_impl<true>(sm.red, &sm.res[buf][0], sm.xop[buf], lane, m, Pc, mp, Pp);
-            double Sv, resid;
-            linear_update_fast<D, H_E1>(mp, Pp, H, p.Xi, yt, m, Pc, Sv, resid);
-            if (lane == 0) {
-                store_vec<D>(&sm.stp[buf][0], m);
-                store_vec<NS>(&sm.stp[buf][D], Pc);
-                *reinterpret_cast<double2 *>(&sm.stp[buf][D + NS]) = make_double2(Sv, resid);
+        // blocks of 32 steps (= 8 rounds of the NBUF buffers): the inner loop is the chain and nothing else
+        for (int t0 = 0; t0 < (int)T; t0 += 32) {
+            const int n = ((int)T - t0 < 32) ? (int)T - t0 : 32;
+            for (int slot = 0; slot < n; slot++) {
+                const int t = t0 + slot, buf = slot % NBUF;
+                const double yt = __shfl_sync(0xffffffffu, yv, slot);
+                // buffer `buf` is free once the consumer has finished step t - NBUF (value read during the previous step)
+                while (cons < t - NBUF + 1) cons = ld_volatile_shared(&sm.consumed);
+                const int cons_next = ld_volatile_shared(&sm.consumed);
+                double mp[D], Pp[NS];
+                pred.template predict_impl<true>(sm.red, &sm.res[buf][0], sm.xop[buf], lane, m, Pc, mp, Pp);
+                double Sv, resid;
+                linear_update_fast<D, H_E1>(mp, Pp, H, p.Xi, yt, m, Pc, Sv, resid);
+                if (lane == 0) {
+                    store_vec<D>(&sm.stp[buf][0], m);
+                    store_vec<NS>(&sm.stp[buf][D], Pc);
+                    *reinterpret_cast<double2 *>(&sm.stp[buf][D + NS]) = make_double2(Sv, resid);
+                }
+                __syncwarp();                               // the lanes' xop / res / stp stores are ordered before the arrive
+                if (lane == 0) mbar_arrive(&sm.full[buf]);
+                cons = cons_next;
             }
-            named_bar_arrive(BAR_FULL + buf);
-            cons = cons_next;
+            // block t0 / 32 + 1 was stored by the consumer while it flushed block t0 / 32 - 1, i.e. before it published
+            // step t0 - 29; the producer is never more than NBUF steps ahead of the published count
+            yv = sm.ybuf[((t0 >> 5) + 1) & 1][lane];
         }
         return;
     }
@@ -145,7 +177,7 @@ __global__ void __maxnreg__(128) gh_duo_filter_kernel(const CgpProblem p, const 
     if (lane < D + NS + 2) sm.prev[lane] = 0.;
     for (int64_t t = 0; t < T; t++) {
         const int slot = (int)(t & 31), buf = (int)(t % NBUF);
-        named_bar_sync(BAR_FULL + buf);
+        mbar_wait(&sm.full[buf], (int)((t / NBUF) & 1));
         if (lane < 16) sm.ring[slot][lane] = sm.stp[buf][lane];
         {
             double ev[V], ec[NE];

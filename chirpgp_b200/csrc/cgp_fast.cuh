@@ -11,9 +11,14 @@ namespace cgp {
 
 // ------------------------------------------------------------------------------------------------ warp-per-chirp sigma-point filters
 // All 32 lanes' partial sums a[0..NA) are combined through shared memory in a fixed tree order; every lane gets
-// the same totals.  red: [NA][33] doubles, res: [NA rounded up to even] doubles (16-byte aligned).
+// the same totals.  red: [NA][kRedPitch] doubles (16-byte aligned rows: the partials are read back with 16-byte loads, and
+// pitch 34 keeps the 8 rows of a quarter-warp on different bank groups), res: [NA rounded up to even] doubles (16-byte aligned).
+constexpr int kRedPitch = 34;
+// rows of `red`: NA rounded up to the number of lanes that read (16 or 32) -- the lanes without a sum read a row of their own
+// (never written, never used) instead of row 0, which would put two different addresses on the bank group of lanes 0 / 8.
+template <int NA> struct RedRows { static constexpr int value = NA <= 16 ? 16 : ((NA + 31) / 32) * 32; };
 template <int NA>
-CGP_DEV void warp_sum_smem(const double (&a)[NA], double (*red)[33], double *res, int lane, double (&tot)[NA]) {
+CGP_DEV void warp_sum_smem(const double (&a)[NA], double (*red)[kRedPitch], double *res, int lane, double (&tot)[NA]) {
     constexpr int KP = (NA <= 16) ? 16 : 32;          // lanes per "half"
     constexpr int HS = 32 / KP;                       // halves: each sums 32 / HS partials
     constexpr int CNT = 32 / HS;
@@ -24,7 +29,10 @@ CGP_DEV void warp_sum_smem(const double (&a)[NA], double (*red)[33], double *res
         const int kk = k0 + k;
         const bool ok = kk < NA;
         double v[CNT];
-        CGP_UNROLL for (int j = 0; j < CNT; j++) v[j] = red[ok ? kk : 0][h * CNT + j];
+        CGP_UNROLL for (int j = 0; j < CNT; j += 2) {
+            const double2 x = *reinterpret_cast<const double2 *>(&red[kk][h * CNT + j]);
+            v[j] = x.x; v[j + 1] = x.y;
+        }
         CGP_UNROLL for (int w2 = 1; w2 < CNT; w2 <<= 1)
             CGP_UNROLL for (int j = 0; j + w2 < CNT; j += 2 * w2) v[j] += v[j + w2];
         double sacc = v[0];
@@ -112,22 +120,25 @@ template <int NH, int P, int DBG = 0> struct GhPredictLCD {
         CGP_UNROLL for (int c = 0; c < D - 1; c++)
             CGP_UNROLL for (int q = 0; q < V; q++) ec[c * V + q] = tab.xb[c] * (tab.Wl * ev[q]);
     }
-    CGP_DEV void predict(double (*red)[33], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&mp)[D],
+    CGP_DEV void predict(double (*red)[kRedPitch], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&mp)[D],
                          double (&Pp)[NS]) const {
         predict_impl<false>(red, res, nullptr, lane, m, Pc, mp, Pp);
     }
     // EXPORT: the cross sums are formed by another warp (cgp_duo.cuh); this lane leaves ev[0..V-1] at xop[0..V-1][lane].
     template <bool EXPORT>
-    CGP_DEV void predict_impl(double (*red)[33], double *res, double (*xop)[33], int lane, const double (&m)[D],
+    CGP_DEV void predict_impl(double (*red)[kRedPitch], double *res, double (*xop)[33], int lane, const double (&m)[D],
                               const double (&Pc)[NS], double (&mp)[D], double (&Pp)[NS]) const {
-        double L[NS];
-        if constexpr (DBG == 3) { CGP_UNROLL for (int i = 0; i < NS; i++) L[i] = Pc[i]; }
-        else chol_lower_sym_rsqrt<D>(Pc, L);
+        // The last pivot L[D-1][D-1] is needed by chi[D-1] only, i.e. after the transcendental chain that starts from chi[V]:
+        // its rsqrt is issued behind the softplus branch, into the latency shadows of sincos (same values, ~60 cycles off the chain).
+        double L[NS], piv;
+        if constexpr (DBG == 3) { CGP_UNROLL for (int i = 0; i < NS; i++) L[i] = Pc[i]; piv = 1.; }
+        else chol_lower_sym_rsqrt_head<D>(Pc, L, piv);
         double chi[D], slast;
         tab.points(m, L, chi, slast);
         typename Model::Trig trig;
         if constexpr (DBG == 2) { CGP_UNROLL for (int k = 0; k < NH; k++) { trig.c[k] = 0.99 + 1e-3 * chi[V]; trig.s[k] = 0.05; } }
         else trig = mdl.template prep_v<true>(chi[V]);
+        if constexpr (DBG != 3) L[sidx(D - 1, D - 1)] = piv * fast_rsqrt(piv);
         // weighted sums over this lane's P points: only chi[D-1] and the Matern rows ev[V], ev[V+1] differ between
         // them, so the sums factor through W = sum w_c, S_t = sum w_c ev[V+t]_c and three quadratic terms
         double a[NA];
@@ -183,13 +194,14 @@ template <int NH, int P> struct GhRhsSDE {
         tab.load(p, lane);
         load_sym<D>(p.Qc + b * p.Qc_stride, Qc);
     }
-    CGP_DEV void rhs(double (*red)[33], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&dm)[D],
+    CGP_DEV void rhs(double (*red)[kRedPitch], double *res, int lane, const double (&m)[D], const double (&Pc)[NS], double (&dm)[D],
                      double (&dP)[NS]) const {
-        double L[NS];
-        chol_lower_sym_rsqrt<D>(Pc, L);
+        double L[NS], piv;                              // last pivot deferred behind the softplus branch, as in GhPredictLCD
+        chol_lower_sym_rsqrt_head<D>(Pc, L, piv);
         double chi[D], slast;
         tab.points(m, L, chi, slast);
         const double w = (kTwoPi * fast_softplus_warp(chi[V])) * mdl.fs;
+        L[sidx(D - 1, D - 1)] = piv * fast_rsqrt(piv);
         double f[D];
         chi[D - 1] = 0.;
         mdl.drift_w(w, chi, f);                         // f[0..V-1] final; f[V], f[V+1] recomputed per point below
@@ -308,7 +320,7 @@ CGP_DEV void gain_record(const double *Ein, const double *tot, const double *mPq
 template <class Pred, bool CD, bool H_E1>
 __global__ void __launch_bounds__(32) gh_warp_filter_kernel(const CgpProblem p, const FilterIO io) {
     constexpr int D = Pred::D, NS = NSym<D>::value, NA = Pred::NA, DD = D * D, REC = D + DD;
-    __shared__ double red[NA][33];
+    __shared__ __align__(16) double red[RedRows<NA>::value][kRedPitch];
     __shared__ __align__(16) double res[(NA + 1) & ~1];
     __shared__ __align__(16) double ring[32][REC];
     __shared__ double nl[32];
@@ -328,51 +340,52 @@ __global__ void __launch_bounds__(32) gh_warp_filter_kernel(const CgpProblem p, 
     double carry = 0.;                 // cumulative nll up to the last flushed step
     double Sk = 1., rk = 0.;           // (S, r) of the step this lane is responsible for
     double yv = (lane < T) ? __ldg(y + lane) : 0.;      // 32 measurements per load, broadcast by shuffle
-    for (int64_t t = 0; t < T; t++) {
-        const int slot = (int)(t & 31);
-        const double yt = __shfl_sync(0xffffffffu, yv, slot);
-        if (slot == 31 && t + 1 < T) yv = (t + 1 + lane < T) ? __ldg(y + t + 1 + lane) : 0.;
-        double mp[D], Pp[NS];
-        if constexpr (CD) {
-            CGP_UNROLL for (int i = 0; i < D; i++) mp[i] = m[i];
-            CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = Pc[i];
-            rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
-                pred.rhs(red, res, lane, mm, PP, dm, dP);
-            }, mp, Pp, dt);
-        } else {
-            pred.predict(red, res, lane, m, Pc, mp, Pp);
-        }
-        // ---- measurement update (filters_smoothers.py:55-68)
-        double S, resid;
-        linear_update_fast<D, H_E1>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
-        if (lane == slot) { Sk = S; rk = resid; }
-        if (store_state && lane == 0) {
-            store_vec<D>(&ring[slot][0], m);
-            store_sym<D>(&ring[slot][D], Pc);
-        }
-        // ---- every 32 steps (and at the end): nll increments in SIMD, sequential accumulation, coalesced stores
-        if (slot == 31 || t == T - 1) {
-            const int n = slot + 1;
-            const int64_t t0 = t - slot;
-            nl[lane] = lane < n ? nll_increment(Sk, rk) : 0.;
-            __syncwarp();
-            if (lane == 0) {
-                double c = carry;
-                for (int j = 0; j < n; j++) { c = c + nl[j]; nl[j] = c; }     // reference order: n_ell = n_ell + inc
+    // Blocks of 32 steps: the inner loop is the chain and nothing else (32-bit counter, no end-of-block tests, the flush code
+    // out of its instruction stream); the next block's measurements are in flight while the block runs.
+    for (int64_t t0 = 0; t0 < T; t0 += 32) {
+        const int n = (T - t0 < 32) ? (int)(T - t0) : 32;
+        const double ynext = (t0 + 32 + lane < T) ? __ldg(y + t0 + 32 + lane) : 0.;
+        for (int slot = 0; slot < n; slot++) {
+            const double yt = __shfl_sync(0xffffffffu, yv, slot);
+            double mp[D], Pp[NS];
+            if constexpr (CD) {
+                CGP_UNROLL for (int i = 0; i < D; i++) mp[i] = m[i];
+                CGP_UNROLL for (int i = 0; i < NS; i++) Pp[i] = Pc[i];
+                rk4_step<D>([&](const double (&mm)[D], const double (&PP)[NS], double (&dm)[D], double (&dP)[NS]) {
+                    pred.rhs(red, res, lane, mm, PP, dm, dP);
+                }, mp, Pp, dt);
+            } else {
+                pred.predict(red, res, lane, m, Pc, mp, Pp);
             }
-            __syncwarp();
-            carry = nl[n - 1];
-            if (store_nell && !io.nell_last_only && lane < n) io.nell[b * T + t0 + lane] = nl[lane];
-            if (store_state) {
-                double2 *dm = reinterpret_cast<double2 *>(io.mfs + (b * T + t0) * D);
-                for (int i = lane; i < n * (D / 2); i += 32)
-                    dm[i] = *reinterpret_cast<const double2 *>(&ring[i / (D / 2)][2 * (i % (D / 2))]);
-                double2 *dP = reinterpret_cast<double2 *>(io.Pfs + (b * T + t0) * DD);
-                for (int i = lane; i < n * (DD / 2); i += 32)
-                    dP[i] = *reinterpret_cast<const double2 *>(&ring[i / (DD / 2)][D + 2 * (i % (DD / 2))]);
+            // ---- measurement update (filters_smoothers.py:55-68)
+            double S, resid;
+            linear_update_fast<D, H_E1>(mp, Pp, H, p.Xi, yt, m, Pc, S, resid);
+            if (lane == slot) { Sk = S; rk = resid; }
+            if (store_state && lane == 0) {
+                store_vec<D>(&ring[slot][0], m);
+                store_sym<D>(&ring[slot][D], Pc);
             }
-            __syncwarp();
         }
+        yv = ynext;
+        // ---- per block: nll increments in SIMD, sequential accumulation, coalesced stores
+        nl[lane] = lane < n ? nll_increment(Sk, rk) : 0.;
+        __syncwarp();
+        if (lane == 0) {
+            double c = carry;
+            for (int j = 0; j < n; j++) { c = c + nl[j]; nl[j] = c; }     // reference order: n_ell = n_ell + inc
+        }
+        __syncwarp();
+        carry = nl[n - 1];
+        if (store_nell && !io.nell_last_only && lane < n) io.nell[b * T + t0 + lane] = nl[lane];
+        if (store_state) {
+            double2 *dm = reinterpret_cast<double2 *>(io.mfs + (b * T + t0) * D);
+            for (int i = lane; i < n * (D / 2); i += 32)
+                dm[i] = *reinterpret_cast<const double2 *>(&ring[i / (D / 2)][2 * (i % (D / 2))]);
+            double2 *dP = reinterpret_cast<double2 *>(io.Pfs + (b * T + t0) * DD);
+            for (int i = lane; i < n * (DD / 2); i += 32)
+                dP[i] = *reinterpret_cast<const double2 *>(&ring[i / (DD / 2)][D + 2 * (i % (DD / 2))]);
+        }
+        __syncwarp();
     }
     if (store_nell && io.nell_last_only && lane == 0) io.nell[b] = carry;
 }
@@ -388,7 +401,7 @@ __global__ void __launch_bounds__(32) cd_ghs_warp_kernel(const CgpProblem p, con
     using Rhs = GhRhsSDE<NH, P>;
     constexpr int D = Rhs::D, NS = NSym<D>::value, NA = Rhs::NA, DD = D * D, REC = D + DD;
     constexpr int PROW = (((D + DD) / 2) % 2 == 1) ? D + DD : D + DD + 2;      // odd number of 16-byte units per row
-    __shared__ double red[NA][33];
+    __shared__ __align__(16) double red[RedRows<NA>::value][kRedPitch];
     __shared__ __align__(16) double res[(NA + 1) & ~1];
     __shared__ __align__(16) double ring[32][REC];
     __shared__ __align__(16) double pre[32][PROW];                             // per step of the block: mf | Gm

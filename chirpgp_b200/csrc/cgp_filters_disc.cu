@@ -103,6 +103,10 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s
                     // experiment (profiles/r2_multi_chirp.txt): NCH chirps interleaved per warp, nll-only
                     const char *mv = getenv("CGP_GH_MULTI");
                     const int nch = (mv && *mv) ? atoi(mv) : 0;
+                    if (nch == 16 && io.mfs == nullptr && io.nell && io.nell_last_only && p.h_unit_index == 1) {
+                        gh_half_nll_kernel<true><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io.ys, io.nell);
+                        return check_launch();
+                    }
                     if (nch >= 1 && nch <= 3 && io.mfs == nullptr && io.nell && io.nell_last_only && p.h_unit_index == 1) {
                         const unsigned grid = (unsigned)ceil_div(p.B, nch);
                         if (nch == 1) gh_warp_multi_nll_kernel<1, true><<<grid, 32, 0, s>>>(p, io.ys, io.nell);

@@ -60,6 +60,31 @@ CGP_MDEV double fast_exp(double x) {
     return (x != x) ? x : res;                                            // fmin/fmax drop NaN: put it back
 }
 
+// The same for -708 <= x <= 708 (finite, no overflow / underflow): no clamp, no NaN restore, one exact power-of-two scale.
+// Bit-identical to fast_exp on that range ((p 2^k1) 2^k2 = p 2^k exactly while everything stays normal).
+CGP_MDEV double fast_exp_inrange(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = 1. + r;
+    const double p23 = fma(r, 1.6666666666666666e-01, 0.5);
+    const double p45 = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    const double p67 = fma(r, 1.9841269841269841e-04, 1.3888888888888889e-03);
+    const double p89 = fma(r, 2.7557319223985893e-06, 2.4801587301587302e-05);
+    const double pab = fma(r, 2.5052108385441720e-08, 2.7557319223985888e-07);
+    const double pcd = fma(r, 1.6059043836821613e-10, 2.0876756987868100e-09);
+    const double q0 = fma(r2, p23, p01);
+    const double q1 = fma(r2, p67, p45);
+    const double q2 = fma(r2, pab, p89);
+    const double s0 = fma(r4, q1, q0);
+    const double s1 = fma(r4, pcd, q2);
+    const double p = fma(r8, s1, s0);
+    return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
 // ---- log(v) for normal positive v (fdlibm's e_log.c kernel with the division replaced by fast_rcp); +inf -> +inf,
 // NaN -> NaN.  Used for log(exp(x) + 1), where v >= 1.
 CGP_MDEV double fast_log_pos(double v) {
@@ -85,7 +110,7 @@ CGP_MDEV double fast_log_pos(double v) {
 
 // series branch of fast_softplus (valid for 3 <= x <= 700)
 CGP_MDEV double softplus_series(double x) {
-    const double u = fast_exp(-x);
+    const double u = fast_exp_inrange(-x);
     const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
     const double p0 = fma(u, -0.5, 1.);
     const double p1 = fma(u, -0.25, 3.3333333333333331e-01);
@@ -121,7 +146,7 @@ CGP_MDEV void fast_softplus_sigmoid(double x, double &g, double &sg) {
         sg = (ex < 1.7976931348623157e308) ? ex * fast_rcp(d) : 1.;     // e^x / (e^x + 1); inf / inf would be NaN
         return;
     }
-    const double u = fast_exp(-x);
+    const double u = fast_exp_inrange(-x);
     const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
     const double p0 = fma(u, -0.5, 1.);
     const double p1 = fma(u, -0.25, 3.3333333333333331e-01);

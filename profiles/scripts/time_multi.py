@@ -16,7 +16,7 @@ for B in [int(a) for a in sys.argv[1:]] or [1000]:
     _, ys, _ = toymodels.synthetic_batch(min(B, 1000), T, DT, Xi=XI, seed=2)
     ys = torch.as_tensor(np.tile(ys, (-(-B // ys.shape[0]), 1))[:B]).to(dev)
     ref = None
-    for nch in ('', '1', '2', '3'):
+    for nch in ('', '16'):
         os.environ['CGP_GH_MULTI'] = nch
         best = 1e9
         for it in range(4):
