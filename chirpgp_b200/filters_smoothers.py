@@ -265,14 +265,14 @@ def _problem(B, T, model, d, nh, consts, cs, m0, m0s, P0, P0s, H, Qc, Qs, sig, X
 
 
 class _SmootherGains:
-    """Smoother workspace ([G | mp | Pp] per (chirp, step)) that a filter call produced together with (mfs, Pfs).  Rides
+    """Smoother workspace ([G | c | C] per (chirp, step)) that a filter call produced together with (mfs, Pfs).  Rides
     on the returned ``mfs`` tensor; the smoother uses it only if it is called with exactly those tensor OBJECTS (identity,
     through weak references -- not addresses, which the allocator recycles), unmodified according to torch's version
     counters, and the same model constants / sigma points / dt -- otherwise it recomputes the gains.
 
     Limits: a write into ``mfs`` / ``Pfs`` that bypasses torch's version counter (a raw-pointer kernel, DLPack / cupy view)
     is invisible here -- callers who do that must pass ``smoother_gains=False`` to ``sgp_filter`` or drop the attribute
-    (``del mfs._cgp_smoother_gains``).  The record keeps (2 d^2 + d) doubles per step alive as long as ``mfs`` lives."""
+    (``del mfs._cgp_smoother_gains``).  The record keeps d^2 + d + d (d + 1) / 2 doubles per step alive as long as ``mfs`` lives."""
     __slots__ = ('ws', 'nbytes', 'mfs_ref', 'Pfs_ref', 'mfs_version', 'Pfs_version', 'consts', 'consts_version',
                  'sig', 'dt', 'shape', 'smoother')
 

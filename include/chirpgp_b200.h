@@ -125,8 +125,9 @@ int cgp_cd_sgp_smoother_f64(const CgpProblem *p, const double *mfs, const double
 /* ---- fused filter + smoother gains.  sgp_smoother's reverse scan (:520-528) recomputes, from (mf_k, Pf_k), the sigma-point
  * prediction that sgp_filter's step k+1 already made (:88-121, called from :483 and :523); only the last two lines of
  * _gaussian_smoother_common (:83-84) depend on the smoothed state.  cgp_sgp_filter_gains_f64 is cgp_sgp_filter_f64 that
- * additionally fills the smoother workspace ([G | mp | Pp] per (chirp, step), cgp_workspace_bytes("sgp_filter_gains")):
- * inside the filter kernel where one exists (cgp_sgp_filter_gains_fused() == 1: chirp LCD model, Gauss-Hermite order 3),
+ * additionally fills the smoother workspace ([G | c | C packed] per (chirp, step) with c = mf - G mp, C = Pf - G D: d^2 + d + d (d + 1) / 2 doubles,
+ * cgp_workspace_bytes("sgp_filter_gains")): inside the filter kernel where one exists (cgp_sgp_filter_gains_fused() == 1: chirp
+ * LCD model with Gauss-Hermite order 3; harmonic chirp models d = 6, 8 with the cubature rule),
  * otherwise by running the time-parallel gain kernel after the filter.  cgp_smoother_sweep_f64 then finishes any of
  * rts / eks / sgp_smoother from a filled workspace (:83-84 for k = T-2 .. 0, stacking :140-142); it reads B, T, d of the
  * problem only.  Filter + sweep give the results of cgp_sgp_filter_f64 + cgp_sgp_smoother_f64 up to rounding. */
