@@ -642,9 +642,10 @@ def run_ours(args):
             # at 1000 chirps per GPU neither throughput roofline is reachable: the kernel time is T x (cycles one producer
             # warp needs per step); floor = the pure dependency latency of one step
             'roofline_chain': {'bound': 'dependency-chain latency of one filter step', 'kernel': 'gh_duo_filter_kernel',
-                               'achieved_cycles_per_step': cyc, 'floor_cycles_per_step': 840, 'scheduled_cycles_per_step': 1394,
-                               'frac': 840. / cyc,
-                               'source': 'profiles/sass_dyn.py (static schedule), profiles/microbench/fp64_latency.cu'},
+                               'achieved_cycles_per_step': cyc, 'floor_cycles_per_step': 840,
+                               'alone_cycles_per_step': 1448, 'frac': 840. / cyc,
+                               'source': 'floor: dependent-issue latencies of profiles/microbench/fp64_latency.cu; alone: one '
+                                         'chain warp per SM sub-partition, profiles/r2_chain_timeline_plain592.txt'},
             'cpu_baseline': cpu,
             'jax': jax_note,
             'configs': other,
