@@ -1,6 +1,7 @@
 // cgp_dispatch.cuh -- runtime (model, d, group size) -> compiled kernel instance.
 #pragma once
 #include "cgp_cubduo.cuh"
+#include "cgp_oct.cuh"
 
 namespace cgp {
 

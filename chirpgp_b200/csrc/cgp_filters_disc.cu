@@ -44,6 +44,14 @@ static int launch_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t 
 // The filter kernel that also fills the smoother workspace exists for the headline configuration (chirp LCD model,
 // Gauss-Hermite order 3, warp per chirp); everything else runs the filter and then the time-parallel gain kernel.
 // Harmonic chirp models (d = 6, 8) with the cubature rule: cub_duo_filter_kernel (cgp_cubduo.cuh), two chirps per CTA.
+// 8-lanes-per-chirp Gauss-Hermite kernel (cgp_oct.cuh): batches from kOctMinB chirps; CGP_GH_OCT=0 / 1 forces it off / on
+// (tests, measurements).
+static const int64_t kOctMinB = 2000;     // measured (profiles/r2_oct_kernel.txt): pair +10 % at 2000 chirps, +34 % at 4000, +61 % at 32 000
+static bool use_oct(const CgpProblem &p) {
+    const char *v = getenv("CGP_GH_OCT");
+    if (v && *v) return atoi(v) != 0;
+    return p.B >= kOctMinB;
+}
 static bool use_cub_duo(const CgpProblem &p) {
     return p.model == CGP_MODEL_LCD && (p.num_harmonics == 2 || p.num_harmonics == 3) && p.d == 2 * p.num_harmonics + 2 &&
            p.sigma_kind == CGP_SIGMA_CUBATURE && p.n_sigma == 2 * p.d && p.B < kThreadPerChirpMinB;
@@ -81,7 +89,7 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s
         } else {
             // Very large batches are FP64-throughput-bound: one thread per chirp (all sigma points serially, no
             // replicated work, no shuffles) issues ~2.4x fewer FP64 warp-instructions per step than a warp per chirp.
-            if (p.B >= kThreadPerChirpMinB && io.ws == nullptr) {
+            if (p.B >= kThreadPerChirpMinB && io.ws == nullptr && !(Model::NH == 1 && share && use_oct(p))) {
                 if (share) return launch_sgp_one<Model, 1, 3>(p, io, s);
                 return launch_sgp_one<Model, 1, 0>(p, io, s);
             }
@@ -94,6 +102,18 @@ int launch_sgp_filter(const CgpProblem &p, const FilterIO &io_in, cudaStream_t s
                 // headline path: chirp model, Gauss-Hermite order 3 -> 27 base indices, one per lane
                 if (share) {
                     using Pred = GhPredictLCD<1, 3>;
+                    // large batches are bound by the FP64 pipe, not by one warp's dependency chain: 8 lanes per chirp (cgp_oct.cuh)
+                    if (use_oct(p)) {
+                        const unsigned grid = (unsigned)ceil_div(p.B, OctCfg::CH);
+                        if (io.ws != nullptr) {
+                            if (p.h_unit_index == 1) gh_oct_filter_kernel<true, true><<<grid, 32, 0, s>>>(p, io);
+                            else gh_oct_filter_kernel<false, true><<<grid, 32, 0, s>>>(p, io);
+                        } else {
+                            if (p.h_unit_index == 1) gh_oct_filter_kernel<true, false><<<grid, 32, 0, s>>>(p, io);
+                            else gh_oct_filter_kernel<false, false><<<grid, 32, 0, s>>>(p, io);
+                        }
+                        return check_launch();
+                    }
                     if (io.ws != nullptr) {
                         // filter + smoother gains: producer / consumer warp pair per chirp (cgp_duo.cuh)
                         if (p.h_unit_index == 1) gh_duo_filter_kernel<true><<<(unsigned)p.B, 64, 0, s>>>(p, io);

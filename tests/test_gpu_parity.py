@@ -310,12 +310,46 @@ def _cuda(x):
 
 
 @pytest.mark.parametrize('T', [3141, 33, 32, 31, 2])
-def test_fused_gains_ghf_ghs_vs_oracle(batch, T):
+def test_fused_gains_ghf_ghs_vs_oracle(batch, T, monkeypatch):
     """sgp_filter on CUDA tensors leaves the smoother gains on the returned mfs; sgp_smoother on those tensors runs the
     sweep only.  Same parity bar against the oracle as the two-kernel smoother, for block-aligned and ragged lengths
     (the filter flushes its gain records every 32 steps)."""
+    monkeypatch.setenv('CGP_GH_OCT', '0')               # the warp-pair kernel (cgp_duo.cuh), whatever the batch size
+    _fused_gains_vs_oracle(batch[3][:, :T], batch[2])
+
+
+@pytest.mark.parametrize('T', [3141, 33, 17, 16, 9, 8, 7, 2, 1])
+def test_large_batch_kernel_ghf_ghs_vs_oracle(batch, T, monkeypatch):
+    """The same checks on the large-batch kernel (cgp_oct.cuh: 8 lanes per chirp, 4 chirps per warp, records every 8 steps),
+    forced by CGP_GH_OCT=1 at a batch size the oracle finishes in seconds; 23 chirps: the last warp has an idle octet.  Also
+    the filter without gains, the nll-only mode and a general measurement row (the kernel's other three instantiations)."""
+    from chirpgp_b200 import mle
+    monkeypatch.setenv('CGP_GH_OCT', '1')
     B, _, dt, ys = batch
-    ys = ys[:, :T]
+    ys = ys[:23, :T]
+    fo = _fused_gains_vs_oracle(ys, dt) if T > 1 else None
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    floor = 'chirp_gh3' if T > 500 else None
+    if fo is None:
+        fo = orc.sgp_filter(spec, sg, H, 0.1, m0, P0, dt, ys)
+    fp = cg.sgp_filter(mc, sg, _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys), smoother_gains=False)
+    assert getattr(fp[0], '_cgp_smoother_gains', None) is None
+    _check_filter([x.cpu().numpy() for x in fp], fo, floor=floor, tag='sgp_filter')
+    v = mle.filter_nll('sgp_filter', (mc,), _cuda(H), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys), sgps=sg)
+    _close(v.cpu().numpy(), fo[2][:, -1], rtol=NLL_RT, atol=1e-9, what='nll-only mode')
+    Hg = np.array(H, dtype=np.float64) * 1.0
+    Hg[0] = 1e-300                                      # not a unit vector: general-H instantiations, same mathematics
+    fg = cg.sgp_filter(mc, sg, _cuda(Hg), 0.1, _cuda(m0), _cuda(P0), dt, _cuda(ys))
+    _check_filter([x.cpu().numpy() for x in fg], fo, floor=floor, tag='sgp_filter')
+    if T > 1:
+        sg_ = cg.sgp_smoother(mc, sg, fg[0], fg[1], dt)
+        so = orc.sgp_smoother(spec, sg, fo[0], fo[1], dt)
+        _check_smoother([x.cpu().numpy() for x in sg_], so, floor=floor, tag='sgp_smoother')
+
+
+def _fused_gains_vs_oracle(ys, dt):
+    B, T = ys.shape
     drift, disp, mc, m0, P0, H, spec = _chirp_setup()
     sg = cg.SigmaPoints.gauss_hermite(4, 3)
     floor = 'chirp_gh3' if T > 500 else None
@@ -360,6 +394,7 @@ def test_fused_gains_ghf_ghs_vs_oracle(batch, T):
     Cm[..., il[0], il[1]] = a[..., 20:]
     Cm = Cm + np.tril(Cm, -1).swapaxes(-1, -2)
     assert np.linalg.eigvalsh(Cm).min() > -1e-12
+    return fo
 
 
 def test_fused_gains_are_dropped_when_inputs_change(batch):
