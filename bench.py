@@ -317,6 +317,23 @@ def run_other_configs(dev, fp64_peak, hbm_peak, with_cpu, flush):
         orc.sgp_smoother(spec4, sg4, f[0], f[1], DT, nthreads=threads)
     out.append(entry(4, 'configs[3]: %d harmonic chirps (3 harmonics, d=8) x T=%d, sgp_filter + sgp_smoother, cubature(8)'
                      % (B_PER_GPU, T), B_PER_GPU, 8, 16, ('sgp_filter', 'sgp_smoother'), tf, ts, cpu_of(cpu4, 32)))
+    # ---- config 2 at the batch size north_star names for the CPU comparison: 10 000 chirps (large-batch kernel, cgp_oct.cuh)
+    del ysd, ys4d
+    torch.cuda.empty_cache()
+    B10 = 10000
+    y10 = torch.as_tensor(np.ascontiguousarray(tile(B10)[:B10])).to(dev)
+    tf, ts = timed(lambda: cg.sgp_filter(mc, sg, H, XI, m0, P0, DT, y10), lambda f: cg.sgp_smoother(mc, sg, f[0], f[1], DT))
+    e = entry('2 @ 10 000 chirps', 'configs[1] at 10 000 chirps x T=%d (north_star: "10k-chirp batch"), sgp_filter + sgp_smoother, '
+              'gauss_hermite(4, 3): gh_oct_filter_kernel (8 lanes per chirp, smoother records inline) + sweep' % T, B10, 4, 81,
+              ('sgp_filter', 'sgp_smoother'), tf, ts, None)
+    e['filter_fp64_frac'] = (B10 * T * flops_per_step('sgp_filter') / (tf * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None
+    # the pair's flop count includes the smoother's own sigma-point prediction, which the fused filter does not execute
+    e['fp64_tflops'] = e['fp64_frac'] = None
+    e['note'] = ('cpu_baseline: the headline cpu_baseline of this line (same workload per chirp); filter_fp64_frac counts the '
+                 'algorithmic flops of sgp_filter only against the filter kernel, as `roofline` does')
+    out.append(e)
+    del y10
+    torch.cuda.empty_cache()
     return out
 
 
@@ -599,6 +616,10 @@ def run_ours(args):
             v, sec, threads = cpu_sample(n)
             cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                    'sample': '%d chirps x %d steps, GHF+GHS, oracle/ C restatement with OpenMP (%.1f s)' % (n, T, sec)}
+        if cpu and other:
+            for e in other:
+                if isinstance(e.get('config'), str) and e['config'].startswith('2 @'):
+                    e['x_cpu_baseline'] = e['value'] / cpu['value']      # device-resident rate / the headline cpu_baseline
         cyc = ms_filter * 1e-3 * (clocks.get('sm_mhz') or 1965.) * 1e6 / T
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
