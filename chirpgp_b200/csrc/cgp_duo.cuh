@@ -28,8 +28,8 @@ namespace cgp {
 
 // Named barriers with IMMEDIATE ids (a register id makes ptxas reserve all 16 hardware barriers of the CTA, and barriers
 // are an SM resource: 16 per CTA would cap the SM at 4 CTAs).  64 = both warps of the CTA.  One predicated instruction per
-// candidate id instead of a branch tree: the producer's bar.arrive sits at the end of every step of the chain (a switch cost
-// ~45 cycles per step there: BSSY / BRA / WARPSYNC / BSYNC with their fixed stall counts).
+// candidate id instead of a branch tree.  Used by cgp_cubduo.cuh; gh_duo_filter_kernel hands over through mbarriers (below):
+// even predicated, the WARPSYNC + BAR.ARV pairs cost ~60 cycles at the end of every step of the chain.
 CGP_DEV void named_bar_arrive5(int id) {
     asm volatile("{\n .reg .pred q;\n"
                  " setp.eq.s32 q, %0, 0;\n @q bar.arrive 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.arrive 1, 64;\n"
@@ -41,16 +41,6 @@ CGP_DEV void named_bar_sync5(int id) {
                  " setp.eq.s32 q, %0, 0;\n @q bar.sync 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.sync 1, 64;\n"
                  " setp.eq.s32 q, %0, 2;\n @q bar.sync 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.sync 3, 64;\n"
                  " setp.eq.s32 q, %0, 4;\n @q bar.sync 4, 64;\n}" ::"r"(id) : "memory");
-}
-CGP_DEV void named_bar_arrive4(int id) {
-    asm volatile("{\n .reg .pred q;\n"
-                 " setp.eq.s32 q, %0, 0;\n @q bar.arrive 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.arrive 1, 64;\n"
-                 " setp.eq.s32 q, %0, 2;\n @q bar.arrive 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.arrive 3, 64;\n}" ::"r"(id) : "memory");
-}
-CGP_DEV void named_bar_sync4(int id) {
-    asm volatile("{\n .reg .pred q;\n"
-                 " setp.eq.s32 q, %0, 0;\n @q bar.sync 0, 64;\n setp.eq.s32 q, %0, 1;\n @q bar.sync 1, 64;\n"
-                 " setp.eq.s32 q, %0, 2;\n @q bar.sync 2, 64;\n setp.eq.s32 q, %0, 3;\n @q bar.sync 3, 64;\n}" ::"r"(id) : "memory");
 }
 // mbarrier (shared-memory barrier object, address in a register): the FULL side of the hand-over in gh_duo_filter_kernel.
 // One elected lane arrives (release), the consumer spins on try_wait (acquire); no convergence barrier, no id dispatch.
