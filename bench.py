@@ -36,6 +36,7 @@ METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
 WORKLOAD = ('configs[1]: 1000 toymodel chirps per GPU x T=3141, dt=1e-3, chirp model d=4, sgp_filter + sgp_smoother with '
             'gauss_hermite(d=4, order=3) (81 points)')
 UNIT = 'steps/s'
+E2E_DEPTH = int(os.environ.get('CGP_E2E_DEPTH', '3'))            # batches in flight in the end-to-end leg (cg.filter_smoother_batches); profiles/r2_batches.txt
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel: read from the committed ncu capture of
 # this very command (`ncu --set full`, raw page as CSV; see profiles/README.md), never a literal
@@ -526,8 +527,35 @@ def run_ours(args):
         wall = (time.perf_counter() - t0) * 1e3 / n
         return e0.elapsed_time(e1) / n, wall, out
 
-    ms_e2e, ms_e2e_wall, out_r = timed_calls(
+    ms_e2e_blk, ms_e2e_blk_wall, out_r = timed_calls(
         lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('freq', 'v_var')), n_e2e)
+    # the same work as a SEQUENCE of batches through cg.filter_smoother_batches (E2E_DEPTH batches in flight on alternating
+    # streams inside the product): what a Monte-Carlo job does (tetralith/jobs/ghfs_mle.py:26-86: one call per run).  Three
+    # distinct pinned input batches in rotation; every batch's measurements cross PCIe (read in place by its filter kernel) and
+    # its 16 B/step readout comes back into pinned host memory; the clock stops when the last result has landed.
+    hosts = [ys_host] + [torch.as_tensor(synthetic_inputs(rank + 1000 * k)).pin_memory() for k in (1, 2)]
+    n_seq = max(3 * args.steps, 30)
+
+    def batch_sequence(n):
+        last = None
+        for last in cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, XI, m0, P0, DT,
+                                               batches=(hosts[i % 3] for i in range(n)), readout=('freq', 'v_var'),
+                                               depth=E2E_DEPTH):
+            pass
+        return last
+    batch_sequence(12); batch_sequence(12)      # warm-up: the per-stream device pools and the pinned result blocks get allocated
+    barrier()
+    flush.fill_(1.)
+    torch.cuda.synchronize(dev)
+    e0, e1 = ev(), ev()
+    t0 = time.perf_counter()
+    e0.record()
+    batch_sequence(n_seq)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_seq
+    ms_e2e = e0.elapsed_time(e1) / n_seq
+    del hosts[1:]
     ms_e2e_full, ms_e2e_full_wall, _ = timed_calls(
         lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('mss', 'Pss')), n_e2e)
     ys_np = ys_host.numpy()
@@ -593,9 +621,9 @@ def run_ours(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np, ms_d2h], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np, ms_d2h, ms_e2e_blk], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np, ms_d2h = [float(x) for x in t.tolist()]
+        ms_step, ms_filter, ms_e2e, ms_pipe, ms_e2e_full, ms_e2e_np, ms_d2h, ms_e2e_blk = [float(x) for x in t.tolist()]
     n_steps_total = world * B_PER_GPU * T
     value = n_steps_total / (ms_step * 1e-3)
 
@@ -632,12 +660,20 @@ def run_ours(args):
             'value_two_streams': {'value': n_steps_total / (ms_pipe * 1e-3), 'unit': UNIT, 'ms_per_step': ms_pipe,
                                   'what': 'same passes, device-resident, issued on two alternating streams (no L2 flush)'},
             'e2e': {'value': n_steps_total / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
-                    'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_e2e,
-                    'ms_per_step_wall_clock': ms_e2e_wall, 'check_mean_frequency_hz': freq_mean,
-                    'what': "blocking product call per step: cg.sgp_filter_smoother(m_and_cov, sgps, H, Xi, m0, P0, dt, ys_host, "
-                            "readout=('freq', 'v_var')) -- pinned host ys in (read in place over PCIe by the filter kernel: h2d bytes "
-                            "cross the bus inside the kernel); posterior frequency estimate E[g(V_k)] (gaussian_expectation on the "
-                            "device) and marginal variance out, 16 B/step (demos/ghfs_mle.py:87-89)"},
+                    'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_seq,
+                    'ms_per_step_wall_clock': ms_e2e_wall, 'batches_in_flight': E2E_DEPTH,
+                    'what': "a sequence of batches through the product's streaming call: for freq, v_var in "
+                            "cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, Xi, m0, P0, dt, batches=<pinned "
+                            "host ys, 3 distinct batches in rotation>, readout=('freq', 'v_var'), depth=%d) -- every batch: pinned host "
+                            "ys in (read in place over PCIe by its filter kernel: the h2d bytes cross the bus inside the kernel), "
+                            "posterior frequency estimate E[g(V_k)] (gaussian_expectation on the device) and marginal variance out into "
+                            "pinned host memory, 16 B/step (demos/ghfs_mle.py:87-89); batch k+1's filter kernel overlaps batch k's sweep, "
+                            "readout and D2H; timed from the first call to the last result on the host" % E2E_DEPTH},
+            'e2e_blocking': {'value': n_steps_total / (ms_e2e_blk * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_blk,
+                             'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_e2e,
+                             'ms_per_step_wall_clock': ms_e2e_blk_wall, 'check_mean_frequency_hz': freq_mean,
+                             'what': "one blocking product call per step, nothing overlapped: cg.sgp_filter_smoother(m_and_cov, sgps, H, "
+                                     "Xi, m0, P0, dt, ys_host, readout=('freq', 'v_var'))"},
             'e2e_full_outputs': {'value': n_steps_total / (ms_e2e_full * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_full,
                                  'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D),
                                  'd2h_gb_per_s': B_PER_GPU * T * 8 * (D + D * D) / (ms_e2e_full * 1e-3) / 1e9,

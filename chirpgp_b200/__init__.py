@@ -4,7 +4,7 @@ frequency estimation, behind the reference's ``chirpgp`` Python interface (see D
 Re-exports follow /root/reference/chirpgp/__init__.py:1-6 (hot-path names only)."""
 from .filters_smoothers import (kf, rts, ekf, eks, cd_ekf, cd_eks, sgp_filter, sgp_smoother, cd_sgp_filter,  # noqa
                                 cd_sgp_smoother, ekf_for_kpt, sgp_filter_smoother, ekf_smoother, cd_ekf_smoother,
-                                cd_sgp_filter_smoother)
+                                cd_sgp_filter_smoother, filter_smoother_batches)
 from .models import (g, g_inv, model_chirp, model_harmonic_chirp, model_lascala, disc_chirp_lcd,  # noqa: F401
                      disc_harmonic_chirp_lcd, disc_model_lascala_lcd, disc_m32, build_chirp_model,
                      build_harmonic_chirp_model, build_lascala_model, build_kpt_chirp_model, posterior_cramer_rao,

@@ -30,7 +30,8 @@ from . import _native as N
 from .models import LCDModel, SDEDrift, Dispersion, LinearDisc, LinearSDE, KPTMeasurement, MODEL_KPT
 
 __all__ = ['kf', 'rts', 'ekf', 'ekf_for_kpt', 'eks', 'cd_ekf', 'cd_eks', 'sgp_filter', 'sgp_smoother', 'cd_sgp_filter',
-           'cd_sgp_smoother', 'sgp_filter_smoother', 'ekf_smoother', 'cd_ekf_smoother', 'cd_sgp_filter_smoother', 'READOUTS']
+           'cd_sgp_smoother', 'sgp_filter_smoother', 'ekf_smoother', 'cd_ekf_smoother', 'cd_sgp_filter_smoother',
+           'filter_smoother_batches', 'READOUTS']
 
 _F64 = torch.float64
 
@@ -71,7 +72,9 @@ def _kind(x):
 _PINNED_MIN_BYTES = 1 << 20
 
 
-def _back(t: torch.Tensor, kind):
+def _back(t: torch.Tensor, kind, sync: bool = True):
+    """Result tensor -> the kind of the caller's input.  ``sync=False`` (filter_smoother_batches): the device->host copy is
+    only queued on the current stream; the caller waits for an event recorded behind it before touching the array."""
     to_host = kind[0] == 'numpy' or (kind[0] == 'torch' and kind[1].type == 'cpu')
     if not to_host:
         return t.to(kind[1])
@@ -82,7 +85,8 @@ def _back(t: torch.Tensor, kind):
         try:
             host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             host.copy_(t, non_blocking=True)
-            torch.cuda.current_stream(t.device).synchronize()
+            if sync:
+                torch.cuda.current_stream(t.device).synchronize()
         except RuntimeError:
             host = None                  # no pinned memory left: pageable copy below
     if host is None:
@@ -511,8 +515,9 @@ def _frequency(mss: torch.Tensor, Pss: torch.Tensor, order: int = 10) -> torch.T
     return out
 
 
-def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order, zero_copy=False):
-    """filter + smoother in one call on the device; only the requested results travel back to a host caller."""
+def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order, zero_copy=False, sync=True):
+    """filter + smoother in one call on the device; only the requested results travel back to a host caller.
+    ``sync=False``: nothing waits for the stream (results and a zero-copy ``ys`` are the caller's to guard with an event)."""
     dev = _device()
     kind = _kind(ys)
     if (zero_copy and ZERO_COPY_YS and isinstance(ys, torch.Tensor) and not ys.is_cuda and ys.dtype == _F64
@@ -522,8 +527,9 @@ def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order, ze
         f = run_filter(_dev(H, dev), _dev(m0, dev), _dev(P0, dev), _dev(ys, dev), False)
     sm = run_smoother(f[0], f[1])
     if readout is None:
-        out = tuple(_back(t, kind) for t in f + sm)
-        torch.cuda.current_stream(dev).synchronize()      # a zero-copy input must outlive the kernels that read it
+        out = tuple(_back(t, kind, sync) for t in f + sm)
+        if sync:
+            torch.cuda.current_stream(dev).synchronize()      # a zero-copy input must outlive the kernels that read it
         return out
     names = (readout,) if isinstance(readout, str) else tuple(readout)
     d = int(sm[0].shape[-1])
@@ -542,13 +548,13 @@ def _filter_smoother(run_filter, run_smoother, H, m0, P0, ys, readout, order, ze
             t = sm[1][..., d - 2, d - 2].contiguous()
         else:
             raise ValueError('unknown readout %r (choose from %s)' % (nm, ', '.join(READOUTS)))
-        out.append(_back(t, kind))
-    if kind[0] == 'numpy' or (kind[0] == 'torch' and kind[1].type == 'cpu'):
+        out.append(_back(t, kind, sync))
+    if sync and (kind[0] == 'numpy' or (kind[0] == 'torch' and kind[1].type == 'cpu')):
         torch.cuda.current_stream(dev).synchronize()      # a zero-copy input must outlive the kernels that read it
     return tuple(out)
 
 
-def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10, *, _sync: bool = True) -> Tuple:
     """``sgp_filter`` followed by ``sgp_smoother`` in one call (extension; what every demo / job does back to back,
     demos/ghfs_mle.py:69-85).  ``readout=None`` returns ``(mfs, Pfs, n_ell, mss, Pss)`` of the kind of ``ys``.  For host
     (NumPy) callers this is the efficient form of the pair: the measurements are uploaded once, the filtering result never
@@ -565,28 +571,92 @@ def sgp_filter_smoother(cond_m_cov, sgps, H, Xi, m0, P0, dt, ys, readout=None, o
             return sgp_filter(cond_m_cov, sgps, H_, Xi, m0_, P0_, dt, ys_, _ys_host=ys_)
         return sgp_filter(cond_m_cov, sgps, H_, Xi, m0_, P0_, dt, ys_)
     return _filter_smoother(run_filter, lambda mfs, Pfs: sgp_smoother(cond_m_cov, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout,
-                            order, zero_copy=True)
+                            order, zero_copy=True, sync=_sync)
 
 
-def ekf_smoother(cond_m_cov, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+def ekf_smoother(cond_m_cov, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10, *, _sync: bool = True) -> Tuple:
     """``ekf`` + ``eks`` in one call (demos/ekfs_mle.py:68-76); ``readout`` as in ``sgp_filter_smoother``."""
     dt = float(dt)
     return _filter_smoother(lambda H_, m0_, P0_, ys_, host: ekf(cond_m_cov, H_, Xi, m0_, P0_, dt, ys_),
-                            lambda mfs, Pfs: eks(cond_m_cov, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+                            lambda mfs, Pfs: eks(cond_m_cov, mfs, Pfs, dt), H, m0, P0, ys, readout, order, sync=_sync)
 
 
-def cd_ekf_smoother(a, b, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+def cd_ekf_smoother(a, b, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10, *, _sync: bool = True) -> Tuple:
     """``cd_ekf`` + ``cd_eks`` in one call (demos/cd_ekfs_mle.py); ``readout`` as in ``sgp_filter_smoother``."""
     dt = float(dt)
     return _filter_smoother(lambda H_, m0_, P0_, ys_, host: cd_ekf(a, b, H_, Xi, m0_, P0_, dt, ys_),
-                            lambda mfs, Pfs: cd_eks(a, b, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+                            lambda mfs, Pfs: cd_eks(a, b, mfs, Pfs, dt), H, m0, P0, ys, readout, order, sync=_sync)
 
 
-def cd_sgp_filter_smoother(a, b, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10) -> Tuple:
+def cd_sgp_filter_smoother(a, b, sgps, H, Xi, m0, P0, dt, ys, readout=None, order: int = 10, *, _sync: bool = True) -> Tuple:
     """``cd_sgp_filter`` + ``cd_sgp_smoother`` in one call (demos/cd_ghfs_mle.py:61-75); ``readout`` as in ``sgp_filter_smoother``."""
     dt = float(dt)
     return _filter_smoother(lambda H_, m0_, P0_, ys_, host: cd_sgp_filter(a, b, sgps, H_, Xi, m0_, P0_, dt, ys_),
-                            lambda mfs, Pfs: cd_sgp_smoother(a, b, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout, order)
+                            lambda mfs, Pfs: cd_sgp_smoother(a, b, sgps, mfs, Pfs, dt), H, m0, P0, ys, readout, order, sync=_sync)
+
+
+_stream_cache = {}
+
+
+def _batch_streams(dev, depth):
+    """The side streams of filter_smoother_batches, kept per device: torch's caching allocator pools freed blocks per
+    stream, so fresh streams on every call would cudaMalloc (and synchronise the device for) every batch buffer again."""
+    have = _stream_cache.setdefault(str(dev), [])
+    while len(have) < depth:
+        have.append(torch.cuda.Stream(dev))
+    return have[:depth]
+
+
+def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int = 10, depth: int = 2):
+    """Run one of the filter + smoother pairs over a SEQUENCE of measurement batches with ``depth`` batches in flight
+    (extension).  The Monte-Carlo jobs of the reference call the pair once per run in a Python loop
+    (tetralith/jobs/ghfs_mle.py:26-86: ``for mc in range(num_mcs)``); issued one blocking call after the other, every
+    batch pays its host->device and device->host transfers and the tail of its latency-bound filter kernel serially.  Here
+    batch k + 1 is already queued on a second CUDA stream while batch k runs: its filter kernel fills the SM sub-partitions
+    that batch k's early-finishing chirps leave idle, and batch k's readout crosses PCIe underneath it.
+
+        for freq, v_var in cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, Xi, m0, P0, dt,
+                                                      batches=ys_batches, readout=('freq', 'v_var')):
+            ...
+
+    ``pair`` is ``sgp_filter_smoother``, ``ekf_smoother``, ``cd_ekf_smoother`` or ``cd_sgp_filter_smoother``; ``model_args`` are
+    that function's positional arguments without the trailing ``ys``; ``batches`` is any iterable of ``ys`` arrays (NumPy,
+    CPU tensors -- pinned ones are read in place by the filter kernel -- or CUDA tensors).  Yields, in order, exactly what
+    ``pair(*model_args, ys, readout=readout, order=order)`` returns for each batch; a yielded result is complete (its stream
+    has been waited for).  Host results live in pinned memory that torch's host allocator recycles once they are dropped.
+    Memory: ``depth`` batches' device buffers are alive at once (config 2: 1.8 GB each)."""
+    if pair not in (sgp_filter_smoother, ekf_smoother, cd_ekf_smoother, cd_sgp_filter_smoother):
+        raise TypeError('filter_smoother_batches: `pair` must be one of the *_smoother pair functions of chirpgp_b200')
+    depth = int(depth)
+    if depth < 1:
+        raise ValueError('depth must be >= 1')
+    from collections import deque
+    dev = _device()
+    streams = _batch_streams(dev, depth)
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))          # the model arguments may still be on their way to the device
+    for st in streams:
+        st.wait_event(ready)
+    inflight = deque()                                    # (results, event, ys kept alive: a zero-copy input of the kernels)
+    try:
+        for k, ys in enumerate(batches):
+            st = streams[k % depth]
+            with torch.cuda.stream(st):
+                out = pair(*model_args, ys, readout=readout, order=order, _sync=False)
+                done = torch.cuda.Event()
+                done.record(st)
+            inflight.append((out, done, ys))
+            if len(inflight) >= depth:
+                out0, done0, _ = inflight.popleft()
+                done0.synchronize()
+                yield out0
+        while inflight:
+            out0, done0, _ = inflight.popleft()
+            done0.synchronize()
+            yield out0
+    finally:
+        for _, done0, _ in inflight:                      # generator closed early: the queued kernels still read their inputs
+            done0.synchronize()
 
 
 def _qc(bm):

@@ -836,6 +836,51 @@ def test_filter_smoother_pairs_and_readout():
     npt.assert_array_equal(g2[0], cg.cd_sgp_smoother(drift, disp(None), sg, fg[0], fg[1], dt)[0])
 
 
+def test_filter_smoother_batches_match_blocking_calls():
+    """filter_smoother_batches (depth batches in flight on alternating streams) yields, in order, exactly what the blocking
+    pair call returns for each batch -- pinned (zero-copy), NumPy and CUDA inputs, readouts and full outputs, ragged last
+    batch, early close."""
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    dt, Xi = 1e-3, 0.1
+    batches = []
+    for k in range(5):
+        _, ys, _ = toymodels.synthetic_batch(6 if k < 4 else 3, 257, dt, Xi=Xi, seed=40 + k)
+        batches.append(np.ascontiguousarray(ys))
+    args = (mc, sg, H, Xi, m0, P0, dt)
+    want = [cg.sgp_filter_smoother(*args, ys, readout=('freq', 'v_var', 'n_ell_last')) for ys in batches]
+    for depth in (1, 2, 3):
+        for conv in (lambda a: a, lambda a: torch.as_tensor(a).pin_memory(), lambda a: torch.as_tensor(a).cuda()):
+            got = list(cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=(conv(b) for b in batches),
+                                                  readout=('freq', 'v_var', 'n_ell_last'), depth=depth))
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert len(g) == 3
+                for a, b in zip(g, w):
+                    a = a.cpu().numpy() if isinstance(a, torch.Tensor) else a
+                    npt.assert_array_equal(a, b)
+    # full outputs, and the siblings
+    full = list(cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=batches[:3]))
+    for g, ys in zip(full, batches):
+        w = cg.sgp_filter_smoother(*args, ys)
+        assert len(g) == 5 and isinstance(g[0], np.ndarray)
+        for a, b in zip(g, w):
+            npt.assert_array_equal(a, b)
+    for pair, pargs in ((cg.ekf_smoother, (mc, H, Xi, m0, P0, dt)), (cg.cd_ekf_smoother, (drift, disp, H, Xi, m0, P0, dt))):
+        got = list(cg.filter_smoother_batches(pair, *pargs, batches=batches[:3], readout=('mss', 'v_var'), depth=2))
+        for g, ys in zip(got, batches):
+            for a, b in zip(g, pair(*pargs, ys, readout=('mss', 'v_var'))):
+                npt.assert_array_equal(a, b)
+    # closing the generator early leaves nothing running on a dead input
+    it = cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=(torch.as_tensor(b).pin_memory() for b in batches),
+                                    readout='freq', depth=3)
+    first = next(it)
+    it.close()
+    npt.assert_array_equal(first[0].numpy(), want[0][0])
+    with pytest.raises(TypeError):
+        next(cg.filter_smoother_batches(cg.sgp_filter, *args, batches=batches))
+
+
 def test_zero_copy_pinned_measurements():
     """sgp_filter_smoother on a PINNED host tensor lets the filter kernel read the measurements in place (no upload); results
     are bit-identical to the uploaded path, for ragged lengths around the 32-sample blocks the producer streams."""
