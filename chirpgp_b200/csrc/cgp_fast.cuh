@@ -627,11 +627,9 @@ struct HalfWarp {
 };
 
 // row i of the drift Jacobian of the chirp SDE (models.py:104-110): J = [[-lam, -w, -w' u1, 0], [w, -lam, w' u0, 0],
-// [0, 0, 0, 1], [0, 0, -gamma^2, -2 gamma]]
-CGP_DEV void chirp_drift_and_jrow(const ModelSDE<1> &mdl, const HalfWarp &hw, const double (&m)[4], double (&a)[4], double (&jr)[4]) {
-    double gv, sg;
-    softplus_and_sigmoid(m[2], gv, sg);
-    const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
+// [0, 0, 0, 1], [0, 0, -gamma^2, -2 gamma]], for given w = 2 pi g(V) fs and w' = 2 pi g'(V) fs
+CGP_DEV void chirp_drift_and_jrow_w(const ModelSDE<1> &mdl, const HalfWarp &hw, const double (&m)[4], double w, double dw,
+                                    double (&a)[4], double (&jr)[4]) {
     mdl.drift_w(w, m, a);
     const bool r0 = hw.i == 0, r1 = hw.i == 1, r2 = hw.i == 2;
     jr[0] = r0 ? -mdl.lam : (r1 ? w : 0.);
@@ -639,24 +637,83 @@ CGP_DEV void chirp_drift_and_jrow(const ModelSDE<1> &mdl, const HalfWarp &hw, co
     jr[2] = r0 ? -dw * m[1] : (r1 ? dw * m[0] : (r2 ? 0. : -mdl.g2));
     jr[3] = (r0 || r1) ? 0. : (r2 ? 1. : -mdl.tg);
 }
+CGP_DEV void chirp_drift_and_jrow(const ModelSDE<1> &mdl, const HalfWarp &hw, const double (&m)[4], double (&a)[4], double (&jr)[4]) {
+    double gv, sg;
+    softplus_and_sigmoid(m[2], gv, sg);
+    chirp_drift_and_jrow_w(mdl, hw, m, (kTwoPi * gv) * mdl.fs, (kTwoPi * sg) * mdl.fs, a, jr);
+}
+// select without a branch (nested ?: over registers are sometimes compiled to BSSY / BRA / BSYNC, ~35 cycles each on a
+// single-warp dependency chain)
+CGP_DEV double selp(bool c, double a, double b) {
+    double r;
+    asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+    return r;
+}
+// Per-lane constants of row i of the chirp SDE's drift Jacobian and the row itself for given (w, w'): two selects on the
+// operands that vary instead of rebuilding the row by seven.
+struct ChirpJRow {
+    bool r0, r1, r01, j0, j1, j2;
+    double c0k, c1k, c2k, c3k, sgn;
+    CGP_DEV ChirpJRow(const ModelSDE<1> &mdl, const HalfWarp &hw)
+        : r0(hw.i == 0), r1(hw.i == 1), r01(hw.i < 2), j0(hw.j == 0), j1(hw.j == 1), j2(hw.j == 2) {
+        c0k = r0 ? -mdl.lam : 0.;
+        c1k = r1 ? -mdl.lam : 0.;
+        c2k = hw.i == 3 ? -mdl.g2 : 0.;
+        c3k = r01 ? 0. : (hw.i == 2 ? 1. : -mdl.tg);
+        sgn = r0 ? -1. : 1.;
+    }
+    CGP_DEV void row(const double (&m)[4], double w, double dw, double (&jr)[4]) const {
+        jr[0] = selp(r1, w, c0k);
+        jr[1] = selp(r0, -w, c1k);
+        jr[2] = selp(r01, (sgn * dw) * selp(r0, m[1], m[0]), c2k);
+        jr[3] = c3k;
+    }
+    CGP_DEV double by_col(const double (&v)[4]) const { return selp(j0, v[0], selp(j1, v[1], selp(j2, v[2], v[3]))); }
+};
+// The (V, V') block of the chirp SDE is linear and never sees the oscillator states, so in the FILTER (rhs = a(m)) the four
+// RK4 stage arguments of V follow from (V, V') alone: the step's four softplus / sigmoid evaluations are independent of each
+// other and of the covariance chain.  Lane (., j) of the half-warp evaluates stage j's (one evaluation per lane instead of
+// four (branch + exp + series) in sequence on the chain -- a single warp pays ~3 cycles per instruction it issues, replicated
+// or not) and the four (w, w') pairs are gathered by shuffle.  Same expressions as rk4_step_lane for the stage arguments.
+// The side of the softplus range split is chosen per chirp (half-warp): a chirp's result does not depend on its neighbour.
+CGP_DEV void chirp_stage_frequencies(const ModelSDE<1> &mdl, const HalfWarp &hw, const ChirpJRow &jc, double v, double vd,
+                                     double dt, double (&w)[4], double (&dw)[4]) {
+    double x[4];
+    x[0] = v;
+    double kv = vd, kd = fma(-mdl.tg, vd, -mdl.g2 * v);
+    double tv = v + dt * kv * 0.5, td = vd + dt * kd * 0.5;
+    x[1] = tv;
+    kv = td; kd = fma(-mdl.tg, td, -mdl.g2 * tv);
+    tv = v + dt * kv * 0.5; td = vd + dt * kd * 0.5;
+    x[2] = tv;
+    kv = td;
+    x[3] = v + dt * kv;
+    const double xs = jc.by_col(x);
+    const unsigned bal = __ballot_sync(0xffffffffu, softplus_in_series_range(xs));
+    double gv, sg;
+    if (((bal >> hw.base) & 0xffffu) == 0xffffu) softplus_sigmoid_series(xs, gv, sg);
+    else softplus_sigmoid_general(xs, gv, sg);
+    const double ws = (kTwoPi * gv) * mdl.fs, dws = (kTwoPi * sg) * mdl.fs;
+    CGP_UNROLL for (int q = 0; q < 4; q++) { w[q] = hw.get(ws, q); dw[q] = hw.get(dws, q); }
+}
 // (A P)_ij for the lane's (i, j), with `arow` = row i of A and P distributed one entry per lane
 CGP_DEV double row_times_P(const HalfWarp &hw, const double (&arow)[4], double Pe) {
     double s = arow[0] * hw.get(Pe, hw.j);
     CGP_UNROLL for (int k = 1; k < 4; k++) s = fma(arow[k], hw.get(Pe, 4 * k + hw.j), s);
     return s;
 }
-template <class Ode> CGP_DEV void rk4_step_lane(Ode &&ode, double (&m)[4], double &Pe, double dt) {
+template <class Ode> CGP_DEV void rk4_step_lane(Ode &&ode, double (&m)[4], double &Pe, double dt) {   // ode(stage, m, P, dm, dP)
     double km[4], kP, am[4], aP, tm[4], tP;
-    ode(m, Pe, km, kP);
+    ode(0, m, Pe, km, kP);
     CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = km[q]; tm[q] = m[q] + dt * km[q] * 0.5; }
     aP = kP; tP = Pe + dt * kP * 0.5;
-    ode(tm, tP, km, kP);
+    ode(1, tm, tP, km, kP);
     CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = am[q] + 2 * km[q]; tm[q] = m[q] + dt * km[q] * 0.5; }
     aP = aP + 2 * kP; tP = Pe + dt * kP * 0.5;
-    ode(tm, tP, km, kP);
+    ode(2, tm, tP, km, kP);
     CGP_UNROLL for (int q = 0; q < 4; q++) { am[q] = am[q] + 2 * km[q]; tm[q] = m[q] + dt * km[q]; }
     aP = aP + 2 * kP; tP = Pe + dt * kP;
-    ode(tm, tP, km, kP);
+    ode(3, tm, tP, km, kP);
     constexpr double kSixth = 1. / 6.;
     CGP_UNROLL for (int q = 0; q < 4; q++) m[q] = m[q] + dt * (am[q] + km[q]) * kSixth;
     Pe = Pe + dt * (aP + kP) * kSixth;
@@ -666,8 +723,8 @@ template <int NH>   // NH == 1: the chirp SDE (d = 4 -> 16 covariance entries ->
 __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, const FilterIO io) {
     static_assert(NH == 1, "16 lanes per chirp need d == 4");
     using Model = ModelSDE<1>;
-    constexpr int D = 4;
-    __shared__ double nl[2][16];
+    constexpr int D = 4, DD = 16, TB = 16;                   // time is walked in blocks of 16 steps (one nll slot per lane)
+    __shared__ double nl[2][TB];
     const int lane = threadIdx.x;
     const HalfWarp hw(lane);
     const int half = lane >> 4;
@@ -676,6 +733,7 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
     const int64_t b = active ? gid : p.B - 1;
     Model mdl;
     mdl.load(p.consts + b * p.consts_stride);
+    const ChirpJRow jc(mdl, hw);
     double m[D], H[D];
     load_vec<D>(p.m0 + b * p.m0_stride, m);
     CGP_UNROLL for (int q = 0; q < D; q++) H[q] = p.H[q];
@@ -683,64 +741,69 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
     const int ii = hw.i > hw.j ? hw.i : hw.j, jj = hw.i > hw.j ? hw.j : hw.i;
     double Pe = (p.P0 + b * p.P0_stride)[ii * D + jj];
     const double Qe = (p.Qc + b * p.Qc_stride)[ii * D + jj];
-    const double hi = H[0] * (hw.i == 0) + H[1] * (hw.i == 1) + H[2] * (hw.i == 2) + H[3] * (hw.i == 3);
-    const double hj = H[0] * (hw.j == 0) + H[1] * (hw.j == 1) + H[2] * (hw.j == 2) + H[3] * (hw.j == 3);
+    const double hj = jc.by_col(H);
     const double *__restrict__ y = io.ys + (b / p.ys_repeat) * p.T;
     const int64_t T = p.T;
     const bool store_state = io.mfs != nullptr && active;
+    const bool store_m = store_state && hw.l < D;
     const bool store_nell = io.nell != nullptr && active;
     const double dt = p.dt, Xi = p.Xi;
-    double carry = 0., Sk = 1., rk = 0.;
-    double yv = (hw.l < T) ? __ldg(y + hw.l) : 0.;
-    for (int64_t t = 0; t < T; t++) {
-        const int slot = (int)(t & 15);
-        const double yt = hw.get(yv, slot);
-        if (slot == 15 && t + 1 < T) yv = (t + 1 + hw.l < T) ? __ldg(y + t + 1 + hw.l) : 0.;
-        rk4_step_lane([&](const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
-            double jr[D];
-            chirp_drift_and_jrow(mdl, hw, mm, dm, jr);
-            const double X = row_times_P(hw, jr, PP);
-            const double Xt = hw.get(X, 4 * hw.j + hw.i);
-            dP = (Xt + X) + Qe;                                  // P J^T + J P + b b^T  (filters_smoothers.py:385)
-        }, m, Pe, dt);
-        // ---- measurement update (filters_smoothers.py:55-68): c = P h, S = h^T c + Xi
-        double cr = Pe * hj;                                     // row sums: c_i = sum_j P_ij h_j
-        cr += __shfl_xor_sync(0xffffffffu, cr, 1);
-        cr += __shfl_xor_sync(0xffffffffu, cr, 2);
-        double c[D];
-        CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
-        double S = H[0] * c[0];
-        CGP_UNROLL for (int q = 1; q < D; q++) S = fma(H[q], c[q], S);
-        S += Xi;
-        double pred = H[0] * m[0];
-        CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], m[q], pred);
-        const double rS = fast_rcp(S), resid = yt - pred;
-        double K[D];
-        CGP_UNROLL for (int q = 0; q < D; q++) K[q] = c[q] * rS;
-        CGP_UNROLL for (int q = 0; q < D; q++) m[q] = fma(K[q], resid, m[q]);
-        const double Ki = hw.i == 0 ? K[0] : (hw.i == 1 ? K[1] : (hw.i == 2 ? K[2] : K[3]));
-        const double Kj = hw.j == 0 ? K[0] : (hw.j == 1 ? K[1] : (hw.j == 2 ? K[2] : K[3]));
-        Pe = fma(-(Ki * Kj), S, Pe);
-        (void)hi;
-        if (hw.l == slot) { Sk = S; rk = resid; }
-        if (store_state) {
-            io.Pfs[(b * T + t) * (D * D) + hw.l] = Pe;
-            if (hw.l < D) io.mfs[(b * T + t) * D + hw.l] = hw.l == 0 ? m[0] : (hw.l == 1 ? m[1] : (hw.l == 2 ? m[2] : m[3]));
-        }
-        if (slot == 15 || t == T - 1) {
-            const int n = slot + 1;
-            const int64_t t0 = t - slot;
-            nl[half][hw.l] = hw.l < n ? nll_increment(Sk, rk) : 0.;
-            __syncwarp();
-            if (hw.l == 0) {
-                double cc = carry;
-                for (int q = 0; q < n; q++) { cc = cc + nl[half][q]; nl[half][q] = cc; }
+    double *pP = store_state ? io.Pfs + b * T * DD + hw.l : nullptr;
+    double *pm = store_state ? io.mfs + b * T * D + hw.j : nullptr;
+    double carry = 0.;
+    double ynext = (hw.l < T) ? __ldg(y + hw.l) : 0.;
+    for (int64_t t0 = 0; t0 < T; t0 += TB) {
+        const int n = (int)(T - t0 < TB ? T - t0 : TB);
+        const double ycur = ynext;
+        if (t0 + TB < T) ynext = (t0 + TB + hw.l < T) ? __ldg(y + t0 + TB + hw.l) : 0.;   // next block's samples in flight
+        double Sk = 1., rk = 0.;
+        // 32-bit inner loop that holds the chain and nothing else (no flush test, no 64-bit trip count)
+        for (int s = 0; s < n; s++) {
+            const double yt = hw.get(ycur, s);
+            double wst[4], dwst[4];
+            chirp_stage_frequencies(mdl, hw, jc, m[2], m[3], dt, wst, dwst);
+            rk4_step_lane([&](int stage, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+                double jr[D];
+                mdl.drift_w(wst[stage], mm, dm);
+                jc.row(mm, wst[stage], dwst[stage], jr);
+                const double X = row_times_P(hw, jr, PP);
+                const double Xt = hw.get(X, 4 * hw.j + hw.i);
+                dP = (Xt + X) + Qe;                                  // P J^T + J P + b b^T  (filters_smoothers.py:385)
+            }, m, Pe, dt);
+            // ---- measurement update (filters_smoothers.py:55-68): c = P h, S = h^T c + Xi
+            double cr = Pe * hj;                                     // row sums: c_i = sum_j P_ij h_j, in every lane of row i
+            cr += __shfl_xor_sync(0xffffffffu, cr, 1);
+            cr += __shfl_xor_sync(0xffffffffu, cr, 2);
+            double c[D];
+            CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
+            const double cj = hw.get(cr, 4 * hw.j);
+            double S = H[0] * c[0];
+            CGP_UNROLL for (int q = 1; q < D; q++) S = fma(H[q], c[q], S);
+            S += Xi;
+            double pred = H[0] * m[0];
+            CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], m[q], pred);
+            const double rS = fast_rcp(S), resid = yt - pred;
+            CGP_UNROLL for (int q = 0; q < D; q++) m[q] = fma(c[q] * rS, resid, m[q]);
+            Pe = fma(-((cr * rS) * (cj * rS)), S, Pe);               // P - K K^T S, K = c / S
+            Sk = selp(hw.l == s, S, Sk);
+            rk = selp(hw.l == s, resid, rk);
+            if (store_state) {
+                *pP = Pe;
+                if (store_m) *pm = jc.by_col(m);
+                pP += DD;
+                pm += D;
             }
-            __syncwarp();
-            carry = nl[half][n - 1];
-            if (store_nell && !io.nell_last_only && hw.l < n) io.nell[b * T + t0 + hw.l] = nl[half][hw.l];
-            __syncwarp();
         }
+        nl[half][hw.l] = hw.l < n ? nll_increment(Sk, rk) : 0.;
+        __syncwarp();
+        if (hw.l == 0) {
+            double cc = carry;
+            for (int q = 0; q < n; q++) { cc = cc + nl[half][q]; nl[half][q] = cc; }
+        }
+        __syncwarp();
+        carry = nl[half][n - 1];
+        if (store_nell && !io.nell_last_only && hw.l < n) io.nell[b * T + t0 + hw.l] = nl[half][hw.l];
+        __syncwarp();
     }
     if (store_nell && io.nell_last_only && hw.l == 0) io.nell[b] = carry;
 }
@@ -801,7 +864,7 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
         double mf[D], xcol[D];                         // column i of X: row i of X^T = gamma Pf^{-1}, and the constant part of M's row i
         load_vec<D>(&pre[half][t & 15][0], mf);
         load_vec<D>(&pre[half][t & 15][D + hw.i * D], xcol);
-        rk4_step_lane([&](const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+        rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
             double jr[D], a[D], z[D];
             chirp_drift_and_jrow(mdl, hw, mm, a, jr);
             CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];

@@ -138,14 +138,14 @@ CGP_MDEV double fast_softplus_warp(double x) {
     if (__all_sync(0xffffffffu, x >= 3. && x <= 700.)) return softplus_series(x);
     return softplus_general(x);
 }
-// softplus and its derivative sigmoid(x) = e^x / (e^x + 1) = 1 / (1 + e^-x)
-CGP_MDEV void fast_softplus_sigmoid(double x, double &g, double &sg) {
-    if (!(x >= 3. && x <= 700.)) {
-        const double ex = fast_exp(x), d = ex + 1.;
-        g = fast_log_pos(d);
-        sg = (ex < 1.7976931348623157e308) ? ex * fast_rcp(d) : 1.;     // e^x / (e^x + 1); inf / inf would be NaN
-        return;
-    }
+// softplus and its derivative sigmoid(x) = e^x / (e^x + 1) = 1 / (1 + e^-x): the two sides of the range split, each
+// branch-free (callers that evaluate several arguments at once pick the side once and interleave the evaluations)
+CGP_MDEV void softplus_sigmoid_general(double x, double &g, double &sg) {
+    const double ex = fast_exp(x), d = ex + 1.;
+    g = fast_log_pos(d);
+    sg = (ex < 1.7976931348623157e308) ? ex * fast_rcp(d) : 1.;         // e^x / (e^x + 1); inf / inf would be NaN
+}
+CGP_MDEV void softplus_sigmoid_series(double x, double &g, double &sg) {   // 3 <= x <= 700
     const double u = fast_exp_inrange(-x);
     const double u2 = u * u, u4 = u2 * u2, u8 = u4 * u4;
     const double p0 = fma(u, -0.5, 1.);
@@ -160,6 +160,14 @@ CGP_MDEV void fast_softplus_sigmoid(double x, double &g, double &sg) {
     const double s = fma(u8, q2, fma(u4, q1, q0));
     g = fma(u, s, x);
     sg = fast_rcp(1. + u);
+}
+CGP_MDEV bool softplus_in_series_range(double x) { return x >= 3. && x <= 700.; }
+CGP_MDEV void fast_softplus_sigmoid(double x, double &g, double &sg) {
+    if (!softplus_in_series_range(x)) {
+        softplus_sigmoid_general(x, g, sg);
+        return;
+    }
+    softplus_sigmoid_series(x, g, sg);
 }
 
 // ---- sincos(x): Cody-Waite reduction by pi/2 in three FMA steps (accurate for |x| <= 1e9), fdlibm kernel
