@@ -5,6 +5,7 @@
 //   * sigma-point partial sums are combined through shared memory in a fixed tree order instead of a
 //     shuffle butterfly (a different, still deterministic, summation order).
 #pragma once
+#include <type_traits>
 #include "cgp_kernels.cuh"
 
 namespace cgp {
@@ -813,12 +814,12 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
 // half-warp loads (mf, Pf) of step j, factorises Pf and solves for X (SIMD over time), and the time loop reads [mf | X] back
 // from shared memory.  With gamma symmetric, gamma Pf^{-1} = X^T, so dm = a + X^T (m - mf): a 4 x 4 product on the chain instead
 // of the reference's two triangular solves per stage (same value up to rounding).
-template <int NH>
+template <int NH, bool STRAIGHT>
 __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, const SmootherIO io) {
     static_assert(NH == 1, "16 lanes per chirp need d == 4");
     using Model = ModelSDE<1>;
-    constexpr int D = 4, DD = 16, PROW = 22;               // [mf (4) | X (16)] + pad: 11 x 16 bytes per row
-    __shared__ __align__(16) double pre[2][16][PROW];
+    constexpr int D = 4, DD = 16, TB = 16, PROW = 22;      // [mf (4) | X (16)] + pad: 11 x 16 bytes per row
+    __shared__ __align__(16) double pre[2][TB][PROW];
     const int lane = threadIdx.x;
     const HalfWarp hw(lane);
     const int half = lane >> 4;
@@ -828,6 +829,7 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
     const int64_t T = p.T;
     Model mdl;
     mdl.load(p.consts + b * p.consts_stride);
+    const ChirpJRow jc(mdl, hw);
     double Qf[D][D];
     CGP_UNROLL for (int r = 0; r < D; r++) CGP_UNROLL for (int c = 0; c < D; c++) {
         const int rr = r > c ? r : c, cc = r > c ? c : r;
@@ -835,52 +837,122 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
     }
     const int ii = hw.i > hw.j ? hw.i : hw.j, jj = hw.i > hw.j ? hw.j : hw.i;
     const double Qe = (p.Qc + b * p.Qc_stride)[ii * D + jj];
+    const double *__restrict__ mfs = io.mfs + b * T * D;
+    const double *__restrict__ Pfs = io.Pfs + b * T * DD;
     double ms[D];
-    load_vec<D>(io.mfs + (b * T + T - 1) * D, ms);
-    double Pe = io.Pfs[(b * T + T - 1) * DD + ii * D + jj];
+    load_vec<D>(mfs + (T - 1) * D, ms);
+    double Pe = Pfs[(T - 1) * DD + ii * D + jj];
+    const bool store_m = active && hw.l < D;
     if (active) {
         io.Pss[(b * T + T - 1) * DD + hw.l] = Pe;
-        if (hw.l < D) io.mss[(b * T + T - 1) * D + hw.l] = io.mfs[(b * T + T - 1) * D + hw.l];
+        if (store_m) io.mss[(b * T + T - 1) * D + hw.l] = mfs[(T - 1) * D + hw.l];
     }
     const double ndt = -p.dt;
-    for (int64_t t = T - 2; t >= 0; t--) {
-        if (t == T - 2 || (t & 15) == 15) {            // first step of a 16-aligned block: lane j prepares step (t & ~15) + j
-            const int64_t tj = (t & ~(int64_t)15) + hw.l;
-            if (tj <= t) {
-                double mfj[D], Pf[D][D], Lf[D][D], rinv[D];
-                load_vec<D>(io.mfs + (b * T + tj) * D, mfj);
-                load_mat<D>(io.Pfs + (b * T + tj) * DD, Pf);
-                chol_lower_rsqrt<D>(Pf, Lf, rinv);
-                store_vec<D>(&pre[half][hw.l][0], mfj);
-                CGP_UNROLL for (int c = 0; c < D; c++) {       // column c of X = Pf^{-1} gamma
-                    double col[D];
-                    CGP_UNROLL for (int q = 0; q < D; q++) col[q] = Qf[q][c];
-                    chol_solve_vec_rinv<D>(Lf, rinv, col);
-                    store_vec<D>(&pre[half][hw.l][D + c * D], col);
+    // steps T-2 ... 0 in 16-aligned blocks, walked downwards; per block lane j prepares step lo + j (SIMD over time), the
+    // 32-bit inner loop holds the chain and nothing else
+    for (int64_t hi = T - 1; hi > 0;) {                    // steps [lo, hi) of this block
+        const int64_t lo = (hi - 1) & ~(int64_t)(TB - 1);
+        const int n = (int)(hi - lo);
+        if (hw.l < n) {
+            const int64_t tj = lo + hw.l;
+            double mfj[D], Pf[D][D], Lf[D][D], rinv[D];
+            load_vec<D>(mfs + tj * D, mfj);
+            load_mat<D>(Pfs + tj * DD, Pf);
+            chol_lower_rsqrt<D>(Pf, Lf, rinv);
+            store_vec<D>(&pre[half][hw.l][0], mfj);
+            CGP_UNROLL for (int c = 0; c < D; c++) {       // column c of X = Pf^{-1} gamma
+                double col[D];
+                CGP_UNROLL for (int q = 0; q < D; q++) col[q] = Qf[q][c];
+                chol_solve_vec_rinv<D>(Lf, rinv, col);
+                store_vec<D>(&pre[half][hw.l][D + c * D], col);
+            }
+        }
+        __syncwarp();
+        double *pP = io.Pss + (b * T + hi - 1) * DD + hw.l;
+        double *pm = io.mss + (b * T + hi - 1) * D + hw.j;
+        for (int s = n - 1; s >= 0; s--) {
+            double mf[D], xcol[D];                         // column i of X: row i of X^T = gamma Pf^{-1}, and the constant part of M's row i
+            load_vec<D>(&pre[half][s][0], mf);
+            load_vec<D>(&pre[half][s][D + hw.i * D], xcol);
+            // One straight-line RK4 step: softplus(V) of stage s+1 does not depend on that of stage s (w_s reaches V only two
+            // stages later, through the oscillator rows of X^T z), so without the per-stage range branch the scheduler can keep
+            // two evaluations in flight.  The side of the split is chosen once per step from V at its start (0.5 of margin);
+            // if a stage argument left [3, 700] after all, the step is redone with the reference's literal formula.
+            auto rk4_with = [&](auto series_tag, double (&mm0)[D], double &PP0) -> bool {
+                constexpr bool SERIES = decltype(series_tag)::value;
+                bool ok = true;
+                rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+                    double jr[D], a[D], z[D], gv, sg;
+                    if constexpr (SERIES) {
+                        ok = ok && softplus_in_series_range(mm[2]);
+                        softplus_sigmoid_series(mm[2], gv, sg);
+                    } else {
+                        softplus_sigmoid_general(mm[2], gv, sg);
+                    }
+                    const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
+                    mdl.drift_w(w, mm, a);
+                    jc.row(mm, w, dw, jr);
+                    CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
+                    CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
+                    // dm_r = a_r + sum_k X_kr z_k: lane (i, .) forms component i with its column of X, the four are gathered
+                    double di = xcol[0] * z[0];
+                    CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
+                    CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
+                    const double Y = row_times_P(hw, jr, PP);
+                    const double Yt = hw.get(Y, 4 * hw.j + hw.i);
+                    dP = (Y + Yt) - Qe;
+                }, mm0, PP0, ndt);
+                return ok;
+            };
+            if constexpr (!STRAIGHT) {
+                // reference schedule: range branch per stage (warp-uniform side)
+                rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+                    double jr[D], a[D], z[D], gv, sg;
+                    softplus_and_sigmoid(mm[2], gv, sg);
+                    const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
+                    mdl.drift_w(w, mm, a);
+                    jc.row(mm, w, dw, jr);
+                    CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
+                    CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
+                    double di = xcol[0] * z[0];
+                    CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
+                    CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
+                    const double Y = row_times_P(hw, jr, PP);
+                    const double Yt = hw.get(Y, 4 * hw.j + hw.i);
+                    dP = (Y + Yt) - Qe;
+                }, ms, Pe, ndt);
+            } else {
+            // the choice is per chirp (the mean is replicated, so `calm` and `ok` are uniform within a half-warp), but the warp
+                // stays converged through both versions -- the shuffles inside are full-warp
+                const bool calm = ms[2] >= 3.5 && ms[2] <= 699.5;
+                bool done = false;
+                if (__any_sync(0xffffffffu, calm)) {
+                    double mt[D] = {ms[0], ms[1], ms[2], ms[3]}, Pt = Pe;
+                    const bool ok = rk4_with(std::true_type{}, mt, Pt);
+                    if (calm && ok) {
+                        CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mt[q];
+                        Pe = Pt;
+                        done = true;
+                    }
+                }
+                if (__any_sync(0xffffffffu, !done)) {
+                    double mt[D] = {ms[0], ms[1], ms[2], ms[3]}, Pt = Pe;
+                    rk4_with(std::false_type{}, mt, Pt);
+                    if (!done) {
+                        CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mt[q];
+                        Pe = Pt;
+                    }
                 }
             }
-            __syncwarp();
+            if (active) {
+                *pP = Pe;
+                if (store_m) *pm = jc.by_col(ms);
+            }
+            pP -= DD;
+            pm -= D;
         }
-        double mf[D], xcol[D];                         // column i of X: row i of X^T = gamma Pf^{-1}, and the constant part of M's row i
-        load_vec<D>(&pre[half][t & 15][0], mf);
-        load_vec<D>(&pre[half][t & 15][D + hw.i * D], xcol);
-        rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
-            double jr[D], a[D], z[D];
-            chirp_drift_and_jrow(mdl, hw, mm, a, jr);
-            CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
-            CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
-            // dm_r = a_r + sum_k X_kr z_k: lane (i, .) forms component i with its column of X, the four are gathered
-            double di = xcol[0] * z[0];
-            CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
-            CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
-            const double Y = row_times_P(hw, jr, PP);
-            const double Yt = hw.get(Y, 4 * hw.j + hw.i);
-            dP = (Y + Yt) - Qe;
-        }, ms, Pe, ndt);
-        if (active) {
-            io.Pss[(b * T + t) * DD + hw.l] = Pe;
-            if (hw.l < D) io.mss[(b * T + t) * D + hw.l] = hw.l == 0 ? ms[0] : (hw.l == 1 ? ms[1] : (hw.l == 2 ? ms[2] : ms[3]));
-        }
+        __syncwarp();
+        hi = lo;
     }
 }
 
