@@ -104,7 +104,10 @@ CGP_DEV void cub_gain_record(const ModelLCD<NH> &mdl, double w, double *row, con
             }
         }
     }
-    CGP_UNROLL for (int r = D - 1; r >= 0; r--) {
+    // a real loop: nothing in it indexes registers by r, and unrolled the eight rows are ~1200 instructions that the consumer
+    // warp walks once per block, i.e. always cold in the instruction cache (ncu: stall_no_instruction 1.4 per issue)
+    #pragma unroll 1
+    for (int r = D - 1; r >= 0; r--) {
         double z[D];
         load_vec<D>(row + r * D, z);
         CGP_UNROLL for (int i = 0; i < D; i++) {
@@ -120,7 +123,8 @@ CGP_DEV void cub_gain_record(const ModelLCD<NH> &mdl, double w, double *row, con
         double cacc = mPq[r];                                   // c_r = m_r - G_r . mp
         CGP_UNROLL for (int k = 0; k < D; k++) cacc = fma(-z[k], mp[k], cacc);
         row[DD + r] = cacc;
-        CGP_UNROLL for (int q = 0; q <= r; q++) {                // C_rq = P_rq - G_r . D_q   (rows q <= r of D are still in place)
+        #pragma unroll 1
+        for (int q = 0; q <= r; q++) {                           // C_rq = P_rq - G_r . D_q   (rows q <= r of D are still in place)
             double dq[D];
             load_vec<D>(row + q * D, dq);
             double acc = mPq[D + sidx(r, q)];
