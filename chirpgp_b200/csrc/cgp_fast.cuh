@@ -5,7 +5,6 @@
 //   * sigma-point partial sums are combined through shared memory in a fixed tree order instead of a
 //     shuffle butterfly (a different, still deterministic, summation order).
 #pragma once
-#include <type_traits>
 #include "cgp_kernels.cuh"
 
 namespace cgp {
@@ -814,7 +813,7 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
 // half-warp loads (mf, Pf) of step j, factorises Pf and solves for X (SIMD over time), and the time loop reads [mf | X] back
 // from shared memory.  With gamma symmetric, gamma Pf^{-1} = X^T, so dm = a + X^T (m - mf): a 4 x 4 product on the chain instead
 // of the reference's two triangular solves per stage (same value up to rounding).
-template <int NH, bool STRAIGHT>
+template <int NH>
 __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, const SmootherIO io) {
     static_assert(NH == 1, "16 lanes per chirp need d == 4");
     using Model = ModelSDE<1>;
@@ -874,76 +873,25 @@ __global__ void __launch_bounds__(32) cd_eks_lane_kernel(const CgpProblem p, con
             double mf[D], xcol[D];                         // column i of X: row i of X^T = gamma Pf^{-1}, and the constant part of M's row i
             load_vec<D>(&pre[half][s][0], mf);
             load_vec<D>(&pre[half][s][D + hw.i * D], xcol);
-            // One straight-line RK4 step: softplus(V) of stage s+1 does not depend on that of stage s (w_s reaches V only two
-            // stages later, through the oscillator rows of X^T z), so without the per-stage range branch the scheduler can keep
-            // two evaluations in flight.  The side of the split is chosen once per step from V at its start (0.5 of margin);
-            // if a stage argument left [3, 700] after all, the step is redone with the reference's literal formula.
-            auto rk4_with = [&](auto series_tag, double (&mm0)[D], double &PP0) -> bool {
-                constexpr bool SERIES = decltype(series_tag)::value;
-                bool ok = true;
-                rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
-                    double jr[D], a[D], z[D], gv, sg;
-                    if constexpr (SERIES) {
-                        ok = ok && softplus_in_series_range(mm[2]);
-                        softplus_sigmoid_series(mm[2], gv, sg);
-                    } else {
-                        softplus_sigmoid_general(mm[2], gv, sg);
-                    }
-                    const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
-                    mdl.drift_w(w, mm, a);
-                    jc.row(mm, w, dw, jr);
-                    CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
-                    CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
-                    // dm_r = a_r + sum_k X_kr z_k: lane (i, .) forms component i with its column of X, the four are gathered
-                    double di = xcol[0] * z[0];
-                    CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
-                    CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
-                    const double Y = row_times_P(hw, jr, PP);
-                    const double Yt = hw.get(Y, 4 * hw.j + hw.i);
-                    dP = (Y + Yt) - Qe;
-                }, mm0, PP0, ndt);
-                return ok;
-            };
-            if constexpr (!STRAIGHT) {
-                // reference schedule: range branch per stage (warp-uniform side)
-                rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
-                    double jr[D], a[D], z[D], gv, sg;
-                    softplus_and_sigmoid(mm[2], gv, sg);
-                    const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
-                    mdl.drift_w(w, mm, a);
-                    jc.row(mm, w, dw, jr);
-                    CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
-                    CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
-                    double di = xcol[0] * z[0];
-                    CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
-                    CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
-                    const double Y = row_times_P(hw, jr, PP);
-                    const double Yt = hw.get(Y, 4 * hw.j + hw.i);
-                    dP = (Y + Yt) - Qe;
-                }, ms, Pe, ndt);
-            } else {
-            // the choice is per chirp (the mean is replicated, so `calm` and `ok` are uniform within a half-warp), but the warp
-                // stays converged through both versions -- the shuffles inside are full-warp
-                const bool calm = ms[2] >= 3.5 && ms[2] <= 699.5;
-                bool done = false;
-                if (__any_sync(0xffffffffu, calm)) {
-                    double mt[D] = {ms[0], ms[1], ms[2], ms[3]}, Pt = Pe;
-                    const bool ok = rk4_with(std::true_type{}, mt, Pt);
-                    if (calm && ok) {
-                        CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mt[q];
-                        Pe = Pt;
-                        done = true;
-                    }
-                }
-                if (__any_sync(0xffffffffu, !done)) {
-                    double mt[D] = {ms[0], ms[1], ms[2], ms[3]}, Pt = Pe;
-                    rk4_with(std::false_type{}, mt, Pt);
-                    if (!done) {
-                        CGP_UNROLL for (int q = 0; q < D; q++) ms[q] = mt[q];
-                        Pe = Pt;
-                    }
-                }
-            }
+            // (a straight-line variant of this step -- side of the softplus split chosen once per step so that two evaluations
+            // could be in flight: V of stage s+1 does not depend on w of stage s -- was measured and dropped: ptxas does not
+            // overlap them, 5.52 vs 5.43 ms, profiles/r2_cd_lane_kernels.txt)
+            rk4_step_lane([&](int, const double (&mm)[D], double PP, double (&dm)[D], double &dP) {
+                double jr[D], a[D], z[D], gv, sg;
+                softplus_and_sigmoid(mm[2], gv, sg);
+                const double w = (kTwoPi * gv) * mdl.fs, dw = (kTwoPi * sg) * mdl.fs;
+                mdl.drift_w(w, mm, a);
+                jc.row(mm, w, dw, jr);
+                CGP_UNROLL for (int q = 0; q < D; q++) jr[q] = jr[q] + xcol[q];
+                CGP_UNROLL for (int q = 0; q < D; q++) z[q] = mm[q] - mf[q];
+                // dm_r = a_r + sum_k X_kr z_k: lane (i, .) forms component i with its column of X, the four are gathered
+                double di = xcol[0] * z[0];
+                CGP_UNROLL for (int k = 1; k < D; k++) di = fma(xcol[k], z[k], di);
+                CGP_UNROLL for (int r = 0; r < D; r++) dm[r] = a[r] + hw.get(di, 4 * r);
+                const double Y = row_times_P(hw, jr, PP);
+                const double Yt = hw.get(Y, 4 * hw.j + hw.i);
+                dP = (Y + Yt) - Qe;
+            }, ms, Pe, ndt);
             if (active) {
                 *pP = Pe;
                 if (store_m) *pm = jc.by_col(ms);

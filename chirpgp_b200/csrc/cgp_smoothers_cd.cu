@@ -1,14 +1,11 @@
 // cd_eks / cd_sgp_smoother launchers (sequential RK4 backwards in time).
-#include <cstdlib>
 #include "cgp_dispatch.cuh"
 
 namespace cgp {
 
 int launch_cd_eks(const CgpProblem &p, const SmootherIO &io, cudaStream_t s) {
     if (p.model == CGP_MODEL_SDE && p.num_harmonics == 1 && p.d == 4 && p.B <= 40000) {
-        const char *v = getenv("CGP_EKS_STRAIGHT");
-        if (v && atoi(v)) cd_eks_lane_kernel<1, true><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
-        else cd_eks_lane_kernel<1, false><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        cd_eks_lane_kernel<1><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
         return check_launch();
     }
     return dispatch_sde(p, [&](auto tag) {
