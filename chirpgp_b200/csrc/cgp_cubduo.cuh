@@ -13,8 +13,8 @@
 //   consumer  does everything that is not on the chain, for both chirps: the cross-covariance (D = L E with
 //             E_j = s w (mu_j+ - mu_j-): the m mp^T terms cancel identically, as in cubature_gain_kernel), the nll increments,
 //             the coalesced stores of mfs / Pfs / nell, and every 8 steps the smoother records [G | c | C] (cgp_kernels.cuh),
-//             lane (chirp, step) working on one record: two d x d Cholesky factorisations, d pairs of triangular solves, in place
-//             in shared memory.
+//             a pair of lanes per (chirp, step) record: two d x d Cholesky factorisations (both lanes), d pairs of triangular
+//             solves (rows dealt to the two), in place in shared memory.
 //
 // Hand-over exactly as in cgp_duo.cuh: NBUF buffers, FULL = one named barrier per buffer (producer bar.arrive, consumer
 // bar.sync), EMPTY = a progress word the producer reads one step ahead.  255 registers x 64 threads x 4 CTAs per SM: 592 CTAs
@@ -68,22 +68,30 @@ CGP_DEV void cub_moments(const ModelLCD<NH> &mdl, double w, const double (&tot)[
 // Smoother record of one step, in place: row = [E (d x d) | tot (d + NSym)] -> [G | c | C]; mPq = [m | P packed] the prediction
 // started from.  D = L E (L = chol(Pq)) overwrites E from the last row up (row r needs E rows <= r); the rows of G = D Pp^{-1}
 // then overwrite D from the last row up as well, because C_rq = P_rq - G_r . D_q needs the rows q <= r of D.
+// A PAIR of lanes works on one record (the block holds 8 steps per chirp, a half-warp has 16 lanes): both factorise (the
+// Cholesky factors live in registers), member 0 takes the odd rows of D and of G, member 1 the even ones -- the rows are
+// independent given the factors.  The in-place order above then needs the pair in step: every row is stored behind a
+// __syncwarp() that follows the other member's reads of it.  Called by all 32 lanes; `valid` = the pair's step exists.
 template <int NH>
-CGP_DEV void cub_gain_record(const ModelLCD<NH> &mdl, double w, double *row, const double *mPq) {
+CGP_DEV void cub_gain_record(const ModelLCD<NH> &mdl, double w, double *row, const double *mPq, int member, bool valid) {
     using C = CubDuoCfg<NH>;
     constexpr int D = C::D, NS = C::NS, NA = C::NA, DD = C::DD;
+    static_assert(D % 2 == 0, "rows are dealt to the two members in pairs");
+    const bool m1 = member != 0;
     {
         double Pq[NS], L[NS];
         load_vec<NS>(mPq + D, Pq);
         chol_lower_sym_rsqrt<D>(Pq, L);
-        CGP_UNROLL for (int r = D - 1; r >= 0; r--) {
+        CGP_UNROLL for (int ra = D - 1; ra >= 1; ra -= 2) {          // member 0: row ra, member 1: row ra - 1 (its last term is 0 e)
             double d[D];
-            CGP_UNROLL for (int k = 0; k <= r; k++) {
+            CGP_UNROLL for (int k = 0; k <= ra; k++) {
                 double e[D];
                 load_vec<D>(row + k * D, e);
-                CGP_UNROLL for (int c = 0; c < D; c++) d[c] = (k == 0) ? L[sidx(r, 0)] * e[c] : fma(L[sidx(r, k)], e[c], d[c]);
+                const double coef = (k == ra) ? selp(m1, 0., L[sidx(ra, ra)]) : selp(m1, L[sidx(ra - 1, k)], L[sidx(ra, k)]);
+                CGP_UNROLL for (int c = 0; c < D; c++) d[c] = (k == 0) ? coef * e[c] : fma(coef, e[c], d[c]);
             }
-            store_vec<D>(row + r * D, d);
+            __syncwarp();
+            if (valid) store_vec<D>(row + (ra - member) * D, d);
         }
     }
     double mp[D], Lq[NS], rinv[D];
@@ -104,10 +112,11 @@ CGP_DEV void cub_gain_record(const ModelLCD<NH> &mdl, double w, double *row, con
             }
         }
     }
-    // a real loop: nothing in it indexes registers by r, and unrolled the eight rows are ~1200 instructions that the consumer
+    __syncwarp();                                                // both members hold tot; every row of D is in place
+    // a real loop: nothing in it indexes registers by r, and unrolled the rows are ~1200 instructions that the consumer
     // warp walks once per block, i.e. always cold in the instruction cache (ncu: stall_no_instruction 1.4 per issue)
     #pragma unroll 1
-    for (int r = D - 1; r >= 0; r--) {
+    for (int r = D - 1 - member; r >= 0; r -= 2) {
         double z[D];
         load_vec<D>(row + r * D, z);
         CGP_UNROLL for (int i = 0; i < D; i++) {
@@ -122,16 +131,17 @@ CGP_DEV void cub_gain_record(const ModelLCD<NH> &mdl, double w, double *row, con
         }
         double cacc = mPq[r];                                   // c_r = m_r - G_r . mp
         CGP_UNROLL for (int k = 0; k < D; k++) cacc = fma(-z[k], mp[k], cacc);
-        row[DD + r] = cacc;
+        if (valid) row[DD + r] = cacc;
         #pragma unroll 1
         for (int q = 0; q <= r; q++) {                           // C_rq = P_rq - G_r . D_q   (rows q <= r of D are still in place)
             double dq[D];
             load_vec<D>(row + q * D, dq);
             double acc = mPq[D + sidx(r, q)];
             CGP_UNROLL for (int k = 0; k < D; k++) acc = fma(-z[k], dq[k], acc);
-            row[DD + D + sidx(r, q)] = acc;
+            if (valid) row[DD + D + sidx(r, q)] = acc;
         }
-        store_vec<D>(row + r * D, z);
+        __syncwarp();
+        if (valid) store_vec<D>(row + r * D, z);
     }
 }
 
@@ -306,7 +316,11 @@ __global__ void __launch_bounds__(64, 4) cub_duo_filter_kernel(const CgpProblem 
         }
         if (gains) {
             // lane j: [E | tot] of iteration t0 + j and the state of step t0 + j - 1 (ring row j) -> workspace record t0 + j - 1
-            if (l < n) cub_gain_record<NH>(mdl, w, &sm.rec[h][l][0], &sm.ring[h][l][0]);
+            // (all 32 lanes call it: the pair (l >> 1) of each half-warp works on step t0 + (l >> 1))
+            static_assert(BLK == 8, "two lanes per record, 16 lanes per chirp");
+            const int jr = l >> 1;
+            const bool valid = jr < n;
+            cub_gain_record<NH>(mdl, w, &sm.rec[h][valid ? jr : 0][0], &sm.ring[h][valid ? jr : 0][0], l & 1, valid);
             __syncwarp();
             const int j0 = (t0 == 0) ? 1 : 0;              // iteration 0 predicts from (m0, P0): no smoother record
             if (active) {
