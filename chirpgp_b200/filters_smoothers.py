@@ -81,7 +81,8 @@ def _back(t: torch.Tensor, kind, sync: bool = True):
     # host callers (NumPy arrays / CPU tensors) get results backed by pinned host memory (torch's caching host allocator
     # recycles the blocks): the device->host copy of the (T, d, d) outputs runs at the PCIe rate instead of the pageable rate
     host = None
-    if t.is_cuda and t.numel() * t.element_size() >= _PINNED_MIN_BYTES:
+    # (sync=False: a small result must not take the blocking pageable copy either -- it would stall the batch sequence)
+    if t.is_cuda and (not sync or t.numel() * t.element_size() >= _PINNED_MIN_BYTES):
         try:
             host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             host.copy_(t, non_blocking=True)
