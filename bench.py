@@ -36,7 +36,7 @@ METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
 WORKLOAD = ('configs[1]: 1000 toymodel chirps per GPU x T=3141, dt=1e-3, chirp model d=4, sgp_filter + sgp_smoother with '
             'gauss_hermite(d=4, order=3) (81 points)')
 UNIT = 'steps/s'
-E2E_DEPTH = int(os.environ.get('CGP_E2E_DEPTH', '3'))            # batches in flight in the end-to-end leg (cg.filter_smoother_batches); profiles/r2_batches.txt
+E2E_DEPTH = int(os.environ.get('CGP_E2E_DEPTH', '8'))            # batches in flight in the end-to-end leg (cg.filter_smoother_batches); profiles/r2_batches.txt
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel: read from the committed ncu capture of
 # this very command (`ncu --set full`, raw page as CSV; see profiles/README.md), never a literal
@@ -480,13 +480,13 @@ def run_ours(args):
     # on alternating streams): the filter of batch i+1 (latency-bound, leaves most issue slots idle) overlaps the tail of batch
     # i's filter and its sweep.  All five outputs (mfs, Pfs, n_ell, mss, Pss) are produced on the device for every batch.
     # Reported as an extra key -- it is the device-resident counterpart of `e2e`; `value` stays the serial, L2-flushed figure.
-    n_pipe = max(3 * args.steps, 30)
+    n_pipe = max(3 * args.steps, 10 * E2E_DEPTH)
 
     def dev_sequence(n):
         for _ in cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, XI, m0, P0, DT,
                                             batches=(ys for _ in range(n)), depth=E2E_DEPTH):
             pass
-    dev_sequence(12)
+    dev_sequence(4 * E2E_DEPTH); dev_sequence(2 * E2E_DEPTH)   # warm-up: every stream's device pool gets allocated (cudaMalloc synchronises)
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
@@ -527,7 +527,7 @@ def run_ours(args):
     # distinct pinned input batches in rotation; every batch's measurements cross PCIe (read in place by its filter kernel) and
     # its 16 B/step readout comes back into pinned host memory; the clock stops when the last result has landed.
     hosts = [ys_host] + [torch.as_tensor(synthetic_inputs(rank + 1000 * k)).pin_memory() for k in (1, 2)]
-    n_seq = max(3 * args.steps, 30)
+    n_seq = max(3 * args.steps, 10 * E2E_DEPTH)
 
     def batch_sequence(n):
         last = None
@@ -536,7 +536,7 @@ def run_ours(args):
                                                depth=E2E_DEPTH):
             pass
         return last
-    batch_sequence(12); batch_sequence(12)      # warm-up: the per-stream device pools and the pinned result blocks get allocated
+    batch_sequence(4 * E2E_DEPTH); batch_sequence(4 * E2E_DEPTH)      # warm-up: the per-stream device pools and the pinned result blocks get allocated
     barrier()
     flush.fill_(1.)
     torch.cuda.synchronize(dev)
@@ -662,8 +662,12 @@ def run_ours(args):
                             "host ys, 3 distinct batches in rotation>, readout=('freq', 'v_var'), depth=%d) -- every batch: pinned host "
                             "ys in (read in place over PCIe by its filter kernel: the h2d bytes cross the bus inside the kernel), "
                             "posterior frequency estimate E[g(V_k)] (gaussian_expectation on the device) and marginal variance out into "
-                            "pinned host memory, 16 B/step (demos/ghfs_mle.py:87-89); batch k+1's filter kernel overlaps batch k's sweep, "
-                            "readout and D2H; timed from the first call to the last result on the host" % E2E_DEPTH},
+                            "pinned host memory, 16 B/step (demos/ghfs_mle.py:87-89); the batches in flight overlap on the device (kernels of "
+                            "different batches share the SMs, sweep / readout / D2H run under the next filters); the library is told "
+                            "how many batches are in flight (CgpProblem.in_flight) and runs gh_oct_filter_kernel (8 lanes per chirp) "
+                            "from 4000 chirps in flight; timed from the first call to the last result on the host" % E2E_DEPTH,
+                    'kernels_per_step': ['gh_oct_filter_kernel (sgp_filter + smoother records)', 'smoother_sweep_lane4_kernel',
+                                         'expect_softplus_kernel (freq readout)']},
             'e2e_blocking': {'value': n_steps_total / (ms_e2e_blk * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_blk,
                              'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_e2e,
                              'ms_per_step_wall_clock': ms_e2e_blk_wall, 'check_mean_frequency_hz': freq_mean,

@@ -25,7 +25,7 @@ class CgpProblem(C.Structure):
         ('model', C.c_int32), ('d', C.c_int32), ('num_harmonics', C.c_int32), ('n_sigma', C.c_int32),
         ('sigma_kind', C.c_int32), ('gh_order', C.c_int32),
         ('ys_repeat', C.c_int64),
-        ('h_unit_index', C.c_int32), ('reserved0', C.c_int32),
+        ('h_unit_index', C.c_int32), ('in_flight', C.c_int32),
         ('consts', C.c_void_p), ('consts_stride', C.c_int64),
         ('m0', C.c_void_p), ('m0_stride', C.c_int64),
         ('P0', C.c_void_p), ('P0_stride', C.c_int64),

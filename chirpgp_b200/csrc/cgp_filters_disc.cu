@@ -47,10 +47,14 @@ static int launch_sgp_one(const CgpProblem &p, const FilterIO &io, cudaStream_t 
 // 8-lanes-per-chirp Gauss-Hermite kernel (cgp_oct.cuh): batches from kOctMinB chirps; CGP_GH_OCT=0 / 1 forces it off / on
 // (tests, measurements).
 static const int64_t kOctMinB = 2000;     // measured (profiles/r2_oct_kernel.txt): pair +10 % at 2000 chirps, +34 % at 4000, +61 % at 32 000
+// A caller that keeps several batches in flight (filter_smoother_batches) says so in CgpProblem::in_flight: what counts then is
+// the throughput of the overlapping launches, and the 8-lane kernel issues 204 instead of 335 FP64 instructions per chirp and step
+// (profiles/r2_batches.txt: 1000 chirps per batch, 3 in flight: 3.00 vs 3.09 ms per batch; 4: 3.00 vs 2.57; 8: 3.00 vs 1.91).
+static const int64_t kOctMinInFlightChirps = 4000;
 static bool use_oct(const CgpProblem &p) {
     const char *v = getenv("CGP_GH_OCT");
     if (v && *v) return atoi(v) != 0;
-    return p.B >= kOctMinB;
+    return p.B >= kOctMinB || p.B * (int64_t)(p.in_flight > 1 ? p.in_flight : 1) >= kOctMinInFlightChirps;
 }
 static bool use_cub_duo(const CgpProblem &p) {
     return p.model == CGP_MODEL_LCD && (p.num_harmonics == 2 || p.num_harmonics == 3) && p.d == 2 * p.num_harmonics + 2 &&

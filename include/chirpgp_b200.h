@@ -77,7 +77,9 @@ typedef struct CgpProblem {
     int32_t h_unit_index;      /* hint: j if H is exactly the unit vector e_j; CGP_H_HARMONIC if H = sum_k e_(2k+1),
                                   k < num_harmonics (the measurement row of the harmonic chirp models); else -1.
                                   Results are identical with and without the hint                            */
-    int32_t reserved0;
+    int32_t in_flight;         /* hint: how many launches of this shape the caller keeps in flight on other streams (0 or 1:
+                                  this one has the GPU to itself).  Only steers the choice between kernels that agree to
+                                  rounding: with several batches in flight the GPU is throughput- rather than latency-bound   */
     const double *consts;  int64_t consts_stride;   /* model constants, see model ids          */
     const double *m0;      int64_t m0_stride;       /* [B|1, d]                                */
     const double *P0;      int64_t P0_stride;       /* [B|1, d, d] (symmetric)                 */

@@ -881,6 +881,33 @@ def test_filter_smoother_batches_match_blocking_calls():
         next(cg.filter_smoother_batches(cg.sgp_filter, *args, batches=batches))
 
 
+def test_filter_smoother_batches_in_flight_hint_switches_kernel():
+    """With >= 4000 chirps in flight (batch size x depth) the library is told so (CgpProblem.in_flight) and runs the 8-lanes-per-chirp
+    Gauss-Hermite kernel: results agree with the blocking calls (warp-pair kernel) to rounding, and bit for bit once the choice is
+    pinned by CGP_GH_OCT=0 -- i.e. the hint is the only thing that changed."""
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    dt, Xi = 1e-3, 0.1
+    batches = [np.ascontiguousarray(toymodels.synthetic_batch(520, 70, dt, Xi=Xi, seed=60 + k)[1]) for k in range(3)]
+    args = (mc, sg, H, Xi, m0, P0, dt)
+    want = [cg.sgp_filter_smoother(*args, ys) for ys in batches]
+    got = list(cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=batches, depth=8))
+    differs = False
+    for g, w in zip(got, want):
+        for a, b, (rt, at) in zip(g, w, ((1e-9, 1e-11),) * 2 + ((1e-11, 0.),) + ((1e-9, 1e-11),) * 2):
+            npt.assert_allclose(a, b, rtol=rt, atol=at)
+            differs = differs or not np.array_equal(a, b)
+    assert differs, 'the in-flight hint did not select the large-batch kernel'
+    os.environ['CGP_GH_OCT'] = '0'
+    try:
+        pinned = list(cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=batches, depth=8))
+    finally:
+        del os.environ['CGP_GH_OCT']
+    for g, w in zip(pinned, want):
+        for a, b in zip(g, w):
+            npt.assert_array_equal(a, b)
+
+
 def test_zero_copy_pinned_measurements():
     """sgp_filter_smoother on a PINNED host tensor lets the filter kernel read the measurements in place (no upload); results
     are bit-identical to the uploaded path, for ragged lengths around the 32-sample blocks the producer streams."""
