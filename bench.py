@@ -36,6 +36,7 @@ METRIC = 'smoothed chirp time-steps/sec (batch x T), GHF+GHS'
 WORKLOAD = ('configs[1]: 1000 toymodel chirps per GPU x T=3141, dt=1e-3, chirp model d=4, sgp_filter + sgp_smoother with '
             'gauss_hermite(d=4, order=3) (81 points)')
 UNIT = 'steps/s'
+N_DISTINCT = 6           # distinct input batches rotating through the batch-sequence legs (6 x 25 MB > L2)
 E2E_DEPTH = int(os.environ.get('CGP_E2E_DEPTH', '8'))            # batches in flight in the end-to-end leg (cg.filter_smoother_batches); profiles/r2_batches.txt
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel: read from the committed ncu capture of
@@ -481,10 +482,12 @@ def run_ours(args):
     # i's filter and its sweep.  All five outputs (mfs, Pfs, n_ell, mss, Pss) are produced on the device for every batch.
     # Reported as an extra key -- it is the device-resident counterpart of `e2e`; `value` stays the serial, L2-flushed figure.
     n_pipe = max(3 * args.steps, 10 * E2E_DEPTH)
+    more_inputs = [torch.as_tensor(synthetic_inputs(rank + 1000 * k)).pin_memory() for k in range(1, N_DISTINCT)]
+    dev_inputs = [ys] + [t.to(dev) for t in more_inputs]
 
     def dev_sequence(n):
         for _ in cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, XI, m0, P0, DT,
-                                            batches=(ys for _ in range(n)), depth=E2E_DEPTH):
+                                            batches=(dev_inputs[i % N_DISTINCT] for i in range(n)), depth=E2E_DEPTH):
             pass
     dev_sequence(4 * E2E_DEPTH); dev_sequence(2 * E2E_DEPTH)   # warm-up: every stream's device pool gets allocated (cudaMalloc synchronises)
     barrier()
@@ -523,16 +526,17 @@ def run_ours(args):
     ms_e2e_blk, ms_e2e_blk_wall, out_r = timed_calls(
         lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('freq', 'v_var')), n_e2e)
     # the same work as a SEQUENCE of batches through cg.filter_smoother_batches (E2E_DEPTH batches in flight on alternating
-    # streams inside the product): what a Monte-Carlo job does (tetralith/jobs/ghfs_mle.py:26-86: one call per run).  Three
-    # distinct pinned input batches in rotation; every batch's measurements cross PCIe (read in place by its filter kernel) and
-    # its 16 B/step readout comes back into pinned host memory; the clock stops when the last result has landed.
-    hosts = [ys_host] + [torch.as_tensor(synthetic_inputs(rank + 1000 * k)).pin_memory() for k in (1, 2)]
+    # streams inside the product): what a Monte-Carlo job does (tetralith/jobs/ghfs_mle.py:26-86: one call per run).  Distinct
+    # pinned input batches in rotation; every batch's measurements cross PCIe (read in place by its filter kernel) and
+    # its 16 B/step readout comes back into pinned host memory; the clock stops when the last result has landed.  N_DISTINCT
+    # input batches (150 MB > the 126 MB L2) rotate, and every batch writes 1.8 GB between two uses of the same input.
+    hosts = [ys_host] + more_inputs
     n_seq = max(3 * args.steps, 10 * E2E_DEPTH)
 
     def batch_sequence(n):
         last = None
         for last in cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, XI, m0, P0, DT,
-                                               batches=(hosts[i % 3] for i in range(n)), readout=('freq', 'v_var'),
+                                               batches=(hosts[i % N_DISTINCT] for i in range(n)), readout=('freq', 'v_var'),
                                                depth=E2E_DEPTH):
             pass
         return last
@@ -548,7 +552,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_seq
     ms_e2e = e0.elapsed_time(e1) / n_seq
-    del hosts[1:]
+    del hosts[1:], more_inputs, dev_inputs[1:]
     ms_e2e_full, ms_e2e_full_wall, _ = timed_calls(
         lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('mss', 'Pss')), n_e2e)
     ys_np = ys_host.numpy()
@@ -653,19 +657,19 @@ def run_ours(args):
             'value_batch_sequence': {'value': n_steps_total / (ms_pipe * 1e-3), 'unit': UNIT, 'ms_per_step': ms_pipe,
                                   'batches_in_flight': E2E_DEPTH, 'steps': n_pipe,
                                   'what': 'same passes, device-resident, as a sequence of batches through cg.filter_smoother_batches '
-                                          '(all five outputs on the device per batch; no L2 flush: 1.8 GB written per batch)'},
+                                          '(all five outputs on the device per batch; %d distinct input batches in rotation, 1.8 GB written per batch)' % N_DISTINCT},
             'e2e': {'value': n_steps_total / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_seq,
                     'ms_per_step_wall_clock': ms_e2e_wall, 'batches_in_flight': E2E_DEPTH,
                     'what': "a sequence of batches through the product's streaming call: for freq, v_var in "
                             "cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, Xi, m0, P0, dt, batches=<pinned "
-                            "host ys, 3 distinct batches in rotation>, readout=('freq', 'v_var'), depth=%d) -- every batch: pinned host "
+                            "host ys, %d distinct batches in rotation>, readout=('freq', 'v_var'), depth=%d) -- every batch: pinned host "
                             "ys in (read in place over PCIe by its filter kernel: the h2d bytes cross the bus inside the kernel), "
                             "posterior frequency estimate E[g(V_k)] (gaussian_expectation on the device) and marginal variance out into "
                             "pinned host memory, 16 B/step (demos/ghfs_mle.py:87-89); the batches in flight overlap on the device (kernels of "
                             "different batches share the SMs, sweep / readout / D2H run under the next filters); the library is told "
                             "how many batches are in flight (CgpProblem.in_flight) and runs gh_oct_filter_kernel (8 lanes per chirp) "
-                            "from 4000 chirps in flight; timed from the first call to the last result on the host" % E2E_DEPTH,
+                            "from 4000 chirps in flight; timed from the first call to the last result on the host" % (N_DISTINCT, E2E_DEPTH),
                     'kernels_per_step': ['gh_oct_filter_kernel (sgp_filter + smoother records)', 'smoother_sweep_lane4_kernel',
                                          'expect_softplus_kernel (freq readout)']},
             'e2e_blocking': {'value': n_steps_total / (ms_e2e_blk * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_blk,
