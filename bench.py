@@ -706,6 +706,15 @@ def run_ours(args):
                                'alone_cycles_per_step': 1448, 'frac': 840. / cyc,
                                'source': 'floor: dependent-issue latencies of profiles/microbench/fp64_latency.cu; alone: one '
                                          'chain warp per SM sub-partition, profiles/r2_chain_timeline_plain592.txt'},
+            # the batch-sequence legs run the 8-lane kernel with ~3 launches overlapping: no per-kernel time exists, so the whole
+            # per-batch time (filter + records + sweep of a batch) is charged against the filter's algorithmic flops -- a lower bound
+            'roofline_batch_sequence': {'bound': 'fp64', 'kernel': 'gh_oct_filter_kernel (+ smoother_sweep_lane4_kernel), %d batches in flight' % E2E_DEPTH,
+                                        'achieved': filt_flops / (ms_pipe * 1e-3) / 1e12, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                                        'frac': filt_flops / (ms_pipe * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                                        'ms_per_batch': ms_pipe, 'flops_per_step': flops_per_step('sgp_filter'),
+                                        'note': 'algorithmic flops of sgp_filter only over the whole per-batch time of the '
+                                                'device-resident sequence; ncu of the kernel alone at 10 000 chirps: FP64 pipe 61 % busy '
+                                                '(profiles/r2_oct_kernel.txt)'},
             'cpu_baseline': cpu,
             'jax': jax_note,
             'configs': other,

@@ -60,6 +60,16 @@ def test_no_cpu_fallback_and_no_oracle_import():
         _, _, mc, m0, P0, H = cg.build_chirp_model(np.array([0.1, 0.1, 0.1, 1., 1., 7.]))
         with pytest.raises(RuntimeError):
             cg.ekf(mc, H, 0.1, m0, P0, 1e-3, np.ones(4))
+        with pytest.raises(RuntimeError):         # the batch-sequence call has no CPU path either
+            next(cg.filter_smoother_batches(cg.ekf_smoother, mc, H, 0.1, m0, P0, 1e-3, batches=[np.ones(4)]))
+
+
+def test_filter_smoother_batches_argument_checks():
+    _, _, mc, m0, P0, H = cg.build_chirp_model(np.array([0.1, 0.1, 0.1, 1., 1., 7.]))
+    with pytest.raises(TypeError):                # only the four pair functions can be sequenced
+        next(cg.filter_smoother_batches(cg.ekf, mc, H, 0.1, m0, P0, 1e-3, batches=[np.ones(4)]))
+    with pytest.raises(ValueError):
+        next(cg.filter_smoother_batches(cg.ekf_smoother, mc, H, 0.1, m0, P0, 1e-3, batches=[np.ones(4)], depth=0))
 
 
 @pytest.mark.parametrize('ell,sigma,dt', [(0.1, 0.1, 0.1), (1., 1., 0.1), (0.5, 2., 0.01), (2.2, 0.3, 1.)])
