@@ -241,6 +241,24 @@ def run_other_configs(dev, fp64_peak, hbm_peak, with_cpu, flush):
             del f, sm
         return statistics.mean(tf), statistics.mean(ts)
 
+    def sequenced(pair, pargs, ys_dev, depth=8, n=24):
+        """ms per batch of the same pair as a device-resident batch sequence (cg.filter_smoother_batches, `depth` in flight)."""
+        def run(k):
+            for _ in cg.filter_smoother_batches(pair, *pargs, batches=(ys_dev for _ in range(k)), depth=depth):
+                pass
+        run(2 * depth)
+        torch.cuda.synchronize(dev)
+        e0, e1 = ev(), ev()
+        e0.record(); run(n); e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    def with_sequence(e, ms_seq, depth=8):
+        e['batch_sequence'] = {'value': e['value'] * (e['filter_ms'] + e['smoother_ms']) / ms_seq, 'unit': UNIT, 'ms_per_batch': ms_seq,
+                               'batches_in_flight': depth,
+                               'what': 'same pair, device-resident, as a sequence of batches through cg.filter_smoother_batches'}
+        return e
+
     def entry(config, what, B, d, n, variants, tf, ts, cpu):
         steps = B * T
         fl = sum(flops_per_step(v, d, n) for v in variants)
@@ -292,8 +310,9 @@ def run_other_configs(dev, fp64_peak, hbm_peak, with_cpu, flush):
     def cpu3a(n):
         f = orc.cd_ekf(spec, Bm, Ho, XI, m0o, P0o, DT, tile(n)[:n], nthreads=threads)
         orc.cd_eks(spec, Bm, f[0], f[1], DT, nthreads=threads)
-    out.append(entry(3, 'configs[2]: %d chirps x T=%d, cd_ekf + cd_eks (one RK4 step per sample)' % (B_PER_GPU, T), B_PER_GPU, 4,
-                     0, ('cd_ekf', 'cd_eks'), tf, ts, cpu_of(cpu3a, 128)))
+    out.append(with_sequence(entry(3, 'configs[2]: %d chirps x T=%d, cd_ekf + cd_eks (one RK4 step per sample)' % (B_PER_GPU, T),
+                                   B_PER_GPU, 4, 0, ('cd_ekf', 'cd_eks'), tf, ts, cpu_of(cpu3a, 128)),
+                             sequenced(cg.cd_ekf_smoother, (drift, disp, H, XI, m0, P0, DT), ysd)))
     bm = disp(None)
     tf, ts = timed(lambda: cg.cd_sgp_filter(drift, bm, sg, H, XI, m0, P0, DT, ysd),
                    lambda f: cg.cd_sgp_smoother(drift, bm, sg, f[0], f[1], DT))
@@ -301,8 +320,9 @@ def run_other_configs(dev, fp64_peak, hbm_peak, with_cpu, flush):
     def cpu3b(n):
         f = orc.cd_sgp_filter(spec, Bm, sg, Ho, XI, m0o, P0o, DT, tile(n)[:n], nthreads=threads)
         orc.cd_sgp_smoother(spec, Bm, sg, f[0], f[1], DT, nthreads=threads)
-    out.append(entry(3, 'configs[2]: %d chirps x T=%d, cd_sgp_filter + cd_sgp_smoother, gauss_hermite(4, 3)' % (B_PER_GPU, T),
-                     B_PER_GPU, 4, 81, ('cd_sgp_filter', 'cd_sgp_smoother'), tf, ts, cpu_of(cpu3b, 16)))
+    out.append(with_sequence(entry(3, 'configs[2]: %d chirps x T=%d, cd_sgp_filter + cd_sgp_smoother, gauss_hermite(4, 3)' % (B_PER_GPU, T),
+                                   B_PER_GPU, 4, 81, ('cd_sgp_filter', 'cd_sgp_smoother'), tf, ts, cpu_of(cpu3b, 16)),
+                             sequenced(cg.cd_sgp_filter_smoother, (drift, bm, sg, H, XI, m0, P0, DT), ysd, n=16)))
     # ---- config 4: harmonic model d = 8, cubature
     _, ys4, _ = toymodels.synthetic_batch(B_PER_GPU, T, DT, num_harmonics=3, seed=4)
     ys4d = torch.as_tensor(ys4).to(dev)
@@ -317,8 +337,10 @@ def run_other_configs(dev, fp64_peak, hbm_peak, with_cpu, flush):
         yy = ys4 if n <= ys4.shape[0] else np.tile(ys4, (-(-n // ys4.shape[0]), 1))
         f = orc.sgp_filter(spec4, sg4, Ho4, XI, m0o4, P0o4, DT, yy[:n], nthreads=threads)
         orc.sgp_smoother(spec4, sg4, f[0], f[1], DT, nthreads=threads)
-    out.append(entry(4, 'configs[3]: %d harmonic chirps (3 harmonics, d=8) x T=%d, sgp_filter + sgp_smoother, cubature(8)'
-                     % (B_PER_GPU, T), B_PER_GPU, 8, 16, ('sgp_filter', 'sgp_smoother'), tf, ts, cpu_of(cpu4, 32)))
+    out.append(with_sequence(entry(4, 'configs[3]: %d harmonic chirps (3 harmonics, d=8) x T=%d, sgp_filter + sgp_smoother, cubature(8)'
+                                   % (B_PER_GPU, T), B_PER_GPU, 8, 16, ('sgp_filter', 'sgp_smoother'), tf, ts, cpu_of(cpu4, 32)),
+                             sequenced(cg.sgp_filter_smoother, (mc4, sg4, H4, XI, m04, P04, DT), ys4d, depth=4, n=16), depth=4))
+    torch.cuda.empty_cache()
     # ---- config 2 at the batch size north_star names for the CPU comparison: 10 000 chirps (large-batch kernel, cgp_oct.cuh)
     del ysd, ys4d
     torch.cuda.empty_cache()
