@@ -200,7 +200,11 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * statistics.mean(secs), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': sample},
+        # the same `config` dict as the GPU arm prints (the driver compares them); what one timed CPU step covers is in `sample`
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B_PER_GPU, 'T': T,
+                   'parallelism': 'chirps sharded x%d, no collective' % int(os.environ.get('WORLD_SIZE', '1')),
+                   'l2': 'flushed between timed steps (256 MiB write)'},
+        'sample': sample,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'JAX not installable here: CPU arm = oracle/ C restatement of the reference algorithm (proxy)',
