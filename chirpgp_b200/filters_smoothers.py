@@ -606,6 +606,7 @@ def cd_sgp_filter_smoother(a, b, sgps, H, Xi, m0, P0, dt, ys, readout=None, orde
 
 
 _stream_cache = {}
+_batch_stats = {'oom_fallbacks': 0}      # how often a batch sequence had to lower its depth (tests, diagnostics)
 _in_flight = threading.local()           # .n = batches filter_smoother_batches keeps in flight (CgpProblem.in_flight hint)
 
 
@@ -635,7 +636,8 @@ def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int
     CPU tensors -- pinned ones are read in place by the filter kernel -- or CUDA tensors).  Yields, in order, exactly what
     ``pair(*model_args, ys, readout=readout, order=order)`` returns for each batch; a yielded result is complete (its stream
     has been waited for).  Host results live in pinned memory that torch's host allocator recycles once they are dropped.
-    Memory: ``depth`` batches' device buffers are alive at once (config 2: 1.8 GB each).  The library is told how many batches
+    Memory: ``depth`` batches' device buffers are alive at once (config 2: 1.8 GB each); if that does not fit, the sequence goes on
+    with as many batches in flight as did.  The library is told how many batches
     are in flight (``CgpProblem.in_flight``) and picks its kernels for the throughput of the overlapping launches rather than for
     the latency of one: from 4000 chirps in flight the Gauss--Hermite pair runs the 8-lanes-per-chirp kernel (results agree with
     the single-call kernels to rounding, not bit for bit).  Config 2 (1000 chirps per batch), host to host: depth 3: 3.4 ms per
@@ -653,19 +655,39 @@ def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int
     for st in streams:
         st.wait_event(ready)
     inflight = deque()                                    # (results, event, ys kept alive: a zero-copy input of the kernels)
+    limit = depth                                         # batches allowed in flight (lowered if the device runs out of memory)
     try:
         for k, ys in enumerate(batches):
             st = streams[k % depth]
-            _in_flight.n = depth
-            try:
-                with torch.cuda.stream(st):
-                    out = pair(*model_args, ys, readout=readout, order=order, _sync=False)
-                    done = torch.cuda.Event()
-                    done.record(st)
-            finally:
-                _in_flight.n = 0
+            for attempt in (0, 1):
+                oom = False
+                _in_flight.n = limit
+                try:
+                    with torch.cuda.stream(st):
+                        out = pair(*model_args, ys, readout=readout, order=order, _sync=False)
+                        done = torch.cuda.Event()
+                        done.record(st)
+                except torch.OutOfMemoryError:
+                    if attempt or not inflight:
+                        raise
+                    oom = True
+                finally:
+                    _in_flight.n = 0
+                if not oom:
+                    break
+                # `depth` batches of this size do not fit: hand out what is in flight, give the streams' pools back to the device
+                # and go on with as many batches in flight as did fit (outside the except clause: the traceback of the failed
+                # call keeps its partial allocations alive)
+                limit = max(1, len(inflight))
+                _batch_stats['oom_fallbacks'] += 1
+                while inflight:
+                    out0, done0, _ = inflight.popleft()
+                    done0.synchronize()
+                    yield out0
+                torch.cuda.synchronize(dev)
+                torch.cuda.empty_cache()
             inflight.append((out, done, ys))
-            if len(inflight) >= depth:
+            if len(inflight) >= limit:
                 out0, done0, _ = inflight.popleft()
                 done0.synchronize()
                 yield out0

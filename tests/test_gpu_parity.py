@@ -908,6 +908,35 @@ def test_filter_smoother_batches_in_flight_hint_switches_kernel():
             npt.assert_array_equal(a, b)
 
 
+def test_filter_smoother_batches_under_a_tight_memory_limit():
+    """`depth` batches' buffers do not fit under the allocator's limit: torch takes the blocks back from the other streams' pools
+    (and, failing that, the sequence lowers its depth -- filters_smoothers._batch_stats): same results, no exception."""
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    sg = cg.SigmaPoints.gauss_hermite(4, 3)
+    dt, Xi = 1e-3, 0.1
+    batches = [np.ascontiguousarray(toymodels.synthetic_batch(64, 3000, dt, Xi=Xi, seed=70 + k)[1]) for k in range(6)]
+    args = (mc, sg, H, Xi, m0, P0, dt)
+    want = [cg.sgp_filter_smoother(*args, ys, readout=('freq', 'n_ell_last')) for ys in batches]
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    _, total = torch.cuda.mem_get_info()
+    # one batch holds ~0.11 GB of device buffers (mfs, Pfs, mss, Pss, workspace): let torch's allocator have room for about
+    # three of them on top of what it holds now (the limit counts the allocator's reserved bytes only)
+    torch.cuda.set_per_process_memory_fraction(min(1., (torch.cuda.memory_reserved() + 0.36e9) / total))
+    from chirpgp_b200 import filters_smoothers as fs
+    before = fs._batch_stats['oom_fallbacks']
+    try:
+        got = list(cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=batches, readout=('freq', 'n_ell_last'), depth=6))
+    finally:
+        torch.cuda.set_per_process_memory_fraction(1.)
+        torch.cuda.empty_cache()
+    assert fs._batch_stats['oom_fallbacks'] >= before
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            npt.assert_array_equal(a, b)
+
+
 def test_zero_copy_pinned_measurements():
     """sgp_filter_smoother on a PINNED host tensor lets the filter kernel read the measurements in place (no upload); results
     are bit-identical to the uploaded path, for ragged lengths around the 32-sample blocks the producer streams."""
