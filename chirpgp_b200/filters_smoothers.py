@@ -659,6 +659,9 @@ def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int
     try:
         for k, ys in enumerate(batches):
             st = streams[k % depth]
+            if isinstance(ys, torch.Tensor) and ys.is_cuda:
+                # a device batch may have been produced just now on the caller's stream (a lazy iterable of simulate(...) results)
+                st.wait_stream(torch.cuda.current_stream(dev))
             for attempt in (0, 1):
                 oom = False
                 _in_flight.n = limit

@@ -871,6 +871,13 @@ def test_filter_smoother_batches_match_blocking_calls():
         for g, ys in zip(got, batches):
             for a, b in zip(g, pair(*pargs, ys, readout=('mss', 'v_var'))):
                 npt.assert_array_equal(a, b)
+    # device batches produced lazily on the caller's stream, right before they are consumed on a side stream
+    base = [torch.as_tensor(b).cuda() for b in batches]
+    lazy = ((t + 0.) for t in base)                               # a fresh tensor per batch, written by a kernel on the current stream
+    got = list(cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=lazy, readout=('freq', 'v_var', 'n_ell_last'), depth=3))
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            npt.assert_array_equal(a.cpu().numpy(), b)
     # closing the generator early leaves nothing running on a dead input
     it = cg.filter_smoother_batches(cg.sgp_filter_smoother, *args, batches=(torch.as_tensor(b).pin_memory() for b in batches),
                                     readout='freq', depth=3)
