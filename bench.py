@@ -553,7 +553,7 @@ def run_ours(args):
         lambda: cg.sgp_filter_smoother(m_and_cov, sgps, H, XI, m0, P0, DT, ys_host, readout=('freq', 'v_var')), n_e2e)
     # the same work as a SEQUENCE of batches through cg.filter_smoother_batches (E2E_DEPTH batches in flight on alternating
     # streams inside the product): what a Monte-Carlo job does (tetralith/jobs/ghfs_mle.py:26-86: one call per run).  Distinct
-    # pinned input batches in rotation; every batch's measurements cross PCIe (read in place by its filter kernel) and
+    # pinned input batches in rotation; every batch's measurements cross PCIe (asynchronous upload on the batch's stream) and
     # its 16 B/step readout comes back into pinned host memory; the clock stops when the last result has landed.  N_DISTINCT
     # input batches (150 MB > the 126 MB L2) rotate, and every batch writes 1.8 GB between two uses of the same input.
     hosts = [ys_host] + more_inputs
@@ -690,7 +690,7 @@ def run_ours(args):
                     'what': "a sequence of batches through the product's streaming call: for freq, v_var in "
                             "cg.filter_smoother_batches(cg.sgp_filter_smoother, m_and_cov, sgps, H, Xi, m0, P0, dt, batches=<pinned "
                             "host ys, %d distinct batches in rotation>, readout=('freq', 'v_var'), depth=%d) -- every batch: pinned host "
-                            "ys in (read in place over PCIe by its filter kernel: the h2d bytes cross the bus inside the kernel), "
+                            "ys uploaded on the batch's stream (asynchronous H2D copy inside the product call), "
                             "posterior frequency estimate E[g(V_k)] (gaussian_expectation on the device) and marginal variance out into "
                             "pinned host memory, 16 B/step (demos/ghfs_mle.py:87-89); the batches in flight overlap on the device (kernels of "
                             "different batches share the SMs, sweep / readout / D2H run under the next filters); the library is told "
@@ -702,7 +702,8 @@ def run_ours(args):
                              'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * 2, 'steps': n_e2e,
                              'ms_per_step_wall_clock': ms_e2e_blk_wall, 'check_mean_frequency_hz': freq_mean,
                              'what': "one blocking product call per step, nothing overlapped: cg.sgp_filter_smoother(m_and_cov, sgps, H, "
-                                     "Xi, m0, P0, dt, ys_host, readout=('freq', 'v_var'))"},
+                                     "Xi, m0, P0, dt, ys_host, readout=('freq', 'v_var')); the pinned host ys are read in place over PCIe "
+                                     "by the filter kernel (the h2d bytes cross the bus inside the kernel)"},
             'e2e_full_outputs': {'value': n_steps_total / (ms_e2e_full * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e_full,
                                  'h2d_bytes_per_step': B_PER_GPU * T * 8, 'd2h_bytes_per_step': B_PER_GPU * T * 8 * (D + D * D),
                                  'd2h_gb_per_s': B_PER_GPU * T * 8 * (D + D * D) / (ms_e2e_full * 1e-3) / 1e9,
