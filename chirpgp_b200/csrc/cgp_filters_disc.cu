@@ -5,7 +5,22 @@
 
 namespace cgp {
 
+// Below this many chirps one thread per chirp leaves the GPU to a handful of warps that each walk ~600 instructions per step;
+// 16 lanes per chirp (cgp_fast.cuh: ekf_lane_kernel) halve the instructions on the chain.  CGP_EKF_LANE=0 / 1 forces the choice
+// (tests, measurements).
+static const int64_t kEkfLaneMaxB = 2048;     // measured (profiles/r2_ekf_lane.txt): 2.45 -> 1.87 ms for one chirp, 3.35 -> 2.34 ms at 1000, 3.38 -> 4.12 ms at 4000
+static bool use_ekf_lane(const CgpProblem &p) {
+    if (!(p.model == CGP_MODEL_LCD && p.num_harmonics == 1 && p.d == 4)) return false;
+    const char *v = getenv("CGP_EKF_LANE");
+    if (v && *v) return atoi(v) != 0;
+    return p.B <= kEkfLaneMaxB;
+}
+
 int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
+    if (use_ekf_lane(p)) {
+        ekf_lane_kernel<1><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        return check_launch();
+    }
     return dispatch_disc(p, [&](auto tag) {
         using Model = typename decltype(tag)::type;
         const int block = 128;
