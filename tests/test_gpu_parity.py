@@ -20,7 +20,7 @@ import pytest
 import torch
 
 import chirpgp_b200 as cg
-from chirpgp_b200 import toymodels
+from chirpgp_b200 import mle, toymodels
 from oracle import oracle as orc
 from parity_tolerances import record, atol_long
 
@@ -942,6 +942,31 @@ def test_filter_smoother_batches_under_a_tight_memory_limit():
     for g, w in zip(got, want):
         for a, b in zip(g, w):
             npt.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('lane', ['0', '1'])
+def test_ekf_both_layouts_vs_oracle(lane):
+    """The discrete EKF has two kernels: one thread per chirp (large batches) and 16 lanes per chirp (up to 2048 chirps).  Both,
+    forced through CGP_EKF_LANE, against the oracle -- with a general measurement row (so that the lane kernel's butterfly sums of
+    the update add non-zero terms), an asymmetric-to-rounding P0, ragged lengths around its 16-step blocks, and the nll-only mode."""
+    drift, disp, mc, m0, P0, H, spec = _chirp_setup()
+    Hg = np.array([0.8, -0.3, 0.15, 0.05])
+    dt, Xi = 1e-3, 0.1
+    os.environ['CGP_EKF_LANE'] = lane
+    try:
+        for B, T in ((5, 1), (3, 15), (3, 16), (4, 17), (7, 700)):
+            _, ys, _ = toymodels.synthetic_batch(B, max(T, 2), dt, Xi=Xi, seed=80 + T)
+            ys = np.ascontiguousarray(ys[:, :T])
+            for Hm in (H, Hg):
+                f = cg.ekf(mc, Hm, Xi, m0, P0, dt, ys)
+                fo = orc.ekf(spec, Hm, Xi, m0, P0, dt, ys)
+                npt.assert_allclose(f[0], fo[0], rtol=1e-9, atol=1e-11)
+                npt.assert_allclose(f[1], fo[1], rtol=1e-9, atol=1e-11)
+                npt.assert_allclose(f[2], fo[2], rtol=1e-11, atol=1e-13)
+                last = mle.filter_nll('ekf', (mc,), Hm, Xi, m0, P0, dt, torch.as_tensor(ys).cuda())
+                npt.assert_allclose(last.cpu().numpy(), fo[2][:, -1], rtol=1e-11, atol=1e-13)
+    finally:
+        del os.environ['CGP_EKF_LANE']
 
 
 def test_zero_copy_pinned_measurements():
