@@ -1090,6 +1090,7 @@ __global__ void __launch_bounds__(32) smoother_sweep_lane4_kernel(const CgpProbl
         __syncwarp();
         const double *tw = my + buf * TILE;
         double *pP = Pss + (lo + n - 1) * DD, *pm = mss + (lo + n - 1) * D;
+        #pragma unroll 4
         for (int jj = n - 1; jj >= 0; jj--) {
             const double *Gm = tw + jj * R, *cv = Gm + DD;
             // rows i and j of the gain (each lane needs both)
