@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
 // rows i and j with selects; X = J P takes column j of P by shuffle, Pp = X J^T + Sigma takes row i of X by shuffle.  The
 // measurement update follows linear_update: S from the column sums H^T Pp, the gain from the row sums Pp H.  ~300 instructions per
 // step in the warp instead of ~600 in a single thread (a lone warp pays ~3 cycles per instruction it issues).
-template <int NH>
+template <int NH, bool H_E1>      // H_E1: H is exactly e_1 (CgpProblem::h_unit_index == 1) -- S, the gain and the prediction are entries, not sums
 __global__ void __launch_bounds__(32) ekf_lane_kernel(const CgpProblem p, const FilterIO io) {
     static_assert(NH == 1, "16 lanes per chirp need d == 4");
     using Model = ModelLCD<1>;
@@ -887,20 +887,29 @@ __global__ void __launch_bounds__(32) ekf_lane_kernel(const CgpProblem p, const 
             CGP_UNROLL for (int k = 1; k < D; k++) Pp = fma(hw.get(X, 4 * hw.i + k), jc[k], Pp);
             Pp += sg_ij;
             // ---- measurement update (filters_smoothers.py:55-68, linear_update): S = (H^T Pp) H + Xi, K = Pp H / S
-            double cc = hi * Pp;                                     // column sums over i
-            cc += __shfl_xor_sync(0xffffffffu, cc, 4);
-            cc += __shfl_xor_sync(0xffffffffu, cc, 8);
-            double cr = Pp * hj;                                     // row sums over j
-            cr += __shfl_xor_sync(0xffffffffu, cr, 1);
-            cr += __shfl_xor_sync(0xffffffffu, cr, 2);
-            double S = hw.get(cc, 0) * H[0];
-            CGP_UNROLL for (int q = 1; q < D; q++) S = fma(hw.get(cc, q), H[q], S);
-            S += Xi;
-            double c[D];
-            CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
-            const double cj = hw.get(cr, 4 * hw.j);
-            double pred = H[0] * mp[0];
-            CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], mp[q], pred);
+            double S, c[D], cr, cj, pred;
+            if constexpr (H_E1) {
+                // H = e_1: H^T Pp H = Pp_11, Pp H = column 1 of Pp, H mp = mp_1 (what the sums below give, adding exact zeros)
+                S = hw.get(Pp, 5) + Xi;
+                CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(Pp, 4 * q + 1);
+                cr = hw.get(Pp, 4 * hw.i + 1);
+                cj = hw.get(Pp, 4 * hw.j + 1);
+                pred = mp[1];
+            } else {
+                double cc = hi * Pp;                                 // column sums over i
+                cc += __shfl_xor_sync(0xffffffffu, cc, 4);
+                cc += __shfl_xor_sync(0xffffffffu, cc, 8);
+                cr = Pp * hj;                                        // row sums over j
+                cr += __shfl_xor_sync(0xffffffffu, cr, 1);
+                cr += __shfl_xor_sync(0xffffffffu, cr, 2);
+                S = hw.get(cc, 0) * H[0];
+                CGP_UNROLL for (int q = 1; q < D; q++) S = fma(hw.get(cc, q), H[q], S);
+                S += Xi;
+                CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
+                cj = hw.get(cr, 4 * hw.j);
+                pred = H[0] * mp[0];
+                CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], mp[q], pred);
+            }
             const double rS = fast_rcp(S), resid = yt - pred;
             CGP_UNROLL for (int q = 0; q < D; q++) m[q] = fma(c[q] * rS, resid, mp[q]);
             Pe = Pp - ((cr * rS) * (cj * rS)) * S;

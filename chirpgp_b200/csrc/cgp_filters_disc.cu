@@ -18,7 +18,8 @@ static bool use_ekf_lane(const CgpProblem &p) {
 
 int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     if (use_ekf_lane(p)) {
-        ekf_lane_kernel<1><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        if (p.h_unit_index == 1) ekf_lane_kernel<1, true><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        else ekf_lane_kernel<1, false><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
         return check_launch();
     }
     return dispatch_disc(p, [&](auto tag) {
