@@ -719,7 +719,7 @@ template <class Ode> CGP_DEV void rk4_step_lane(Ode &&ode, double (&m)[4], doubl
     Pe = Pe + dt * (aP + kP) * kSixth;
 }
 
-template <int NH>   // NH == 1: the chirp SDE (d = 4 -> 16 covariance entries -> half a warp)
+template <int NH, bool H_E1>   // NH == 1: the chirp SDE (d = 4 -> 16 covariance entries -> half a warp); H_E1: H is exactly e_1
 __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, const FilterIO io) {
     static_assert(NH == 1, "16 lanes per chirp need d == 4");
     using Model = ModelSDE<1>;
@@ -771,17 +771,26 @@ __global__ void __launch_bounds__(32) cd_ekf_lane_kernel(const CgpProblem p, con
                 dP = (Xt + X) + Qe;                                  // P J^T + J P + b b^T  (filters_smoothers.py:385)
             }, m, Pe, dt);
             // ---- measurement update (filters_smoothers.py:55-68): c = P h, S = h^T c + Xi
-            double cr = Pe * hj;                                     // row sums: c_i = sum_j P_ij h_j, in every lane of row i
-            cr += __shfl_xor_sync(0xffffffffu, cr, 1);
-            cr += __shfl_xor_sync(0xffffffffu, cr, 2);
-            double c[D];
-            CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
-            const double cj = hw.get(cr, 4 * hw.j);
-            double S = H[0] * c[0];
-            CGP_UNROLL for (int q = 1; q < D; q++) S = fma(H[q], c[q], S);
-            S += Xi;
-            double pred = H[0] * m[0];
-            CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], m[q], pred);
+            double cr, cj, c[D], S, pred;
+            if constexpr (H_E1) {
+                // H = e_1: P h = column 1 of P, h^T P h = P_11, h^T m = m_1 (what the sums below give, adding exact zeros)
+                CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(Pe, 4 * q + 1);
+                cr = hw.get(Pe, 4 * hw.i + 1);
+                cj = hw.get(Pe, 4 * hw.j + 1);
+                S = c[1] + Xi;
+                pred = m[1];
+            } else {
+                cr = Pe * hj;                                        // row sums: c_i = sum_j P_ij h_j, in every lane of row i
+                cr += __shfl_xor_sync(0xffffffffu, cr, 1);
+                cr += __shfl_xor_sync(0xffffffffu, cr, 2);
+                CGP_UNROLL for (int q = 0; q < D; q++) c[q] = hw.get(cr, 4 * q);
+                cj = hw.get(cr, 4 * hw.j);
+                S = H[0] * c[0];
+                CGP_UNROLL for (int q = 1; q < D; q++) S = fma(H[q], c[q], S);
+                S += Xi;
+                pred = H[0] * m[0];
+                CGP_UNROLL for (int q = 1; q < D; q++) pred = fma(H[q], m[q], pred);
+            }
             const double rS = fast_rcp(S), resid = yt - pred;
             CGP_UNROLL for (int q = 0; q < D; q++) m[q] = fma(c[q] * rS, resid, m[q]);
             Pe = fma(-((cr * rS) * (cj * rS)), S, Pe);               // P - K K^T S, K = c / S

@@ -9,7 +9,8 @@ static const int64_t kLaneKernelMaxB = 40000;
 
 int launch_cd_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
     if (p.model == CGP_MODEL_SDE && p.num_harmonics == 1 && p.d == 4 && p.B <= kLaneKernelMaxB) {
-        cd_ekf_lane_kernel<1><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        if (p.h_unit_index == 1) cd_ekf_lane_kernel<1, true><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
+        else cd_ekf_lane_kernel<1, false><<<(unsigned)ceil_div(p.B, 2), 32, 0, s>>>(p, io);
         return check_launch();
     }
     return dispatch_sde(p, [&](auto tag) {
