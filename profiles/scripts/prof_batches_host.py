@@ -1,5 +1,5 @@
 import os, sys, time, cProfile, pstats
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
 os.environ['CGP_GH_OCT'] = '1'
 import numpy as np, torch
 import chirpgp_b200 as cg
