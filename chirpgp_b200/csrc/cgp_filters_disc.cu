@@ -13,7 +13,7 @@ static bool use_ekf_lane(const CgpProblem &p) {
     if (!(p.model == CGP_MODEL_LCD && p.num_harmonics == 1 && p.d == 4)) return false;
     const char *v = getenv("CGP_EKF_LANE");
     if (v && *v) return atoi(v) != 0;
-    return p.B <= kEkfLaneMaxB;
+    return p.B * (int64_t)(p.in_flight > 1 ? p.in_flight : 1) <= kEkfLaneMaxB;     // chirps in flight over all overlapping launches
 }
 
 int launch_ekf(const CgpProblem &p, const FilterIO &io, cudaStream_t s) {
