@@ -622,6 +622,26 @@ def _batch_streams(dev, depth):
     return have[:depth]
 
 
+_PINNED_SEED_MAX_BYTES = 1 << 30
+
+
+def _seed_pinned_pool(outs, n):
+    """Host results of a batch sequence come from torch's caching host allocator, which hands a freed block out again only once
+    an event recorded at free time -- behind everything queued on the batch's stream by then, i.e. up to `depth` later batches --
+    has completed.  A steady sequence therefore cycles through ~2 x depth blocks per result; left to grow on demand, the pool takes
+    a cudaHostAlloc (~14 ms, synchronising) whenever timing jitter leaves no completed block.  Allocating the blocks up front and
+    dropping them (never used on a stream: immediately reusable) moves that cost to the start of the sequence."""
+    shapes = [tuple(o.shape) for o in outs if isinstance(o, np.ndarray) or (isinstance(o, torch.Tensor) and not o.is_cuda)]
+    total = sum(8 * int(np.prod(sh)) for sh in shapes) * n
+    if not shapes or total > _PINNED_SEED_MAX_BYTES or min(8 * int(np.prod(sh)) for sh in shapes) < _PINNED_MIN_BYTES:
+        return
+    try:
+        spare = [torch.empty(sh, dtype=_F64, pin_memory=True) for sh in shapes for _ in range(n)]
+        del spare
+    except RuntimeError:
+        pass                              # no pinned memory to spare: the pool grows on demand as before
+
+
 def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int = 10, depth: int = 4):
     """Run one of the filter + smoother pairs over a SEQUENCE of measurement batches with ``depth`` batches in flight
     (extension).  The Monte-Carlo jobs of the reference call the pair once per run in a Python loop
@@ -692,6 +712,8 @@ def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int
                     yield out0
                 torch.cuda.synchronize(dev)
                 torch.cuda.empty_cache()
+            if k == 0:
+                _seed_pinned_pool(out, 2 * depth + 2)
             inflight.append((out, done, ys))
             if len(inflight) >= limit:
                 out0, done0, _ = inflight.popleft()
