@@ -632,8 +632,9 @@ def _seed_pinned_pool(outs, n):
     a cudaHostAlloc (~14 ms, synchronising) whenever timing jitter leaves no completed block.  Allocating the blocks up front and
     dropping them (never used on a stream: immediately reusable) moves that cost to the start of the sequence."""
     shapes = [tuple(o.shape) for o in outs if isinstance(o, np.ndarray) or (isinstance(o, torch.Tensor) and not o.is_cuda)]
+    shapes = [sh for sh in shapes if 8 * int(np.prod(sh)) >= _PINNED_MIN_BYTES]          # small results: nothing to gain
     total = sum(8 * int(np.prod(sh)) for sh in shapes) * n
-    if not shapes or total > _PINNED_SEED_MAX_BYTES or min(8 * int(np.prod(sh)) for sh in shapes) < _PINNED_MIN_BYTES:
+    if not shapes or total > _PINNED_SEED_MAX_BYTES:
         return
     try:
         spare = [torch.empty(sh, dtype=_F64, pin_memory=True) for sh in shapes for _ in range(n)]
