@@ -665,7 +665,7 @@ def filter_smoother_batches(pair, *model_args, batches, readout=None, order: int
     are in flight (``CgpProblem.in_flight``) and picks its kernels for the throughput of the overlapping launches rather than for
     the latency of one: from 4000 chirps in flight the Gauss--Hermite pair runs the 8-lanes-per-chirp kernel (results agree with
     the single-call kernels to rounding, not bit for bit).  Config 2 (1000 chirps per batch), host to host: depth 3: 3.4 ms per
-    batch, depth 4 (the default): 3.0 ms, depth 8: 2.4 ms (one blocking call: 5.3 ms)."""
+    batch, depth 4 (the default): 3.0 ms, depth 8: 2.3 ms (one blocking call: 5.2 ms)."""
     if pair not in (sgp_filter_smoother, ekf_smoother, cd_ekf_smoother, cd_sgp_filter_smoother):
         raise TypeError('filter_smoother_batches: `pair` must be one of the *_smoother pair functions of chirpgp_b200')
     depth = int(depth)
